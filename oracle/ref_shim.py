@@ -1,0 +1,452 @@
+"""TEST INFRASTRUCTURE — not product code.  Only tests/, gen_golden.py and bench
+tooling may import this module; nothing under articulation3d_b200/ does.
+
+Import the UNMODIFIED reference temporal optimizer from /root/reference on a
+CPU-only box.  Nothing from the reference is copied: this
+module only (1) stubs the third-party packages that are not installed and that
+the hot path never executes (imageio, pycocotools, mapbox_earcut, quaternion,
+fvcore, skimage, matplotlib, seaborn, qutip and the unused corners of
+detectron2 / pytorch3d), (2) provides small real stand-ins for the handful of
+third-party functions the path DOES execute
+
+    detectron2.structures.{Boxes, Instances, pairwise_iou}
+        call sites: articulation3d/utils/opt_utils.py:406,540,646,668,1168,1180
+    pytorch3d.transforms.{Transform3d, Translate, Rotate, axis_angle_to_matrix}
+        call sites: articulation3d/utils/opt_utils.py:420-435,554-574,726-728,865-867
+
+    [3P-unverified] these stand-ins restate the published behaviour of
+    pytorch3d 0.7 / detectron2 0.6 (pinned in the reference README:26,41) from
+    the library documentation; the library sources are not in /root/reference.
+
+(3) turns ``Tensor.cuda`` into the identity, and (4) rebinds
+``opt_utils.project2D`` to a CPU statement of its own CUDA branch
+(articulation3d/utils/vis.py:71-75), which is the only branch that accepts a
+torch tensor.
+
+This only works where /root/reference exists (the build container).  The GPU
+box has no reference; tests there use the committed fixtures in tests/golden/.
+"""
+from __future__ import annotations
+
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+REFERENCE_ROOT = os.environ.get("A3D_REFERENCE_ROOT", "/root/reference/articulation3d")
+
+_STUB_ROOTS = (
+    "imageio", "pycocotools", "pytorch3d", "detectron2", "mapbox_earcut",
+    "quaternion", "fvcore", "skimage", "matplotlib", "seaborn", "qutip",
+    "plotly", "yacs", "iopath",
+)
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "articulation3d", "utils"))
+
+
+# --------------------------------------------------------------------------
+# permissive stubs for everything the hot path never executes
+# --------------------------------------------------------------------------
+class _StubMeta(type):
+    def __getattr__(cls, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _make_stub(f"{cls.__name__}.{name}")
+
+    def __iter__(cls):
+        return iter(())
+
+    def __len__(cls):
+        return 0
+
+    def __getitem__(cls, item):
+        return _make_stub(f"{cls.__name__}[]")
+
+    def __call__(cls, *a, **k):
+        if cls.__dict__.get("_a3d_is_stub_base", False):
+            return _make_stub(cls.__name__ + "()")
+        return super().__call__(*a, **k)
+
+
+def _make_stub(name: str):
+    return _StubMeta(name, (), {"_a3d_is_stub_base": True,
+                                "__init__": lambda self, *a, **k: None})
+
+
+class _StubModule(types.ModuleType):
+    __path__: list = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        full = f"{self.__name__}.{name}"
+        if full in sys.modules:
+            return sys.modules[full]
+        obj = _make_stub(name)
+        setattr(self, name, obj)
+        return obj
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] in _STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _StubModule(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+# --------------------------------------------------------------------------
+# detectron2.structures stand-ins  [3P-unverified]
+# --------------------------------------------------------------------------
+class Boxes:
+    def __init__(self, tensor):
+        device = tensor.device if isinstance(tensor, torch.Tensor) else torch.device("cpu")
+        tensor = torch.as_tensor(tensor, dtype=torch.float32, device=device)
+        if tensor.numel() == 0:
+            tensor = tensor.reshape((-1, 4)).to(dtype=torch.float32)
+        assert tensor.dim() == 2 and tensor.size(-1) == 4, tensor.size()
+        self.tensor = tensor
+
+    def area(self):
+        box = self.tensor
+        return (box[:, 2] - box[:, 0]) * (box[:, 3] - box[:, 1])
+
+    def get_centers(self):
+        return (self.tensor[:, :2] + self.tensor[:, 2:]) / 2
+
+    def __getitem__(self, item):
+        if isinstance(item, int):
+            return Boxes(self.tensor[item].view(1, -1))
+        b = self.tensor[item]
+        assert b.dim() == 2
+        return Boxes(b)
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+
+def pairwise_iou(boxes1: Boxes, boxes2: Boxes) -> torch.Tensor:
+    area1, area2 = boxes1.area(), boxes2.area()
+    b1, b2 = boxes1.tensor, boxes2.tensor
+    wh = torch.min(b1[:, None, 2:], b2[:, 2:]) - torch.max(b1[:, None, :2], b2[:, :2])
+    wh.clamp_(min=0)
+    inter = wh.prod(dim=2)
+    return torch.where(inter > 0, inter / (area1[:, None] + area2 - inter),
+                       torch.zeros(1, dtype=inter.dtype, device=inter.device))
+
+
+class Instances:
+    def __init__(self, image_size, **kwargs):
+        object.__setattr__(self, "_image_size", image_size)
+        object.__setattr__(self, "_fields", {})
+        for k, v in kwargs.items():
+            self.set(k, v)
+
+    @property
+    def image_size(self):
+        return self._image_size
+
+    def __setattr__(self, name, val):
+        if name.startswith("_"):
+            object.__setattr__(self, name, val)
+        else:
+            self.set(name, val)
+
+    def __getattr__(self, name):
+        if name == "_fields" or name not in self._fields:
+            raise AttributeError(f"Cannot find field '{name}' in the given Instances!")
+        return self._fields[name]
+
+    def set(self, name, value):
+        data_len = len(value)
+        if len(self._fields):
+            assert len(self) == data_len, f"field {name}: {data_len} vs {len(self)}"
+        self._fields[name] = value
+
+    def has(self, name):
+        return name in self._fields
+
+    def get_fields(self):
+        return self._fields
+
+    def __len__(self):
+        for v in self._fields.values():
+            return v.__len__()
+        raise NotImplementedError("Empty Instances does not support __len__!")
+
+
+# --------------------------------------------------------------------------
+# pytorch3d.transforms stand-ins  [3P-unverified]
+# --------------------------------------------------------------------------
+def _broadcast_bmm(a, b):
+    if a.dim() == 2:
+        a = a[None]
+    if len(a) != len(b):
+        if not ((len(a) == 1) or (len(b) == 1)):
+            raise ValueError("Expected batch dim for bmm to be equal or 1")
+        if len(a) == 1:
+            a = a.expand(len(b), -1, -1)
+        if len(b) == 1:
+            b = b.expand(len(a), -1, -1)
+    return a.bmm(b)
+
+
+class Transform3d:
+    def __init__(self, dtype=torch.float32, device="cpu", matrix=None):
+        if matrix is None:
+            self._matrix = torch.eye(4, dtype=dtype, device=device).view(1, 4, 4)
+        else:
+            self._matrix = matrix.view(-1, 4, 4)
+        self._transforms = []
+        self.device = device
+        self.dtype = dtype
+
+    def __len__(self):
+        return self.get_matrix().shape[0]
+
+    def compose(self, *others):
+        out = Transform3d(dtype=self.dtype, device=self.device)
+        out._matrix = self._matrix.clone()
+        out._transforms = self._transforms + list(others)
+        return out
+
+    def get_matrix(self):
+        composed = self._matrix.clone()
+        for other in self._transforms:
+            composed = _broadcast_bmm(composed, other.get_matrix())
+        return composed
+
+    def _get_matrix_inverse(self):
+        return torch.inverse(self._matrix)
+
+    def inverse(self, invert_composed=False):
+        tinv = Transform3d(dtype=self.dtype, device=self.device)
+        if invert_composed:
+            tinv._matrix = torch.inverse(self.get_matrix())
+        else:
+            i_matrix = self._get_matrix_inverse()
+            if len(self._transforms) > 0:
+                tinv._transforms = [t.inverse() for t in reversed(self._transforms)]
+                last = Transform3d(dtype=self.dtype, device=self.device)
+                last._matrix = i_matrix
+                tinv._transforms.append(last)
+            else:
+                tinv._matrix = i_matrix
+        return tinv
+
+    def transform_points(self, points, eps=None):
+        points_batch = points.clone()
+        if points_batch.dim() == 2:
+            points_batch = points_batch[None]
+        N, P, _3 = points_batch.shape
+        ones = torch.ones(N, P, 1, dtype=points.dtype, device=points.device)
+        points_batch = torch.cat([points_batch, ones], dim=2)
+        composed = self.get_matrix()
+        points_out = _broadcast_bmm(points_batch, composed)
+        denom = points_out[..., 3:]
+        if eps is not None:
+            denom_sign = denom.sign() + (denom == 0.0).type_as(denom)
+            denom = denom_sign * torch.clamp(denom.abs(), eps)
+        points_out = points_out[..., :3] / denom
+        if points_out.shape[0] == 1 and points.dim() == 2:
+            points_out = points_out.reshape(points.shape)
+        return points_out
+
+    def transform_normals(self, normals):
+        composed = self.get_matrix()
+        mat = composed[:, :3, :3]
+        normals_out = _broadcast_bmm(normals, mat.transpose(1, 2).inverse())
+        if normals_out.shape[0] == 1 and normals.dim() == 2:
+            normals_out = normals_out.reshape(normals.shape)
+        return normals_out
+
+    def translate(self, *args, **kwargs):
+        return self.compose(Translate(*args, device=self.device, dtype=self.dtype, **kwargs))
+
+    def rotate(self, *args, **kwargs):
+        return self.compose(Rotate(*args, device=self.device, dtype=self.dtype, **kwargs))
+
+    def to(self, *a, **k):
+        return self
+
+    def cuda(self):
+        return self
+
+    def cpu(self):
+        return self
+
+
+def _handle_coord(c, dtype, device):
+    if not torch.is_tensor(c):
+        c = torch.tensor(c, dtype=dtype, device=device)
+    if c.dim() == 0:
+        c = c.view(1)
+    if c.device != torch.device(device) or c.dtype != dtype:
+        c = c.to(device=device, dtype=dtype)
+    return c
+
+
+def _handle_input(x, y, z, dtype, device, name):
+    if torch.is_tensor(x) and x.dim() == 2:
+        if x.shape[1] != 3:
+            raise ValueError(f"Expected tensor of shape (N, 3); got {x.shape} (in {name})")
+        if y is not None or z is not None:
+            raise ValueError(f"Expected y and z to be None (in {name})")
+        return x.to(device=device, dtype=dtype)
+    xyz = [_handle_coord(c, dtype, device) for c in [x, y, z]]
+    sizes = [c.shape[0] for c in xyz]
+    N = max(sizes)
+    for c in xyz:
+        if c.shape[0] != 1 and c.shape[0] != N:
+            raise ValueError(f"Got non-broadcastable sizes {sizes} (in {name})")
+    xyz = [c.expand(N) for c in xyz]
+    return torch.stack(xyz, dim=1)
+
+
+class Translate(Transform3d):
+    def __init__(self, x, y=None, z=None, dtype=torch.float32, device=None):
+        device = "cpu" if device is None else device
+        xyz = _handle_input(x, y, z, dtype, device, "Translate")
+        super().__init__(device=device, dtype=dtype)
+        N = xyz.shape[0]
+        mat = torch.eye(4, dtype=dtype, device=device).view(1, 4, 4).repeat(N, 1, 1)
+        mat[:, 3, :3] = xyz
+        self._matrix = mat
+
+    def _get_matrix_inverse(self):
+        inv_mask = self._matrix.new_ones([1, 4, 4])
+        inv_mask[0, 3, :3] = -1.0
+        return self._matrix * inv_mask
+
+
+class Rotate(Transform3d):
+    def __init__(self, R, dtype=torch.float32, device=None, orthogonal_tol=1e-5):
+        device = "cpu" if device is None else device
+        super().__init__(device=device, dtype=dtype)
+        if R.dim() == 2:
+            R = R[None]
+        if R.shape[-2:] != (3, 3):
+            raise ValueError(f"R must have shape (3, 3) or (N, 3, 3); got {R.shape}")
+        R = R.to(device=device, dtype=dtype)
+        RRt = R @ R.transpose(1, 2)
+        if not torch.allclose(RRt, torch.eye(3, dtype=dtype).expand_as(RRt), atol=orthogonal_tol):
+            warnings.warn("R is not a valid rotation matrix")
+        N = R.shape[0]
+        mat = torch.eye(4, dtype=dtype, device=device).view(1, 4, 4).repeat(N, 1, 1)
+        mat[:, :3, :3] = R
+        self._matrix = mat
+
+    def _get_matrix_inverse(self):
+        return self._matrix.permute(0, 2, 1).contiguous()
+
+
+def axis_angle_to_quaternion(axis_angle):
+    angles = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
+    half_angles = angles * 0.5
+    eps = 1e-6
+    small_angles = angles.abs() < eps
+    sin_half_angles_over_angles = torch.empty_like(angles)
+    sin_half_angles_over_angles[~small_angles] = (
+        torch.sin(half_angles[~small_angles]) / angles[~small_angles])
+    sin_half_angles_over_angles[small_angles] = (
+        0.5 - (angles[small_angles] * angles[small_angles]) / 48)
+    return torch.cat([torch.cos(half_angles), axis_angle * sin_half_angles_over_angles], dim=-1)
+
+
+def quaternion_to_matrix(quaternions):
+    r, i, j, k = torch.unbind(quaternions, -1)
+    two_s = 2.0 / (quaternions * quaternions).sum(-1)
+    o = torch.stack(
+        (
+            1 - two_s * (j * j + k * k),
+            two_s * (i * j - k * r),
+            two_s * (i * k + j * r),
+            two_s * (i * j + k * r),
+            1 - two_s * (i * i + k * k),
+            two_s * (j * k - i * r),
+            two_s * (i * k - j * r),
+            two_s * (j * k + i * r),
+            1 - two_s * (i * i + j * j),
+        ),
+        -1,
+    )
+    return o.reshape(quaternions.shape[:-1] + (3, 3))
+
+
+def axis_angle_to_matrix(axis_angle):
+    return quaternion_to_matrix(axis_angle_to_quaternion(axis_angle))
+
+
+# --------------------------------------------------------------------------
+# installation
+# --------------------------------------------------------------------------
+_installed = None
+
+
+def _project2D_cpu(pcd, h=480, w=640, focal_length=517.97):
+    """CPU statement of the reference's CUDA branch, vis.py:64-75 (same ops,
+    same dtypes, no .cuda())."""
+    K = [[focal_length, 0, w / 2], [0, focal_length, h / 2], [0, 0, 1]]
+    K = torch.FloatTensor(K)
+    proj = (K @ (pcd.T)).T
+    proj = proj[:, :2] / proj[:, 2][:, None]
+    return proj
+
+
+def load_reference():
+    """Returns the reference's ``articulation3d.utils.opt_utils`` module,
+    imported unmodified from REFERENCE_ROOT under the shims above."""
+    global _installed
+    if _installed is not None:
+        return _installed
+    if not available():
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+
+    sys.meta_path.insert(0, _StubFinder())
+
+    def _real(name, **attrs):
+        m = _StubModule(name)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    _real("detectron2")
+    _real("detectron2.structures", Boxes=Boxes, Instances=Instances, pairwise_iou=pairwise_iou)
+    _real("detectron2.structures.boxes", Boxes=Boxes, pairwise_iou=pairwise_iou)
+    sys.modules["detectron2"].structures = sys.modules["detectron2.structures"]
+    sys.modules["detectron2.structures"].boxes = sys.modules["detectron2.structures.boxes"]
+    _real("pytorch3d")
+    _real("pytorch3d.transforms", Transform3d=Transform3d, Translate=Translate, Rotate=Rotate,
+          axis_angle_to_matrix=axis_angle_to_matrix, quaternion_to_matrix=quaternion_to_matrix,
+          axis_angle_to_quaternion=axis_angle_to_quaternion)
+    sys.modules["pytorch3d"].transforms = sys.modules["pytorch3d.transforms"]
+
+    # Device transfers on a CPU-only box: ``.cuda()`` is the identity, and
+    # ``.cpu()`` must then COPY (a real D2H transfer never aliases; without this
+    # the in-place sign flips at opt_utils.py:617-620 would accumulate on the
+    # shared ``normal_trans`` rows).
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.cpu = lambda self, *a, **k: self.clone()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import importlib
+    opt_utils = importlib.import_module("articulation3d.utils.opt_utils")
+    opt_utils.project2D = _project2D_cpu
+    _installed = opt_utils
+    return opt_utils
