@@ -1,0 +1,93 @@
+"""ctypes binding of the C ABI in include/a3d.h (csrc/liba3d.so).
+
+There is NO fallback: if the shared library is missing or a call fails, this
+module raises.  Build the library with ``python -c "import __graft_entry__ as g;
+g.build()"`` (or ``python -m articulation3d_b200.build``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liba3d.so")
+
+A3D_F32, A3D_U8 = 0, 1
+MODE_SEQ, MODE_COMPOSED, MODE_TRANSLATE = 0, 1, 2
+
+
+class Camera(C.Structure):
+    """a3d_camera_t"""
+    _fields_ = [("kinv", C.c_double * 9), ("f", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("H", C.c_int32), ("W", C.c_int32)]
+
+
+# a3d_job_t as a numpy structured dtype (64 bytes, C layout)
+JOB_DTYPE = np.dtype([
+    ("src_mask", "<i4"), ("mode", "<i4"), ("cand_begin", "<i4"), ("n_cand", "<i4"),
+    ("tgt_begin", "<i4"), ("n_tgt", "<i4"),
+    ("normal", "<f4", (3,)), ("offset", "<f4"),
+    ("pivot", "<f4", (3,)), ("pad0", "<f4"),
+    ("tab_begin", "<i8"),
+], align=True)
+assert JOB_DTYPE.itemsize == 64, JOB_DTYPE.itemsize
+
+# every symbol include/a3d.h declares
+EXPORTS = (
+    "a3d_version", "a3d_last_error_string", "a3d_pitch_words", "a3d_project_max_tile",
+    "a3d_pack_masks", "a3d_mask_meta", "a3d_project", "a3d_score", "a3d_emit_masks",
+)
+
+_lib = None
+
+
+class A3DError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen liba3d.so and declare the prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise A3DError(
+            f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "articulation3d_b200 has no CPU fallback for the hot path.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    lib.a3d_version.restype = C.c_int
+    lib.a3d_version.argtypes = []
+    lib.a3d_last_error_string.restype = C.c_char_p
+    lib.a3d_last_error_string.argtypes = []
+    lib.a3d_pitch_words.restype = C.c_int
+    lib.a3d_pitch_words.argtypes = [i32]
+    lib.a3d_project_max_tile.restype = C.c_int
+    lib.a3d_project_max_tile.argtypes = [i32, i32]
+    lib.a3d_pack_masks.restype = C.c_int
+    lib.a3d_pack_masks.argtypes = [vp, i32, i64, i32, i32, f32, vp, vp, vp]
+    lib.a3d_mask_meta.restype = C.c_int
+    lib.a3d_mask_meta.argtypes = [vp, i64, i32, i32, vp, vp, vp]
+    lib.a3d_project.restype = C.c_int
+    lib.a3d_project.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.a3d_score.restype = C.c_int
+    lib.a3d_score.argtypes = [i32, i32, vp, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                              vp, vp, vp, vp, vp]
+    lib.a3d_emit_masks.restype = C.c_int
+    lib.a3d_emit_masks.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc < 0:
+        msg = load().a3d_last_error_string().decode("utf-8", "replace")
+        raise A3DError(f"{what} failed ({rc}): {msg}")
+    return rc
+
+
+def pitch_words(W: int) -> int:
+    """Pure-python twin of a3d_pitch_words (ceil(W/32) rounded up to 4 words)."""
+    return (((W + 31) >> 5) + 3) & ~3

@@ -1,0 +1,645 @@
+// a3d.cu — sm_100a kernels + C ABI (include/a3d.h) of the temporal articulation
+// optimizer hot path.  See DESIGN.md for the data layout and per-kernel roofline.
+//
+// Arithmetic contract (bit-exactness against oracle/): every floating point
+// operation that decides a pixel index is written with explicit round-to-nearest
+// intrinsics (__fmul_rn/__fadd_rn/__fdiv_rn, __dmul_rn/__dadd_rn/__ddiv_rn) in the
+// exact left-to-right order of the reference's matrix products, so nvcc can never
+// contract them into FMAs (SURVEY.md §7 hard part 2).  The TU is additionally
+// built with -fmad=false.
+#include "a3d.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define A3D_CUDA_TRY(expr)                                                              \
+    do {                                                                                \
+        cudaError_t e__ = (expr);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return fail(A3D_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                            \
+    } while (0)
+
+struct Cam {
+    double k[9];
+    float f, cx, cy;
+    int H, W, pitch;
+    int sparse;   // kinv has the [[a,0,b],[0,c,d],[0,0,1]] pattern
+};
+
+__host__ __device__ inline int pitch_words(int W) { return (((W + 31) >> 5) + 3) & ~3; }
+
+// ---------------------------------------------------------------------------
+// pack: dense (n,H,W) -> bits.  One warp per image row, 32 pixels per ballot.
+// Pure streaming: 4 B (fp32) or 1 B (u8) read per pixel, 1/8 B written.
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack(const T* __restrict__ src, int64_t n_rows, int W,
+                                              int pitch, float thresh, uint32_t* __restrict__ gt,
+                                              uint32_t* __restrict__ nz) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int wwords = (W + 31) >> 5;
+    for (int64_t row = warp0; row < n_rows; row += nwarps) {
+        const T* rp = src + row * (int64_t)W;
+        for (int j0 = 0; j0 < pitch; j0 += 32) {
+            uint32_t mine_gt = 0, mine_nz = 0;
+            const int jend = min(32, wwords - j0);
+#pragma unroll 4
+            for (int j = 0; j < jend; ++j) {
+                const int px = ((j0 + j) << 5) + lane;
+                float v = 0.f;
+                if (px < W) v = (float)rp[px];
+                const uint32_t bg = __ballot_sync(0xffffffffu, v > thresh);
+                const uint32_t bn = __ballot_sync(0xffffffffu, v != 0.f);
+                if (lane == j) { mine_gt = bg; mine_nz = bn; }
+            }
+            if (j0 + lane < pitch) {
+                gt[row * pitch + j0 + lane] = mine_gt;
+                if (nz) nz[row * pitch + j0 + lane] = mine_nz;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// block-level reduction helpers (popcount sum + bounding box)
+// ---------------------------------------------------------------------------
+struct MaskStat {
+    int popc, rmin, rmax, cmin, cmax;
+};
+
+__device__ inline MaskStat stat_identity() { return {0, 0x7fffffff, -1, 0x7fffffff, -1}; }
+
+__device__ inline void stat_add_word(MaskStat& s, uint32_t w, int row, int col) {
+    if (w) {
+        s.popc += __popc(w);
+        s.rmin = min(s.rmin, row);
+        s.rmax = max(s.rmax, row);
+        s.cmin = min(s.cmin, col);
+        s.cmax = max(s.cmax, col);
+    }
+}
+
+__device__ inline MaskStat stat_warp_reduce(MaskStat s) {
+    s.popc = __reduce_add_sync(0xffffffffu, s.popc);
+    s.rmin = __reduce_min_sync(0xffffffffu, s.rmin);
+    s.rmax = __reduce_max_sync(0xffffffffu, s.rmax);
+    s.cmin = __reduce_min_sync(0xffffffffu, s.cmin);
+    s.cmax = __reduce_max_sync(0xffffffffu, s.cmax);
+    return s;
+}
+
+// red points at 5 ints in shared memory initialised to the identity.
+__device__ inline void stat_block_accumulate(int* red, MaskStat s) {
+    s = stat_warp_reduce(s);
+    if ((threadIdx.x & 31) == 0 && s.rmax >= 0) {
+        atomicAdd(&red[0], s.popc);
+        atomicMin(&red[1], s.rmin);
+        atomicMax(&red[2], s.rmax);
+        atomicMin(&red[3], s.cmin);
+        atomicMax(&red[4], s.cmax);
+    }
+}
+
+__device__ inline void stat_store(const int* red, int32_t* popc, int32_t* bbox) {
+    *popc = red[0];
+    if (red[2] < 0) {
+        bbox[0] = 0; bbox[1] = -1; bbox[2] = 0; bbox[3] = -1;
+    } else {
+        bbox[0] = red[1]; bbox[1] = red[2]; bbox[2] = red[3]; bbox[3] = red[4];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mask_meta(const uint32_t* __restrict__ bits, int H, int pitch,
+                                                   int32_t* __restrict__ popc, int32_t* __restrict__ bbox) {
+    __shared__ int red[5];
+    if (threadIdx.x == 0) { red[0] = 0; red[1] = 0x7fffffff; red[2] = -1; red[3] = 0x7fffffff; red[4] = -1; }
+    __syncthreads();
+    const int64_t m = blockIdx.x;
+    const uint4* p = reinterpret_cast<const uint4*>(bits + m * (int64_t)H * pitch);
+    const int p4 = pitch >> 2, n4 = H * p4;
+    MaskStat s = stat_identity();
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const uint4 v = __ldg(p + i);
+        const int row = i / p4, c = (i - row * p4) << 2;
+        stat_add_word(s, v.x, row, c);
+        stat_add_word(s, v.y, row, c + 1);
+        stat_add_word(s, v.z, row, c + 2);
+        stat_add_word(s, v.w, row, c + 3);
+    }
+    stat_block_accumulate(red, s);
+    __syncthreads();
+    if (threadIdx.x == 0) stat_store(red, popc + m, bbox + 4 * m);
+}
+
+// ---------------------------------------------------------------------------
+// project: unproject -> transform -> project -> splat, one CTA per
+// (job, candidate tile); the tile's bit-masks live in shared memory.
+// ---------------------------------------------------------------------------
+
+// emulate `.long()` of an fp32 on x86 followed by the reference's clamp to
+// [0, n-1] (opt_utils.py:445-450): truncation toward zero; NaN, +-inf and
+// |v| >= 2^63 become INT64_MIN, which clamps to 0.
+__device__ __forceinline__ int clamp_index(float v, int n) {
+    int i = 0;
+    if (v >= 0.f) i = (v < (float)n) ? (int)v : ((v < 9.2233720368547758e18f) ? n - 1 : 0);
+    return i;
+}
+
+constexpr int kProjThreads = 512;
+
+template <bool kSparseK>
+__global__ void __launch_bounds__(kProjThreads, 1)
+k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand,
+          const uint32_t* __restrict__ src_bits, const int32_t* __restrict__ src_bbox,
+          const float* __restrict__ xform, uint32_t* __restrict__ proj_bits,
+          int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const a3d_job_t job = jobs[blockIdx.x];
+    const int c0 = blockIdx.y * tile_cand;
+    const int nc = min(tile_cand, job.n_cand - c0);
+    if (nc <= 0) return;
+
+    const int H = cam.H, W = cam.W, pitch = cam.pitch;
+    const int words = H * pitch;
+    uint32_t* masks = smem;                                        // [tile_cand][words]
+    float* xf = reinterpret_cast<float*>(smem + (size_t)tile_cand * words);   // [tile_cand][12]
+    int* red = reinterpret_cast<int*>(xf + tile_cand * 12);        // [tile_cand][5]
+
+    {
+        uint4* m4 = reinterpret_cast<uint4*>(masks);
+        const int n4 = (nc * words) >> 2;
+        for (int i = threadIdx.x; i < n4; i += kProjThreads) m4[i] = make_uint4(0, 0, 0, 0);
+        const float* gx = xform + (size_t)(job.cand_begin + c0) * 12;
+        for (int i = threadIdx.x; i < nc * 12; i += kProjThreads) xf[i] = gx[i];
+        for (int i = threadIdx.x; i < nc; i += kProjThreads) {
+            red[5 * i + 0] = 0; red[5 * i + 1] = 0x7fffffff; red[5 * i + 2] = -1;
+            red[5 * i + 3] = 0x7fffffff; red[5 * i + 4] = -1;
+        }
+    }
+    __syncthreads();
+
+    const int32_t* sb = src_bbox + 4 * (size_t)job.src_mask;
+    const int r0 = sb[0], r1 = sb[1], w0 = sb[2], w1 = sb[3];
+    if (r1 >= r0) {
+        const uint32_t* src = src_bits + (size_t)job.src_mask * words;
+        const int ncols = w1 - w0 + 1;
+        const int nitems = (r1 - r0 + 1) * ncols * 4;       // one item = one byte = 8 pixels of a row
+        const double n0 = (double)job.normal[0], n1 = (double)job.normal[1], n2 = (double)job.normal[2];
+        const double off = (double)job.offset;
+        const float ax = job.pivot[0], ay = job.pivot[1], az = job.pivot[2];
+        const int mode = job.mode;
+        const float NaNf = __int_as_float(0x7fffffff);
+
+        for (int item = threadIdx.x; item < nitems; item += kProjThreads) {
+            const int widx = item >> 2, byte = item & 3;
+            const int rr = widx / ncols;
+            const int row = r0 + rr, wc = w0 + (widx - rr * ncols);
+            const uint32_t bits8 = (src[row * pitch + wc] >> (8 * byte)) & 0xffu;
+            if (bits8 == 0) continue;
+
+            // ---- unproject 8 pixels (get_pcd, vis.py:96-100) in float64 -------------
+            float X[8], Y[8], Z[8];
+            const double yd = (double)row;
+            const int xbase = wc * 32 + byte * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if ((bits8 >> k) & 1u) {
+                    const double xd = (double)(xbase + k);
+                    double rx, ry, rz;
+                    if (kSparseK) {
+                        rx = __dadd_rn(__dmul_rn(cam.k[0], xd), cam.k[2]);
+                        ry = __dadd_rn(__dmul_rn(cam.k[4], yd), cam.k[5]);
+                        rz = 1.0;
+                    } else {
+                        rx = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[0], xd), __dmul_rn(cam.k[1], yd)), cam.k[2]);
+                        ry = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[3], xd), __dmul_rn(cam.k[4], yd)), cam.k[5]);
+                        rz = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[6], xd), __dmul_rn(cam.k[7], yd)), cam.k[8]);
+                    }
+                    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(n0, rx), __dmul_rn(n1, ry)), __dmul_rn(n2, rz));
+                    const double depth = __ddiv_rn(off, dot);
+                    float x = __double2float_rn(__dmul_rn(depth, rx));
+                    float y = __double2float_rn(__dmul_rn(depth, ry));
+                    float z = __double2float_rn(__dmul_rn(depth, rz));
+                    // a point with any non-finite coordinate leaves the first homogeneous
+                    // transform all-NaN (every output mixes 0*coordinate terms)
+                    if (!(fabsf(x) <= 3.402823466e38f && fabsf(y) <= 3.402823466e38f &&
+                          fabsf(z) <= 3.402823466e38f)) { x = NaNf; y = NaNf; z = NaNf; }
+                    X[k] = x; Y[k] = y; Z[k] = z;
+                } else {
+                    X[k] = 0.f; Y[k] = 0.f; Z[k] = 0.f;
+                }
+            }
+
+            // ---- every candidate of the tile ---------------------------------------
+            for (int c = 0; c < nc; ++c) {
+                const float* m = xf + 12 * c;
+                const float R00 = m[0], R01 = m[1], R02 = m[2], R10 = m[3], R11 = m[4], R12 = m[5];
+                const float R20 = m[6], R21 = m[7], R22 = m[8], t0 = m[9], t1 = m[10], t2 = m[11];
+                uint32_t* cm = masks + (size_t)c * words;
+                int cur_wi = -1;
+                uint32_t cur_bits = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (!((bits8 >> k) & 1u)) continue;
+                    float px = X[k], py = Y[k], pz = Z[k];
+                    float sx, sy, sz;
+                    if (mode == A3D_MODE_TRANSLATE) {
+                        sx = __fadd_rn(px, t0); sy = __fadd_rn(py, t1); sz = __fadd_rn(pz, t2);
+                    } else {
+                        if (mode == A3D_MODE_SEQ) {
+                            px = __fsub_rn(px, ax); py = __fsub_rn(py, ay); pz = __fsub_rn(pz, az);
+                        }
+                        sx = __fadd_rn(__fadd_rn(__fmul_rn(px, R00), __fmul_rn(py, R10)), __fmul_rn(pz, R20));
+                        sy = __fadd_rn(__fadd_rn(__fmul_rn(px, R01), __fmul_rn(py, R11)), __fmul_rn(pz, R21));
+                        sz = __fadd_rn(__fadd_rn(__fmul_rn(px, R02), __fmul_rn(py, R12)), __fmul_rn(pz, R22));
+                        if (mode == A3D_MODE_SEQ) {
+                            sx = __fadd_rn(sx, ax); sy = __fadd_rn(sy, ay); sz = __fadd_rn(sz, az);
+                        } else {
+                            sx = __fadd_rn(sx, t0); sy = __fadd_rn(sy, t1); sz = __fadd_rn(sz, t2);
+                        }
+                    }
+                    // project2D (vis.py:72-75): K@p, then /w.  The 0*X, 0*Y terms only matter
+                    // for non-finite inputs; keeping them in w reproduces those cases exactly.
+                    const float u = __fadd_rn(__fmul_rn(cam.f, sx), __fmul_rn(cam.cx, sz));
+                    const float v = __fadd_rn(__fmul_rn(cam.f, sy), __fmul_rn(cam.cy, sz));
+                    const float w = __fadd_rn(__fadd_rn(__fmul_rn(0.f, sx), __fmul_rn(0.f, sy)), sz);
+                    const int col = clamp_index(__fdiv_rn(u, w), W);
+                    const int rw = clamp_index(__fdiv_rn(v, w), H);
+                    const int wi = rw * pitch + (col >> 5);
+                    const uint32_t bm = 1u << (col & 31);
+                    if (wi != cur_wi) {
+                        if (cur_bits) atomicOr(cm + cur_wi, cur_bits);
+                        cur_wi = wi;
+                        cur_bits = bm;
+                    } else {
+                        cur_bits |= bm;
+                    }
+                }
+                if (cur_bits) atomicOr(cm + cur_wi, cur_bits);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stream the tile out, with popcount + bounding box per candidate ----------
+    const int p4 = pitch >> 2, n4 = H * p4;
+    for (int c = 0; c < nc; ++c) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
+        uint4* d4 = reinterpret_cast<uint4*>(proj_bits + (size_t)(job.cand_begin + c0 + c) * words);
+        MaskStat s = stat_identity();
+        for (int i = threadIdx.x; i < n4; i += kProjThreads) {
+            const uint4 v = s4[i];
+            d4[i] = v;
+            if (v.x | v.y | v.z | v.w) {
+                const int row = i / p4, cc = (i - row * p4) << 2;
+                stat_add_word(s, v.x, row, cc);
+                stat_add_word(s, v.y, row, cc + 1);
+                stat_add_word(s, v.z, row, cc + 2);
+                stat_add_word(s, v.w, row, cc + 3);
+            }
+        }
+        stat_block_accumulate(red + 5 * c, s);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < nc; c += kProjThreads) {
+        const size_t g = (size_t)job.cand_begin + c0 + c;
+        stat_store(red + 5 * c, proj_popc + g, proj_bbox + 4 * g);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// score: inter[t][c] = popc(T_t & P_c) over the overlap of the bounding boxes;
+// union = |T_t| + |P_c| - inter; iou = fp32 divide; arg-max over candidates is
+// fused through a 64-bit atomicMax key  (iou bits << 32) | ~candidate
+// (first maximum wins; NaN = 0/0 orders above every finite value, as in torch).
+// CTA = 8 warps = (2 target groups) x (4 candidate groups); each warp owns a
+// 4x4 register tile of (target, candidate) pairs and strides its lanes over the
+// words of the region.
+// ---------------------------------------------------------------------------
+constexpr int kScoreTT = 8;    // targets per CTA
+constexpr int kScoreCT = 16;   // candidates per CTA
+
+__global__ void __launch_bounds__(256)
+k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch,
+        const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
+        const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
+        const uint32_t* __restrict__ proj_bits, const int32_t* __restrict__ proj_popc,
+        const int32_t* __restrict__ proj_bbox, unsigned long long* __restrict__ key_ws,
+        int32_t* __restrict__ inter_tab) {
+    const a3d_job_t job = jobs[blockIdx.x];
+    const int tb = blockIdx.y * kScoreTT;
+    const int cb = blockIdx.z * kScoreCT;
+    if (tb >= job.n_tgt || cb >= job.n_cand) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = tb + (warp >> 2) * 4;
+    const int c0 = cb + (warp & 3) * 4;
+    if (t0 >= job.n_tgt || c0 >= job.n_cand) return;
+    const int nt = min(4, job.n_tgt - t0), ncd = min(4, job.n_cand - c0);
+    const size_t words = (size_t)H * pitch;
+
+    const uint32_t* tp[4];
+    const uint32_t* pp[4];
+    int tmask[4];
+    // region = (union of candidate boxes) ∩ (union of target boxes)
+    int pr0 = 0x7fffffff, pr1 = -1, pc0 = 0x7fffffff, pc1 = -1;
+    int qr0 = 0x7fffffff, qr1 = -1, qc0 = 0x7fffffff, qc1 = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int ti = min(i, nt - 1);
+        tmask[i] = tgt_index[job.tgt_begin + t0 + ti];
+        tp[i] = tgt_bits + (size_t)tmask[i] * words;
+        const int32_t* b = tgt_bbox + 4 * (size_t)tmask[i];
+        if (b[1] >= b[0]) { qr0 = min(qr0, b[0]); qr1 = max(qr1, b[1]); qc0 = min(qc0, b[2]); qc1 = max(qc1, b[3]); }
+        const int ci = min(i, ncd - 1);
+        const size_t g = (size_t)job.cand_begin + c0 + ci;
+        pp[i] = proj_bits + g * words;
+        const int32_t* pb = proj_bbox + 4 * g;
+        if (pb[1] >= pb[0]) { pr0 = min(pr0, pb[0]); pr1 = max(pr1, pb[1]); pc0 = min(pc0, pb[2]); pc1 = max(pc1, pb[3]); }
+    }
+    const int ra = max(pr0, qr0), rb = min(pr1, qr1), ca = max(pc0, qc0), cbw = min(pc1, qc1);
+
+    int acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[i][k] = 0;
+
+    if (rb >= ra && cbw >= ca) {
+        const int ncols = cbw - ca + 1;
+        const int total = (rb - ra + 1) * ncols;
+        const int dr = 32 / ncols, dc = 32 - dr * ncols;
+        int r = lane / ncols, c = lane - r * ncols;
+        for (int idx = lane; idx < total; idx += 32) {
+            const int o = (ra + r) * pitch + ca + c;
+            uint32_t tw[4], pw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { tw[i] = __ldg(tp[i] + o); pw[i] = __ldg(pp[i] + o); }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[i][k] += __popc(tw[i] & pw[k]);
+            r += dr; c += dc;
+            if (c >= ncols) { c -= ncols; ++r; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[i][k] = __reduce_add_sync(0xffffffffu, acc[i][k]);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i >= nt) break;
+            const int pt = tgt_popc[tmask[i]];
+            unsigned long long best = 0ull;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k >= ncd) break;
+                const int inter = acc[i][k];
+                const int uni = pt + proj_popc[(size_t)job.cand_begin + c0 + k] - inter;
+                const float iou = __fdiv_rn((float)inter, (float)uni);
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(iou) << 32) | (unsigned)(~(unsigned)(c0 + k));
+                best = key > best ? key : best;
+                if (inter_tab) inter_tab[job.tab_begin + (int64_t)(t0 + i) * job.n_cand + c0 + k] = inter;
+            }
+            atomicMax(key_ws + job.tgt_begin + t0 + i, best);
+        }
+    }
+}
+
+// one warp per target: decode the winning candidate and recompute its counts
+__global__ void __launch_bounds__(256)
+k_finalize(const a3d_job_t* __restrict__ jobs, int H, int pitch,
+           const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
+           const int32_t* __restrict__ tgt_index, const uint32_t* __restrict__ proj_bits,
+           const int32_t* __restrict__ proj_popc, const int32_t* __restrict__ proj_bbox,
+           const unsigned long long* __restrict__ key_ws, int32_t* __restrict__ best_cand,
+           int32_t* __restrict__ best_inter, int32_t* __restrict__ best_union,
+           float* __restrict__ best_iou) {
+    const a3d_job_t job = jobs[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const size_t words = (size_t)H * pitch;
+    for (int t = blockIdx.y * nw + warp; t < job.n_tgt; t += gridDim.y * nw) {
+        const size_t slot = (size_t)job.tgt_begin + t;
+        const unsigned long long key = key_ws[slot];
+        const int cand = (int)(~(unsigned)(key & 0xffffffffull));
+        const size_t g = (size_t)job.cand_begin + cand;
+        const int tm = tgt_index[slot];
+        const uint32_t* tp = tgt_bits + (size_t)tm * words;
+        const uint32_t* pp = proj_bits + g * words;
+        const int32_t* pb = proj_bbox + 4 * g;
+        int inter = 0;
+        if (pb[1] >= pb[0]) {
+            const int ncols = pb[3] - pb[2] + 1;
+            const int total = (pb[1] - pb[0] + 1) * ncols;
+            for (int idx = lane; idx < total; idx += 32) {
+                const int r = idx / ncols, c = idx - r * ncols;
+                const int o = (pb[0] + r) * pitch + pb[2] + c;
+                inter += __popc(__ldg(tp + o) & __ldg(pp + o));
+            }
+        }
+        inter = __reduce_add_sync(0xffffffffu, inter);
+        if (lane == 0) {
+            const int uni = tgt_popc[tm] + proj_popc[g] - inter;
+            best_cand[slot] = cand;
+            best_inter[slot] = inter;
+            best_union[slot] = uni;
+            best_iou[slot] = __fdiv_rn((float)inter, (float)uni);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_emit(const uint32_t* __restrict__ bits, const int32_t* __restrict__ index, int H, int W, int pitch,
+       T* __restrict__ out) {
+    const int64_t i = blockIdx.y;
+    const int64_t m = index ? index[i] : i;
+    const uint32_t* b = bits + m * (int64_t)H * pitch;
+    T* o = out + i * (int64_t)H * W;
+    const int npx = H * W;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += gridDim.x * blockDim.x) {
+        const int r = p / W, x = p - r * W;
+        o[p] = (T)((b[r * pitch + (x >> 5)] >> (x & 31)) & 1u);
+    }
+}
+
+int device_smem_optin() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return 0;
+    return v;
+}
+
+size_t project_smem_bytes(int H, int pitch, int tile) {
+    return (size_t)tile * H * pitch * 4 + (size_t)tile * 12 * 4 + (size_t)tile * 5 * 4;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int a3d_version(void) { return A3D_VERSION; }
+
+const char* a3d_last_error_string(void) { return g_err; }
+
+int a3d_pitch_words(int W) { return W > 0 ? pitch_words(W) : 0; }
+
+int a3d_project_max_tile(int H, int W) {
+    if (H <= 0 || W <= 0) return fail(A3D_EINVAL, "a3d_project_max_tile: bad shape %dx%d", H, W);
+    const int optin = device_smem_optin();
+    if (optin <= 0) return fail(A3D_ECUDA, "a3d_project_max_tile: no CUDA device");
+    const int pitch = pitch_words(W);
+    int tile = 0;
+    while (project_smem_bytes(H, pitch, tile + 1) <= (size_t)optin) ++tile;
+    if (tile < 1)
+        return fail(A3D_ELIMIT, "a3d_project: a %dx%d mask (%zu B packed) does not fit the %d B of shared memory",
+                    H, W, (size_t)H * pitch * 4, optin);
+    return tile;
+}
+
+int a3d_pack_masks(const void* src, int dtype, int64_t n, int H, int W, float thresh,
+                   uint32_t* bits_gt, uint32_t* bits_nz, void* stream) {
+    if (n < 0 || H <= 0 || W <= 0) return fail(A3D_EINVAL, "a3d_pack_masks: bad shape");
+    if (n == 0) return A3D_OK;
+    if (!src || !bits_gt) return fail(A3D_EINVAL, "a3d_pack_masks: null pointer");
+    const int pitch = pitch_words(W);
+    const int64_t rows = n * H;
+    const int64_t want = (rows + 7) / 8;
+    const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == A3D_F32)
+        k_pack<float><<<grid, 256, 0, s>>>((const float*)src, rows, W, pitch, thresh, bits_gt, bits_nz);
+    else if (dtype == A3D_U8)
+        k_pack<unsigned char><<<grid, 256, 0, s>>>((const unsigned char*)src, rows, W, pitch, thresh, bits_gt, bits_nz);
+    else
+        return fail(A3D_EINVAL, "a3d_pack_masks: unknown dtype %d", dtype);
+    A3D_CUDA_TRY(cudaGetLastError());
+    return A3D_OK;
+}
+
+int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W, int32_t* popc, int32_t* bbox,
+                  void* stream) {
+    if (n < 0 || H <= 0 || W <= 0) return fail(A3D_EINVAL, "a3d_mask_meta: bad shape");
+    if (n == 0) return A3D_OK;
+    if (!bits || !popc || !bbox) return fail(A3D_EINVAL, "a3d_mask_meta: null pointer");
+    if (n > 0x7fffffff) return fail(A3D_ELIMIT, "a3d_mask_meta: n too large");
+    k_mask_meta<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(bits, H, pitch_words(W), popc, bbox);
+    A3D_CUDA_TRY(cudaGetLastError());
+    return A3D_OK;
+}
+
+int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
+                int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,
+                const float* xform, uint32_t* proj_bits, int32_t* proj_popc,
+                int32_t* proj_bbox, void* stream) {
+    if (!cam || n_jobs < 0 || max_cand < 0) return fail(A3D_EINVAL, "a3d_project: bad argument");
+    if (n_jobs == 0 || max_cand == 0) return A3D_OK;
+    if (!jobs || !src_bits || !src_bbox || !xform || !proj_bits || !proj_popc || !proj_bbox)
+        return fail(A3D_EINVAL, "a3d_project: null pointer");
+    const int max_tile = a3d_project_max_tile(cam->H, cam->W);
+    if (max_tile < 0) return max_tile;
+    if (tile_cand <= 0) tile_cand = max_tile;
+    if (tile_cand > max_tile)
+        return fail(A3D_EINVAL, "a3d_project: tile_cand %d > max %d for %dx%d", tile_cand, max_tile, cam->H, cam->W);
+    if (tile_cand > max_cand) tile_cand = max_cand;
+
+    Cam c;
+    memcpy(c.k, cam->kinv, sizeof(c.k));
+    c.f = cam->f; c.cx = cam->cx; c.cy = cam->cy;
+    c.H = cam->H; c.W = cam->W; c.pitch = pitch_words(cam->W);
+    c.sparse = (c.k[1] == 0.0 && c.k[3] == 0.0 && c.k[6] == 0.0 && c.k[7] == 0.0 && c.k[8] == 1.0);
+
+    const size_t smem = project_smem_bytes(c.H, c.pitch, tile_cand);
+    const dim3 grid((unsigned)n_jobs, (unsigned)((max_cand + tile_cand - 1) / tile_cand));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c.sparse) {
+        A3D_CUDA_TRY(cudaFuncSetAttribute(k_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_project<true><<<grid, kProjThreads, smem, s>>>(c, jobs, tile_cand, src_bits, src_bbox, xform,
+                                                         proj_bits, proj_popc, proj_bbox);
+    } else {
+        A3D_CUDA_TRY(cudaFuncSetAttribute(k_project<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_project<false><<<grid, kProjThreads, smem, s>>>(c, jobs, tile_cand, src_bits, src_bbox, xform,
+                                                          proj_bits, proj_popc, proj_bbox);
+    }
+    A3D_CUDA_TRY(cudaGetLastError());
+    return A3D_OK;
+}
+
+int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int max_cand,
+              int64_t n_tgt_total,
+              const uint32_t* tgt_bits, const int32_t* tgt_popc, const int32_t* tgt_bbox,
+              const int32_t* tgt_index,
+              const uint32_t* proj_bits, const int32_t* proj_popc, const int32_t* proj_bbox,
+              uint64_t* key_ws, int32_t* inter_tab,
+              int32_t* best_cand, int32_t* best_inter, int32_t* best_union, float* best_iou,
+              void* stream) {
+    if (H <= 0 || W <= 0 || n_jobs < 0 || max_tgt < 0 || max_cand < 0 || n_tgt_total < 0)
+        return fail(A3D_EINVAL, "a3d_score: bad argument");
+    if (n_jobs == 0 || max_tgt == 0 || n_tgt_total == 0) return A3D_OK;
+    if (max_cand == 0) return fail(A3D_EINVAL, "a3d_score: jobs need at least one candidate");
+    if (!jobs || !tgt_bits || !tgt_popc || !tgt_bbox || !tgt_index || !proj_bits || !proj_popc ||
+        !proj_bbox || !key_ws || !best_cand || !best_inter || !best_union || !best_iou)
+        return fail(A3D_EINVAL, "a3d_score: null pointer");
+    const int pitch = pitch_words(W);
+    cudaStream_t s = (cudaStream_t)stream;
+    A3D_CUDA_TRY(cudaMemsetAsync(key_ws, 0, sizeof(uint64_t) * (size_t)n_tgt_total, s));
+    const dim3 grid((unsigned)n_jobs, (unsigned)((max_tgt + kScoreTT - 1) / kScoreTT),
+                    (unsigned)((max_cand + kScoreCT - 1) / kScoreCT));
+    if (grid.y > 65535 || grid.z > 65535) return fail(A3D_ELIMIT, "a3d_score: too many targets/candidates per job");
+    k_score<<<grid, 256, 0, s>>>(jobs, H, pitch, tgt_bits, tgt_popc, tgt_bbox, tgt_index, proj_bits,
+                                 proj_popc, proj_bbox, (unsigned long long*)key_ws, inter_tab);
+    A3D_CUDA_TRY(cudaGetLastError());
+    const dim3 fgrid((unsigned)n_jobs, (unsigned)((max_tgt + 7) / 8 < 64 ? (max_tgt + 7) / 8 : 64));
+    k_finalize<<<fgrid, 256, 0, s>>>(jobs, H, pitch, tgt_bits, tgt_popc, tgt_index, proj_bits, proj_popc,
+                                     proj_bbox, (const unsigned long long*)key_ws, best_cand, best_inter,
+                                     best_union, best_iou);
+    A3D_CUDA_TRY(cudaGetLastError());
+    return A3D_OK;
+}
+
+int a3d_emit_masks(const uint32_t* bits, const int32_t* index, int64_t n, int H, int W,
+                   int out_dtype, void* out, void* stream) {
+    if (n < 0 || H <= 0 || W <= 0) return fail(A3D_EINVAL, "a3d_emit_masks: bad shape");
+    if (n == 0) return A3D_OK;
+    if (!bits || !out) return fail(A3D_EINVAL, "a3d_emit_masks: null pointer");
+    if (n > 65535) return fail(A3D_ELIMIT, "a3d_emit_masks: at most 65535 masks per call");
+    const int pitch = pitch_words(W);
+    const int bx = (H * W + 255) / 256;
+    const dim3 grid((unsigned)(bx < 64 ? bx : 64), (unsigned)n);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (out_dtype == A3D_F32)
+        k_emit<float><<<grid, 256, 0, s>>>(bits, index, H, W, pitch, (float*)out);
+    else if (out_dtype == A3D_U8)
+        k_emit<unsigned char><<<grid, 256, 0, s>>>(bits, index, H, W, pitch, (unsigned char*)out);
+    else
+        return fail(A3D_EINVAL, "a3d_emit_masks: unknown dtype %d", out_dtype);
+    A3D_CUDA_TRY(cudaGetLastError());
+    return A3D_OK;
+}
+
+}  // extern "C"

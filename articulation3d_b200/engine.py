@@ -1,0 +1,272 @@
+"""Device side of the hot path: bit-packed mask pools and batched scoring passes.
+
+A *pass* takes a batch of jobs — one source frame per job, each with its own list
+of candidate rigid transforms and target frames — and returns, per target, the
+first candidate of maximal mask IoU with its integer counts.  This is the unit
+the reference executes one (source, angle) and one (target) at a time in Python
+(utils/opt_utils.py:438-488).  PyTorch is used for device memory and streams
+only; all arithmetic is in csrc/a3d.cu behind the C ABI of include/a3d.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import OptConfig
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.A3DError(f"{name} must live on a CUDA device (the hot path has no CPU fallback)")
+
+
+def camera_struct(cfg: OptConfig) -> _lib.Camera:
+    cam = _lib.Camera()
+    kinv = cfg.K_inv().reshape(-1)
+    for i in range(9):
+        cam.kinv[i] = float(kinv[i])
+    cam.f = float(cfg.focal_length)
+    cam.cx = float(cfg.cx)
+    cam.cy = float(cfg.cy)
+    cam.H, cam.W = int(cfg.height), int(cfg.width)
+    return cam
+
+
+@dataclass
+class MaskPool:
+    """Bit-packed masks resident in HBM plus their popcounts / bounding boxes."""
+    bits: torch.Tensor                    # (n, H, pitch) int32: bit = mask > thresh
+    popc: torch.Tensor                    # (n,) int32
+    bbox: torch.Tensor                    # (n, 4) int32 {row_min,row_max,word_min,word_max}
+    H: int
+    W: int
+    bits_nz: torch.Tensor | None = None   # bit = mask != 0 (source pixel lists), if it differs
+    bbox_nz: torch.Tensor | None = None
+
+    def __len__(self):
+        return self.bits.shape[0]
+
+    @property
+    def source_bits(self):
+        return self.bits if self.bits_nz is None else self.bits_nz
+
+    @property
+    def source_bbox(self):
+        return self.bbox if self.bbox_nz is None else self.bbox_nz
+
+
+def mask_meta(bits: torch.Tensor, H: int, W: int):
+    lib = _lib.load()
+    _require_cuda(bits, "bits")
+    n = bits.shape[0]
+    popc = torch.empty(n, dtype=torch.int32, device=bits.device)
+    bbox = torch.empty(n, 4, dtype=torch.int32, device=bits.device)
+    _lib.check(lib.a3d_mask_meta(bits.data_ptr(), n, H, W, popc.data_ptr(), bbox.data_ptr(), _stream_ptr()),
+               "a3d_mask_meta")
+    return popc, bbox
+
+
+def pack_masks(masks: torch.Tensor, thresh: float = 0.5, with_nonzero: bool = False) -> MaskPool:
+    """(n, H, W) fp32 / uint8 / bool CUDA tensor -> MaskPool."""
+    lib = _lib.load()
+    _require_cuda(masks, "masks")
+    if masks.dim() != 3:
+        raise ValueError("masks must be (n, H, W)")
+    if masks.dtype == torch.bool:
+        masks = masks.view(torch.uint8)
+    if masks.dtype == torch.float32:
+        dt = _lib.A3D_F32
+    elif masks.dtype == torch.uint8:
+        dt = _lib.A3D_U8
+    else:
+        raise TypeError(f"unsupported mask dtype {masks.dtype}")
+    masks = masks.contiguous()
+    n, H, W = masks.shape
+    pitch = _lib.pitch_words(W)
+    with torch.cuda.device(masks.device):
+        bits = torch.empty(n, H, pitch, dtype=torch.int32, device=masks.device)
+        nz = torch.empty_like(bits) if with_nonzero else None
+        _lib.check(lib.a3d_pack_masks(masks.data_ptr(), dt, n, H, W, float(thresh), bits.data_ptr(),
+                                      nz.data_ptr() if nz is not None else None, _stream_ptr()),
+                   "a3d_pack_masks")
+        popc, bbox = mask_meta(bits, H, W)
+        pool = MaskPool(bits, popc, bbox, H, W)
+        if with_nonzero:
+            popc_nz, bbox_nz = mask_meta(nz, H, W)
+            # identical for binary masks (the contract); keep the second copy only if needed
+            if not torch.equal(popc_nz, popc):
+                pool.bits_nz, pool.bbox_nz = nz, bbox_nz
+    return pool
+
+
+def pool_from_bits(bits: torch.Tensor, H: int, W: int) -> MaskPool:
+    """Wrap already packed masks ((n, H, pitch) int32 on the device)."""
+    _require_cuda(bits, "bits")
+    assert bits.dtype == torch.int32 and bits.shape[1] == H and bits.shape[2] == _lib.pitch_words(W)
+    with torch.cuda.device(bits.device):
+        popc, bbox = mask_meta(bits.contiguous(), H, W)
+    return MaskPool(bits.contiguous(), popc, bbox, H, W)
+
+
+@dataclass
+class JobBatch:
+    """Host description of one pass (numpy, ready for a single H2D each)."""
+    jobs: np.ndarray          # (n_jobs,) _lib.JOB_DTYPE
+    xform: np.ndarray         # (n_cand_total, 12) fp32
+    tgt_index: np.ndarray     # (n_tgt_total,) int32 indices into the target pool
+
+    @property
+    def n_jobs(self):
+        return len(self.jobs)
+
+    @property
+    def units(self) -> int:
+        """track-frame x candidate IoU evaluations in this pass."""
+        return int((self.jobs["n_cand"].astype(np.int64) * self.jobs["n_tgt"]).sum())
+
+
+def build_batch(sources, modes, normals, offsets, pivots, xforms, targets) -> JobBatch:
+    """Assemble a JobBatch from per-job python/numpy pieces.
+
+    sources[i] pool index; modes[i] MODE_*; normals[i] (3,), offsets[i], pivots[i] (3,);
+    xforms[i] (A_i, 12) fp32; targets[i] sequence of pool indices."""
+    n = len(sources)
+    jobs = np.zeros(n, dtype=_lib.JOB_DTYPE)
+    cand = tgt = tab = 0
+    for i in range(n):
+        a, t = len(xforms[i]), len(targets[i])
+        jobs[i]["src_mask"] = sources[i]
+        jobs[i]["mode"] = modes[i]
+        jobs[i]["cand_begin"], jobs[i]["n_cand"] = cand, a
+        jobs[i]["tgt_begin"], jobs[i]["n_tgt"] = tgt, t
+        jobs[i]["normal"] = np.asarray(normals[i], dtype=np.float32)
+        jobs[i]["offset"] = np.float32(offsets[i])
+        jobs[i]["pivot"] = np.asarray(pivots[i], dtype=np.float32)
+        jobs[i]["tab_begin"] = tab
+        cand += a
+        tgt += t
+        tab += a * t
+    xform = (np.concatenate([np.asarray(x, dtype=np.float32).reshape(-1, 12) for x in xforms])
+             if n else np.zeros((0, 12), np.float32))
+    tgt_index = (np.concatenate([np.asarray(t, dtype=np.int32).reshape(-1) for t in targets])
+                 if n else np.zeros(0, np.int32))
+    return JobBatch(jobs, np.ascontiguousarray(xform), np.ascontiguousarray(tgt_index))
+
+
+@dataclass
+class PassResult:
+    best_cand: torch.Tensor       # (n_tgt_total,) int32, candidate index local to the job
+    best_inter: torch.Tensor      # (n_tgt_total,) int32
+    best_union: torch.Tensor      # (n_tgt_total,) int32
+    best_iou: torch.Tensor        # (n_tgt_total,) fp32
+    proj_bits: torch.Tensor       # (n_cand_total, H, pitch) int32
+    proj_popc: torch.Tensor       # (n_cand_total,) int32
+    proj_bbox: torch.Tensor       # (n_cand_total, 4) int32
+    inter_tab: torch.Tensor | None
+
+
+class DeviceBatch:
+    """A JobBatch uploaded to the device (inputs resident in HBM)."""
+
+    def __init__(self, batch: JobBatch, device):
+        self.host = batch
+        self.n_jobs = batch.n_jobs
+        self.n_cand_total = int(batch.xform.shape[0])
+        self.n_tgt_total = int(batch.tgt_index.shape[0])
+        self.max_cand = int(batch.jobs["n_cand"].max()) if self.n_jobs else 0
+        self.max_tgt = int(batch.jobs["n_tgt"].max()) if self.n_jobs else 0
+        self.tab_total = int((batch.jobs["n_cand"].astype(np.int64) * batch.jobs["n_tgt"]).sum())
+        self.jobs = torch.from_numpy(batch.jobs.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
+        self.xform = torch.from_numpy(batch.xform).to(device, non_blocking=True)
+        self.tgt_index = torch.from_numpy(batch.tgt_index).to(device, non_blocking=True)
+
+
+class Workspace:
+    """Reusable device buffers of a pass (outputs and projected masks)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._bufs = {}
+
+    def get(self, name, shape, dtype):
+        n = int(np.prod(shape))
+        buf = self._bufs.get(name)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._bufs[name] = buf
+        return buf[:n].view(*shape)
+
+
+def choose_tile(cfg: OptConfig, n_cand_total: int, sm_count: int = 148) -> int:
+    """Candidates per projection CTA: as many as shared memory holds, fewer when
+    the batch would otherwise leave SMs idle."""
+    lib = _lib.load()
+    max_tile = _lib.check(lib.a3d_project_max_tile(cfg.height, cfg.width), "a3d_project_max_tile")
+    want = max(1, -(-n_cand_total // (2 * sm_count)))
+    return int(min(max_tile, want))
+
+
+def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace | None = None,
+             want_table: bool = False, tile_cand: int | None = None) -> PassResult:
+    """project + score one batch, asynchronously on the current stream."""
+    lib = _lib.load()
+    dev = pool.bits.device
+    ws = ws or Workspace(dev)
+    H, W = cfg.height, cfg.width
+    if (pool.H, pool.W) != (H, W):
+        raise ValueError(f"mask pool is {pool.H}x{pool.W}, camera is {H}x{W}")
+    pitch = _lib.pitch_words(W)
+    nc, nt = dbatch.n_cand_total, dbatch.n_tgt_total
+    with torch.cuda.device(dev):
+        proj_bits = ws.get("proj_bits", (nc, H, pitch), torch.int32)
+        proj_popc = ws.get("proj_popc", (nc,), torch.int32)
+        proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
+        key_ws = ws.get("key_ws", (nt,), torch.int64)
+        best_cand = ws.get("best_cand", (nt,), torch.int32)
+        best_inter = ws.get("best_inter", (nt,), torch.int32)
+        best_union = ws.get("best_union", (nt,), torch.int32)
+        best_iou = ws.get("best_iou", (nt,), torch.float32)
+        inter_tab = ws.get("inter_tab", (dbatch.tab_total,), torch.int32) if want_table else None
+        if dbatch.n_jobs == 0:
+            return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab)
+        cam = camera_struct(cfg)
+        stream = _stream_ptr()
+        tile = tile_cand if tile_cand is not None else choose_tile(cfg, nc)
+        _lib.check(lib.a3d_project(C.byref(cam), dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_cand, tile,
+                                   pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(),
+                                   dbatch.xform.data_ptr(), proj_bits.data_ptr(), proj_popc.data_ptr(),
+                                   proj_bbox.data_ptr(), stream), "a3d_project")
+        _lib.check(lib.a3d_score(H, W, dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_tgt, dbatch.max_cand, nt,
+                                 pool.bits.data_ptr(), pool.popc.data_ptr(), pool.bbox.data_ptr(),
+                                 dbatch.tgt_index.data_ptr(), proj_bits.data_ptr(), proj_popc.data_ptr(),
+                                 proj_bbox.data_ptr(), key_ws.data_ptr(),
+                                 inter_tab.data_ptr() if inter_tab is not None else None,
+                                 best_cand.data_ptr(), best_inter.data_ptr(), best_union.data_ptr(),
+                                 best_iou.data_ptr(), stream), "a3d_score")
+    return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab)
+
+
+def emit_masks(bits: torch.Tensor, index: torch.Tensor | None, H: int, W: int,
+               dtype=torch.float32) -> torch.Tensor:
+    """Dense (n, H, W) images of selected packed masks (``reg_masks``)."""
+    lib = _lib.load()
+    _require_cuda(bits, "bits")
+    n = int(index.numel()) if index is not None else int(bits.shape[0])
+    out = torch.empty(n, H, W, dtype=dtype, device=bits.device)
+    code = {torch.float32: _lib.A3D_F32, torch.uint8: _lib.A3D_U8}[dtype]
+    with torch.cuda.device(bits.device):
+        for lo in range(0, n, 65535):
+            hi = min(n, lo + 65535)
+            idx_ptr = index[lo:hi].data_ptr() if index is not None else None
+            src = bits if index is not None else bits[lo:hi]
+            _lib.check(lib.a3d_emit_masks(src.data_ptr(), idx_ptr, hi - lo, H, W, code,
+                                          out[lo:hi].data_ptr(), _stream_ptr()), "a3d_emit_masks")
+    return out

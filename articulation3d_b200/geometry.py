@@ -1,0 +1,138 @@
+"""Host-side scalar geometry of one source frame (a handful of flops per job).
+
+What stays on the host, and why: the plane conversion, the integer axis
+end-points, the two unprojected axis points, the unit axis direction and the
+per-candidate rigid transforms are O(candidates) numbers per job and are built
+in float64 with the same torch/numpy calls the reference makes, so they are
+bit-identical by construction; the O(pixels x candidates) work runs on the
+device (csrc/a3d.cu).  Reference call sites (utils/opt_utils.py):
+:400-417 / :536-552 (rotation), :700-721 / :840-860 (translation),
+:420-432, :553-574, :724-728 (transforms).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .axis import angle_offset_to_axis
+from .config import OptConfig
+
+
+@dataclass
+class SourceGeometry:
+    normal: torch.Tensor        # (3,) fp32 unit normal, camera frame
+    offset: torch.Tensor        # 0-dim fp32
+    pts: torch.Tensor           # (n_boxes, 4) int64 axis end-points of every box of the frame
+    axis3d: np.ndarray          # (2, 3) float64 unprojected end-points of this box's axis
+    dir_vec: np.ndarray         # (3,) float64 unit axis direction
+    pivot: np.ndarray           # (3,) fp32  = Translate(axis3d[0]) as pytorch3d stores it
+
+
+def unproject_points(verts_xy, normal: torch.Tensor, offset: torch.Tensor, cfg: OptConfig) -> np.ndarray:
+    """Ray/plane intersection of a few pixels in float64 (utils/vis.py:86-102),
+    products and sums separately rounded, left to right — the same order the
+    device kernel uses for the mask pixels."""
+    K = cfg.K_inv()
+    v = np.asarray(verts_xy, dtype=np.float64).reshape(-1, 2)
+    x, y = v[:, 0], v[:, 1]
+    n = normal.detach().cpu().numpy().astype(np.float32).astype(np.float64)
+    off = np.float64(np.float32(float(offset)))
+    with np.errstate(all="ignore"):
+        rx = (K[0, 0] * x + K[0, 1] * y) + K[0, 2]
+        ry = (K[1, 0] * x + K[1, 1] * y) + K[1, 2]
+        rz = (K[2, 0] * x + K[2, 1] * y) + K[2, 2]
+        depth = off / ((n[0] * rx + n[1] * ry) + n[2] * rz)
+        return np.stack([depth * rx, depth * ry, depth * rz], axis=1)
+
+
+def source_geometry(p_instance, box_id: int, cfg: OptConfig, translation: bool) -> SourceGeometry:
+    plane = p_instance.pred_planes[box_id:(box_id + 1)].clone()
+    plane[:, [1, 2]] = plane[:, [2, 1]]            # [a, b, c] -> [a, -c, b]
+    plane[:, 1] = -plane[:, 1]
+    normal = F.normalize(plane, p=2)[0]
+    offset = torch.norm(plane, p=2)
+    centers = p_instance.pred_boxes.get_centers()
+    if translation:
+        axis = p_instance.pred_tran_axis
+        axis = torch.cat((axis, torch.zeros(len(axis), 1)), 1)     # offset column = 0
+    else:
+        axis = p_instance.pred_rot_axis
+    pts = angle_offset_to_axis(axis, centers, H=cfg.height, W=cfg.width)
+    axis3d = unproject_points(pts[box_id].reshape(-1, 2).numpy(), normal, offset, cfg)
+    with np.errstate(all="ignore"):
+        d = axis3d[1] - axis3d[0]
+        d = d / np.linalg.norm(d)
+    return SourceGeometry(normal, offset, pts, axis3d, d, axis3d[0].astype(np.float32))
+
+
+def _axis_angle_to_matrix(axis_angle: torch.Tensor) -> torch.Tensor:
+    """Rotation matrices of axis-angle vectors via unit quaternions, in the input
+    dtype (float64 here) — the construction pytorch3d's ``axis_angle_to_matrix``
+    documents: q = [cos(t/2), v sin(t/2)/t] (Taylor 1/2 - t^2/48 for |t| < 1e-6),
+    R from two_s = 2/|q|^2."""
+    t = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
+    half = t * 0.5
+    small = t.abs() < 1e-6
+    k = torch.empty_like(t)
+    k[~small] = torch.sin(half[~small]) / t[~small]
+    k[small] = 0.5 - (t[small] * t[small]) / 48
+    q = torch.cat([torch.cos(half), axis_angle * k], dim=-1)
+    r, i, j, kk = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    m = torch.stack((
+        1 - two_s * (j * j + kk * kk), two_s * (i * j - kk * r), two_s * (i * kk + j * r),
+        two_s * (i * j + kk * r), 1 - two_s * (i * i + kk * kk), two_s * (j * kk - i * r),
+        two_s * (i * kk - j * r), two_s * (j * kk + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return m.reshape(q.shape[:-1] + (3, 3))
+
+
+def rotation_matrices(grid, dir_vec) -> np.ndarray:
+    """(A,) grid x (..., 3) float64 axis -> (..., A, 3, 3) fp32.  fp32 angles times the
+    float64 axis, matrix in float64, stored fp32 (what ``Rotate`` keeps)."""
+    angles = torch.as_tensor(np.asarray(grid), dtype=torch.float32)[:, None]       # (A,1)
+    d = torch.as_tensor(np.asarray(dir_vec, dtype=np.float64))
+    aa = angles * d[..., None, :]                                                  # float64
+    return _axis_angle_to_matrix(aa).to(torch.float32).numpy()
+
+
+def xforms_seq(R: np.ndarray) -> np.ndarray:
+    """Cluster phase: R only (the pivot travels in the job record).  (..., A, 12) fp32."""
+    out = np.zeros(R.shape[:-2] + (12,), dtype=np.float32)
+    out[..., :9] = R.reshape(R.shape[:-2] + (9,))
+    return out
+
+
+def xforms_composed(R: np.ndarray, pivot: np.ndarray) -> np.ndarray:
+    """Final phase: one composed fp32 matrix (M_t3 M_R) M_t1; its last row is
+    ((-a0 R0j + -a1 R1j) + -a2 R2j) + a_j, every step rounded to fp32."""
+    a = np.asarray(pivot, dtype=np.float32)
+    with np.errstate(all="ignore"):
+        na = -a
+        t = (na[..., None, 0, None] * R[..., 0, :] + na[..., None, 1, None] * R[..., 1, :]) \
+            + na[..., None, 2, None] * R[..., 2, :]
+        t = (t + a[..., None, :]).astype(np.float32)
+    out = np.empty(R.shape[:-2] + (12,), dtype=np.float32)
+    out[..., :9] = R.reshape(R.shape[:-2] + (9,))
+    out[..., 9:] = t
+    return out
+
+
+def xforms_translate(grid, dir_vec) -> np.ndarray:
+    """Translation candidates: fp32 offsets x float64 direction, stored fp32."""
+    g = torch.as_tensor(grid, dtype=torch.float32)[:, None]
+    d = torch.as_tensor(np.asarray(dir_vec, dtype=np.float64))
+    v = (g * d[..., None, :]).to(torch.float32).numpy()
+    out = np.zeros(v.shape[:-1] + (12,), dtype=np.float32)
+    out[..., 0] = out[..., 4] = out[..., 8] = 1.0
+    out[..., 9:] = v
+    return out
+
+
+def transform_normals(normal: torch.Tensor, R: np.ndarray) -> torch.Tensor:
+    """Normals under the composed transform: n (M^T)^-1 over the 3x3 block (fp32)."""
+    m = torch.from_numpy(np.ascontiguousarray(R))
+    n = normal.reshape(1, 1, 3).expand(len(m), -1, -1)
+    return n.bmm(m.transpose(1, 2).inverse())[:, 0]

@@ -1,0 +1,503 @@
+"""Drop-in temporal articulation optimizer: ``track_planes`` / ``optimize_planes``.
+
+Same names, argument meaning, return values, in-place side effects and global
+``random`` consumption as the reference's utils/opt_utils.py (:962-974 dispatcher,
+:382-682 ``optimize_planes_3dc``, :685-959 ``optimize_planes_3d_trans``,
+:112-379 legacy ``'3d'``, :75-109 ``'average'``, :1156-1208 ``track_planes``),
+with the pixel work moved to the device:
+
+    reference (per source frame)                     here
+    -------------------------------------------     ---------------------------------
+    nonzero + get_pcd + Transform3d x A + project2D  a3d_project   (one launch per pass)
+      + A python-loop scatters
+    per target: >0.5, &, |, sum, sum, /, argmax      a3d_score     (one launch per pass)
+    proj_masks[angle_id].cpu() per frame             lazy a3d_emit_masks
+
+The control flow that depends on Python's global RNG and on list mutation
+ is kept on the host, written once as a generator per
+track list: it *yields* a job (source frame, candidate transforms, target frames)
+and is *sent* the per-target arg-max back.  One video is driven job by job; many
+videos are driven in lock-step so each device pass carries one job per video
+(``optimize_videos``).
+
+Additions over the reference (never removals): every optimised track gets
+``plane['fit']`` — the per-frame angle index / inter / union / iou of the final
+assignment, cluster R^2 values and the centre frame — i.e. the "angle-per-frame
+track" the reference only holds implicitly; ``plane['reg_masks']`` is a lazy
+mapping that materialises the fp32 masks on access instead of copying T x 1.2 MB
+to the host eagerly.
+"""
+from __future__ import annotations
+
+import random as _global_random
+from collections.abc import Mapping
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+from scipy.stats import linregress
+
+from . import _lib, engine, geometry
+from .axis import angle_offset_to_axis, axis_to_angle_offset
+from .config import OptConfig
+from .structures import pairwise_iou
+
+__all__ = ["track_planes", "optimize_planes", "optimize_planes_3dc", "optimize_planes_3d_trans",
+           "optimize_planes_3d", "optimize_planes_average", "optimize_videos", "RegMasks"]
+
+
+# ---------------------------------------------------------------------------
+# tracker (host only; reference utils/opt_utils.py:1156-1208)
+# ---------------------------------------------------------------------------
+def track_planes(preds, cfg: OptConfig | None = None):
+    """Greedy online box tracker -> {'rot': [...], 'trans': [...]}; each track is
+    {'bbox', 'ids': {frame: box_id}, 'latest_frame'}.  A box joins the FIRST live
+    track of its class (class 1 -> 'trans') whose latest box overlaps it with
+    IoU > 0.5 and whose gap is <= 5 frames; tracks shorter than 10 frames are
+    dropped."""
+    cfg = cfg or OptConfig()
+    planes = {'rot': [], 'trans': []}
+    for idx, p_instance in enumerate(preds):
+        pred_classes = p_instance.pred_classes
+        pred_boxes = p_instance.pred_boxes
+        for box_id in range(pred_boxes.tensor.shape[0]):
+            current_box = pred_boxes[box_id]
+            cat = 'trans' if pred_classes[box_id] == 1 else 'rot'
+            matched = False
+            for plane in planes[cat]:
+                if idx - plane['latest_frame'] > cfg.track_max_gap:
+                    continue
+                if pairwise_iou(current_box, plane['bbox']).item() > cfg.track_iou:
+                    plane['ids'][idx] = box_id
+                    plane['bbox'] = current_box
+                    plane['latest_frame'] = idx
+                    matched = True
+                    break
+            if not matched:
+                planes[cat].append({'bbox': current_box, 'ids': {idx: box_id}, 'latest_frame': idx})
+    for cat in planes:
+        planes[cat] = [p for p in planes[cat] if len(p['ids']) >= cfg.track_min_len]
+    return planes
+
+
+# ---------------------------------------------------------------------------
+# lazy reg_masks
+# ---------------------------------------------------------------------------
+class RegMasks(Mapping):
+    """``plane['reg_masks']``: frame -> (H, W) fp32 CPU mask of the best candidate
+    (reference utils/opt_utils.py:614, 906), unpacked from the device-resident
+    bit-packed copy on first access."""
+
+    def __init__(self, frames, packed: torch.Tensor, H: int, W: int):
+        self._frames = list(frames)
+        self._row = {f: i for i, f in enumerate(self._frames)}
+        self.packed = packed            # (T, H, pitch) int32 on the device
+        self._H, self._W = H, W
+        self._cache = {}
+
+    def __getitem__(self, frame):
+        i = self._row[frame]
+        if i not in self._cache:
+            idx = torch.tensor([i], dtype=torch.int32, device=self.packed.device)
+            self._cache[i] = engine.emit_masks(self.packed, idx, self._H, self._W)[0].cpu()
+        return self._cache[i]
+
+    def __iter__(self):
+        return iter(self._frames)
+
+    def __len__(self):
+        return len(self._frames)
+
+    def dense(self, dtype=torch.float32) -> torch.Tensor:
+        """All masks as one (T, H, W) device tensor."""
+        return engine.emit_masks(self.packed, None, self._H, self._W, dtype=dtype)
+
+
+# ---------------------------------------------------------------------------
+# the host control flow, as a generator of device jobs
+# ---------------------------------------------------------------------------
+@dataclass
+class JobSpec:
+    source: int                    # pool index of the source mask
+    mode: int
+    normal: np.ndarray
+    offset: float
+    pivot: np.ndarray
+    xform: np.ndarray              # (A, 12) fp32
+    targets: list                  # pool indices, in id_list order
+    keep_masks: bool = False       # final phase: return the winning packed masks
+
+
+@dataclass
+class JobResult:
+    best_cand: np.ndarray          # (n_tgt,) int32
+    best_iou: np.ndarray           # (n_tgt,) fp32
+    best_inter: np.ndarray
+    best_union: np.ndarray
+    masks: torch.Tensor | None = None     # (n_tgt, H, pitch) int32 device, if keep_masks
+
+
+@dataclass
+class Stats:
+    """What was evaluated, in the reference's accounting: one unit =
+    one (visited frame, candidate) IoU."""
+    units_visited: int = 0         # units the reference's loops evaluate
+    units_computed: int = 0        # units the device evaluated (all of id_list each round)
+    passes: int = 0
+    jobs: int = 0
+    h2d_bytes: int = 0             # masks + job descriptors copied host -> device
+    d2h_bytes: int = 0             # per-target results copied device -> host
+    detail: list = field(default_factory=list)
+
+
+def _phase_setup(translation: bool, legacy: bool, cfg: OptConfig):
+    if translation:
+        return cfg.trans_grid, cfg.trans_grid, _lib.MODE_TRANSLATE, _lib.MODE_TRANSLATE
+    if legacy:
+        return cfg.legacy_grid, cfg.legacy_grid, _lib.MODE_SEQ, _lib.MODE_SEQ
+    return cfg.rot_cluster_grid, cfg.rot_final_grid, _lib.MODE_SEQ, _lib.MODE_COMPOSED
+
+
+def _candidates(geo: geometry.SourceGeometry, grid, mode: int):
+    """(A,12) transforms, the (A,1) fp32 angle tensor the reference indexes, and R."""
+    if mode == _lib.MODE_TRANSLATE:
+        return geometry.xforms_translate(grid, geo.dir_vec), torch.as_tensor(grid, dtype=torch.float32).unsqueeze(1), None
+    R = geometry.rotation_matrices(grid, geo.dir_vec)
+    angles = torch.FloatTensor(np.asarray(grid)[:, np.newaxis])
+    if mode == _lib.MODE_SEQ:
+        return geometry.xforms_seq(R), angles, R
+    return geometry.xforms_composed(R, geo.pivot), angles, R
+
+
+def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, stats: Stats,
+                legacy: bool = False):
+    """Cluster rounds, model selection and final assignment for a list of tracks
+    (reference :386-622 / :689-908 / legacy :113-340).  Mutates ``planes``."""
+    cgrid, fgrid, cmode, fmode = _phase_setup(translation, legacy, cfg)
+    remove_inliers = not legacy
+    for plane in planes:
+        ids = plane['ids']
+        id_list = list(ids.keys())
+        clusters = []
+        for _ in range(cfg.rounds):
+            if len(id_list) == 0 and remove_inliers:
+                break
+            select_idx = rng.choice(id_list)
+            box_id = ids[select_idx]
+            geo = geometry.source_geometry(preds[select_idx], box_id, cfg, translation)
+            xf, angles, _ = _candidates(geo, cgrid, cmode)
+            order = list(id_list)
+            res = yield JobSpec(pool_of[(select_idx, box_id)], cmode, geo.normal.numpy(), float(geo.offset),
+                                geo.pivot, xf, [pool_of[(i, ids[i])] for i in order])
+            row = {f: k for k, f in enumerate(order)}
+            inliers, c_angles, c_ious = [], [], []
+            it = 0
+            while it < len(id_list):            # `for idx in id_list` with in-loop removal
+                idx = id_list[it]
+                it += 1
+                k = row[idx]
+                stats.units_visited += len(xf)
+                if res.best_iou[k] > np.float32(cfg.inlier_iou):
+                    inliers.append(idx)
+                    if remove_inliers:
+                        id_list.remove(idx)
+                    c_angles.append(angles[int(res.best_cand[k])][0])
+                    c_ious.append(float(res.best_iou[k]))
+            clusters.append({'center_id': select_idx, 'inliners': inliers,
+                             'angles': torch.FloatTensor(c_angles), 'ious': c_ious})
+
+        rsqs = []
+        for cluster in clusters:
+            if len(cluster['inliners']) < cfg.min_inliers:
+                rsqs.append(0.0)
+                continue
+            rsqs.append(linregress(range(cluster['angles'].shape[0]), cluster['angles']).rvalue ** 2)
+        rsqs = np.array(rsqs)
+        if rsqs.max() < cfg.rsq_thresh:
+            plane['has_rot'] = False
+            plane['fit'] = {'rsq': rsqs, 'clusters': clusters}
+            continue
+        plane['has_rot'] = True
+
+        final_cluster = clusters[rsqs.argmax()]
+        select_idx = final_cluster['center_id']
+        box_id = ids[select_idx]
+        p_instance = preds[select_idx]
+        geo = geometry.source_geometry(p_instance, box_id, cfg, translation)
+        xf, angles, R = _candidates(geo, fgrid, fmode)
+        frames = list(ids.keys())
+        res = yield JobSpec(pool_of[(select_idx, box_id)], fmode, geo.normal.numpy(), float(geo.offset),
+                            geo.pivot, xf, [pool_of[(i, ids[i])] for i in frames], keep_masks=True)
+        stats.units_visited += len(xf) * len(frames)
+        H, W = cfg.height, cfg.width
+        plane['reg_masks'] = RegMasks(frames, res.masks, H, W)
+        if fmode == _lib.MODE_COMPOSED:
+            normal_trans = geometry.transform_normals(geo.normal, R)
+            plane['reg_normals'] = {}
+            for k, idx in enumerate(frames):
+                n = normal_trans[int(res.best_cand[k])].clone()
+                n[1] = -n[1]
+                n[[1, 2]] = n[[2, 1]]
+                plane['reg_normals'][idx] = n
+        if translation:
+            plane['std_axis'] = p_instance.pred_tran_axis[box_id]
+        elif legacy:
+            plane['std_axis'] = geo.pts.clone()
+        else:
+            plane['std_axis'] = geo.pts[box_id]
+        plane['fit'] = {
+            'frames': frames, 'center_frame': select_idx, 'rsq': rsqs, 'clusters': clusters,
+            'angle_id': res.best_cand.copy(), 'angle': angles[:, 0].numpy()[res.best_cand],
+            'inter': res.best_inter.copy(), 'union': res.best_union.copy(), 'iou': res.best_iou.copy(),
+        }
+
+
+# ---------------------------------------------------------------------------
+# write-back (host; reference :624-682, :910-959, legacy :342-379)
+# ---------------------------------------------------------------------------
+def _rebuild(p_instance, scores):
+    out = type(p_instance)(p_instance.image_size)
+    out.scores = scores
+    out.pred_boxes = p_instance.pred_boxes
+    out.pred_planes = p_instance.pred_planes
+    out.pred_rot_axis = p_instance.pred_rot_axis
+    out.pred_tran_axis = p_instance.pred_tran_axis
+    out.pred_masks = p_instance.pred_masks
+    out.pred_classes = p_instance.pred_classes
+    return out
+
+
+def _write_back(preds, planes, cfg: OptConfig, kind: str):
+    """kind: 'rot' | 'trans' | 'legacy'."""
+    opt_preds = []
+    for idx, p_instance in enumerate(preds):
+        pred_boxes = p_instance.pred_boxes
+        pred_classes = p_instance.pred_classes
+        chosen = [False] * pred_boxes.tensor.shape[0]
+        if kind != 'legacy':
+            keep_class = 1 if kind == 'rot' else 0          # the other articulation type is never filtered
+            for i in range(pred_classes.size):
+                if pred_classes[i] == keep_class:
+                    chosen[i] = True
+        if kind == 'rot':
+            p_instance.pred_rot_axis = p_instance.pred_rot_axis.clone()
+            p_instance.pred_planes = p_instance.pred_planes.clone()
+        for plane in planes:
+            if idx not in plane['ids']:
+                continue
+            box_id = plane['ids'][idx]
+            if not plane['has_rot']:
+                chosen[box_id] = False
+                continue
+            chosen[box_id] = True
+            if kind == 'rot':
+                centers = pred_boxes.get_centers()[box_id:(box_id + 1)]
+                std_axis = axis_to_angle_offset(plane['std_axis'].unsqueeze(0).numpy().tolist(), centers)
+                p_instance.pred_rot_axis[box_id] = std_axis[0, :3]
+            elif kind == 'trans':
+                p_instance.pred_tran_axis[box_id] = plane['std_axis']     # in place, like the reference
+        chosen = np.array(chosen, dtype=bool)
+        scores = np.copy(p_instance.scores)
+        decay = cfg.legacy_score_decay if kind == 'legacy' else cfg.score_decay
+        scores[~chosen] = scores[~chosen] * decay
+        opt_preds.append(_rebuild(p_instance, scores))
+    return opt_preds
+
+
+# ---------------------------------------------------------------------------
+# device session: mask pool + job driver
+# ---------------------------------------------------------------------------
+class _Session:
+    """Packed masks of every tracked box of a set of videos, resident on one GPU."""
+
+    def __init__(self, videos, cfg: OptConfig, device):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.ws = engine.Workspace(self.device)
+        self.pool_of = []                   # per video: {(frame, box_id): pool index}
+        chunks, n = [], 0
+        for preds, plane_lists in videos:
+            need = {}
+            for planes in plane_lists:
+                for plane in planes:
+                    for f, b in plane['ids'].items():
+                        need.setdefault(f, set()).add(b)
+            index = {}
+            for f in sorted(need):
+                boxes = sorted(need[f])
+                m = preds[f].pred_masks
+                sel = m if len(boxes) == m.shape[0] else m[boxes]
+                if tuple(sel.shape[1:]) != (cfg.height, cfg.width):
+                    raise ValueError(f"mask shape {tuple(sel.shape[1:])} != camera {cfg.height}x{cfg.width}")
+                chunks.append(sel)
+                for b in boxes:
+                    index[(f, b)] = n
+                    n += 1
+            self.pool_of.append(index)
+        self.h2d_bytes = 0
+        if n == 0:
+            self.pool = None
+            return
+        dev_chunks = []
+        for c in chunks:
+            if c.dtype not in (torch.float32, torch.uint8, torch.bool):
+                c = c.float()
+            if not c.is_cuda:
+                self.h2d_bytes += c.numel() * c.element_size()
+            dev_chunks.append(c.to(self.device, non_blocking=True))
+        dt = dev_chunks[0].dtype
+        dense = torch.cat([c if c.dtype == dt else c.to(dt) for c in dev_chunks])
+        self.pool = engine.pack_masks(dense, cfg.mask_thresh, with_nonzero=(dt == torch.float32))
+        del dense, dev_chunks
+
+    def run(self, specs, stats: Stats | None = None):
+        """One device pass over a list of JobSpec -> list of JobResult."""
+        batch = engine.build_batch([s.source for s in specs], [s.mode for s in specs],
+                                   [s.normal for s in specs], [s.offset for s in specs],
+                                   [s.pivot for s in specs], [s.xform for s in specs],
+                                   [s.targets for s in specs])
+        dbatch = engine.DeviceBatch(batch, self.device)
+        res = engine.run_pass(self.cfg, self.pool, dbatch, self.ws)
+        packed = torch.stack([res.best_cand, res.best_inter, res.best_union,
+                              res.best_iou.view(torch.int32)]).cpu().numpy()     # one D2H, syncs
+        if stats is not None:
+            stats.h2d_bytes += batch.jobs.nbytes + batch.xform.nbytes + batch.tgt_index.nbytes
+            stats.d2h_bytes += packed.nbytes
+        out = []
+        for j, s in enumerate(specs):
+            a, n = int(batch.jobs[j]["tgt_begin"]), int(batch.jobs[j]["n_tgt"])
+            r = JobResult(packed[0, a:a + n].copy(), packed[3, a:a + n].copy().view(np.float32),
+                          packed[1, a:a + n].copy(), packed[2, a:a + n].copy())
+            if s.keep_masks:
+                gidx = (res.best_cand[a:a + n].long() + int(batch.jobs[j]["cand_begin"]))
+                r.masks = res.proj_bits.index_select(0, gidx)       # copy out of the workspace
+            out.append(r)
+        return out, batch.units
+
+
+def _drive(gens, session: _Session, stats: Stats):
+    """Run generators in lock-step: every device pass carries the pending job of
+    each still-active generator."""
+    pending = {}
+    for i, g in enumerate(gens):
+        try:
+            pending[i] = next(g)
+        except StopIteration:
+            pass
+    while pending:
+        keys = list(pending.keys())
+        results, units = session.run([pending[k] for k in keys], stats)
+        stats.passes += 1
+        stats.jobs += len(keys)
+        stats.units_computed += units
+        for k, r in zip(keys, results):
+            try:
+                pending[k] = gens[k].send(r)
+            except StopIteration:
+                del pending[k]
+
+
+def _default_device(device):
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        raise _lib.A3DError("articulation3d_b200 needs a CUDA device; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ---------------------------------------------------------------------------
+# public API (reference signatures)
+# ---------------------------------------------------------------------------
+def optimize_planes_3d_trans(preds, planes, frames=None, cfg=None, device=None, rng=None,
+                             _session=None, stats=None):
+    """Translation tracks (reference utils/opt_utils.py:685-959)."""
+    cfg, stats = cfg or OptConfig(), stats or Stats()
+    session = _session or _Session([(preds, [planes])], cfg, _default_device(device))
+    _drive([_tracks_gen(preds, planes, cfg, True, rng or _global_random, session.pool_of[0], stats)],
+           session, stats)
+    return _write_back(preds, planes, cfg, 'trans')
+
+
+def optimize_planes_3dc(preds, planes, frames=None, cfg=None, device=None, rng=None,
+                        _session=None, stats=None):
+    """Rotation tracks with 3-D clustering (reference utils/opt_utils.py:382-682)."""
+    cfg, stats = cfg or OptConfig(), stats or Stats()
+    session = _session or _Session([(preds, [planes])], cfg, _default_device(device))
+    _drive([_tracks_gen(preds, planes, cfg, False, rng or _global_random, session.pool_of[0], stats)],
+           session, stats)
+    return _write_back(preds, planes, cfg, 'rot')
+
+
+def optimize_planes_3d(preds, planes, cfg=None, device=None, rng=None, stats=None):
+    """Legacy method '3d' (reference utils/opt_utils.py:112-379)."""
+    cfg, stats = cfg or OptConfig(), stats or Stats()
+    session = _Session([(preds, [planes])], cfg, _default_device(device))
+    _drive([_tracks_gen(preds, planes, cfg, False, rng or _global_random, session.pool_of[0], stats,
+                        legacy=True)], session, stats)
+    return _write_back(preds, planes, cfg, 'legacy')
+
+
+def optimize_planes_average(preds, planes):
+    """Method 'average' (reference utils/opt_utils.py:75-109); host only."""
+    for plane in planes:
+        std_axes = []
+        for idx in plane['ids']:
+            box_id = plane['ids'][idx]
+            p_instance = preds[idx]
+            pts = angle_offset_to_axis(p_instance.pred_rot_axis, p_instance.pred_boxes.get_centers())
+            img_centers = torch.FloatTensor(np.array([[320, 240]]))
+            std_axis = axis_to_angle_offset(pts.numpy().tolist(), img_centers)[:, :3]
+            std_axes.append(std_axis[box_id:(box_id + 1)])
+        plane['std_axis'] = torch.cat(std_axes).mean(axis=0)
+    for idx, p_instance in enumerate(preds):
+        for plane in planes:
+            if idx in plane['ids']:
+                p_instance.pred_rot_axis[plane['ids'][idx]] = plane['std_axis']
+    return list(preds)
+
+
+def optimize_planes(preds, planes, method, frames=None, cfg=None, device=None, stats=None):
+    """Reference dispatcher (utils/opt_utils.py:962-974).  ``planes`` is the dict
+    ``track_planes`` returns for '3dc', a list of tracks for 'average' / '3d'."""
+    if method == 'average':
+        return optimize_planes_average(preds, planes)
+    elif method == '3d':
+        return optimize_planes_3d(preds, planes, cfg=cfg, device=device, stats=stats)
+    elif method == '3dc':
+        cfg = cfg or OptConfig()
+        stats = stats if stats is not None else Stats()
+        session = _Session([(preds, [planes['trans'], planes['rot']])], cfg, _default_device(device))
+        stats.h2d_bytes += session.h2d_bytes
+        opt_preds = optimize_planes_3d_trans(preds, planes['trans'], frames=frames, cfg=cfg,
+                                             _session=session, stats=stats)
+        return optimize_planes_3dc(opt_preds, planes['rot'], frames=frames, cfg=cfg,
+                                   _session=session, stats=stats)
+    else:
+        raise NotImplementedError
+
+
+def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
+    """Batched '3dc' over independent videos: ``videos`` is a list of
+    ``(preds, planes)``; video i draws its source frames from
+    ``random.Random(seeds[i])`` (the reference seeds one process per video,
+    tools/inference.py:172), so the result of every video equals
+    ``random.seed(seeds[i]); optimize_planes(preds, planes, '3dc')``.  All videos
+    advance in lock-step: one device pass per chain step carries one job per
+    video."""
+    cfg = cfg or OptConfig()
+    stats = stats if stats is not None else Stats()
+    session = _Session([(p, [pl['trans'], pl['rot']]) for p, pl in videos], cfg, _default_device(device))
+    stats.h2d_bytes += session.h2d_bytes
+    rngs = [_global_random.Random(s) for s in seeds]
+
+    def video_gen(i):
+        preds, planes = videos[i]
+        yield from _tracks_gen(preds, planes['trans'], cfg, True, rngs[i], session.pool_of[i], stats)
+        mid = _write_back(preds, planes['trans'], cfg, 'trans')
+        outs[i] = mid
+        yield from _tracks_gen(mid, planes['rot'], cfg, False, rngs[i], session.pool_of[i], stats)
+        outs[i] = _write_back(mid, planes['rot'], cfg, 'rot')
+
+    outs = [None] * len(videos)
+    _drive([video_gen(i) for i in range(len(videos))], session, stats)
+    return outs

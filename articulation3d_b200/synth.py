@@ -169,9 +169,11 @@ def _mask_boxes(masks: torch.Tensor) -> torch.Tensor:
     return box
 
 
-def track_predictions(scene: VideoScene, track: int, cfg: OptConfig, masks: torch.Tensor):
+def track_predictions(scene: VideoScene, track: int, cfg: OptConfig, masks: torch.Tensor,
+                      frames=None):
     """Per-frame detector outputs of one track (CPU fp32 tensors):
-    boxes (T,4), pred_planes (T,3), pred_rot_axis (T,3), pred_tran_axis (T,2)."""
+    boxes (T,4), pred_planes (T,3), pred_rot_axis (T,3), pred_tran_axis (T,2).
+    ``frames`` restricts the (python-loop) axis fields to those frames."""
     T = scene.n_frames
     f = cfg.focal_length
     boxes = _mask_boxes(masks).cpu() + scene.box_jitter[track]
@@ -195,7 +197,7 @@ def track_predictions(scene: VideoScene, track: int, cfg: OptConfig, masks: torc
     tran_axis = torch.zeros(T, 2)
     mid = h + 0.5 * scene.width[track] * w
     ta, tb = proj(mid), proj(mid + 0.1 * scene.slide[track])
-    for t in range(T):
+    for t in (range(T) if frames is None else frames):
         line = [[float(a[t, 0]), float(a[t, 1]), float(b[t, 0]), float(b[t, 1])]]
         rot_axis[t] = axis_to_angle_offset(line, centers[t:t + 1])[0, :3]
         dxy = (tb[t] - ta[t])

@@ -1,0 +1,123 @@
+"""Named synthetic workloads (BASELINE.json ``configs``) as
+device-resident scoring passes and as host-side clips.
+
+A *pass* = one source frame per track x T target frames x A candidates; one
+unit of work = one (target frame, candidate) IoU evaluation.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, engine, geometry, synth
+from .config import OptConfig, rot_grid
+from .structures import Boxes, Instances
+
+
+@dataclass
+class Workload:
+    name: str
+    description: str
+    videos: int          # per GPU
+    tracks: int          # per video
+    frames: int
+    cand: int            # candidate grid of the scoring pass
+    width: int = 640
+    height: int = 480
+
+    def cfg(self) -> OptConfig:
+        final = max(1, int(round(self.cand * 2 / 3)))
+        return OptConfig.scaled(self.width, self.height,
+                                rot_cluster_grid=rot_grid(self.cand),
+                                rot_final_grid=rot_grid(final, -np.pi / 2, np.pi / 2)) \
+            if (self.width, self.height) != (640, 480) else \
+            OptConfig(rot_cluster_grid=rot_grid(self.cand),
+                      rot_final_grid=rot_grid(final, -np.pi / 2, np.pi / 2))
+
+    @property
+    def units_per_pass(self) -> int:
+        return self.videos * self.tracks * self.frames * self.cand
+
+    def alg_bytes_per_pass(self) -> int:
+        """per track (T+1) packed masks + 16 B/frame of results + 48 B/candidate."""
+        pitch = _lib.pitch_words(self.width)
+        per_track = (self.frames + 1) * self.height * pitch * 4 + 16 * self.frames + 48 * self.cand
+        return self.videos * self.tracks * per_track
+
+
+WORKLOADS = {
+    # configs[1]: the single-GPU configuration the metric is quoted on
+    "c2": Workload("c2", "opt_arti synthetic: 1 video, 4 plane tracks x 60 frames, 90-angle grid, 640x480",
+                   1, 4, 60, 90),
+    # configs[2] per-GPU shard at 8 GPUs (256 videos / 8), and the whole thing on one GPU
+    "c3_shard": Workload("c3_shard", "batched opt_arti shard: 32 videos x 8 tracks x 120 frames, 180-angle grid",
+                         32, 8, 120, 180),
+    "c3": Workload("c3", "batched opt_arti: 256 videos x 8 tracks x 120 frames, 180-angle grid",
+                   256, 8, 120, 180),
+    # configs[3] per-GPU shard: 1024x768, 720 rotation candidates (translation candidates are a second pass)
+    "c4_shard": Workload("c4_shard", "dense sweep shard: 8 videos x 8 tracks x 120 frames, 720-angle grid, 1024x768",
+                         8, 8, 120, 720, 1024, 768),
+}
+
+
+@dataclass
+class PassInputs:
+    cfg: OptConfig
+    pool: engine.MaskPool
+    batch: engine.JobBatch
+    dbatch: engine.DeviceBatch
+    units: int
+
+
+def build_pass(wl: Workload, seed0: int, device, source_frame: int | None = None,
+               progress=None) -> PassInputs:
+    """Render every track of ``wl`` on the device, pack the masks, and describe one
+    cluster-phase (three-step rotation) pass with the middle frame of each track as source."""
+    cfg = wl.cfg()
+    T = wl.frames
+    s = T // 2 if source_frame is None else source_frame
+    bits, srcs, normals, offsets, pivots, dirs = [], [], [], [], [], []
+    n = 0
+    for v in range(wl.videos):
+        scene = synth.make_scene(seed0 + v, wl.tracks, T, cfg, kinds=[synth.KIND_ROT] * wl.tracks)
+        for k in range(wl.tracks):
+            masks = synth.render_track_masks(scene, k, cfg, device=device)            # (T,H,W) bool
+            boxes, planes, rot_axis, tran_axis = synth.track_predictions(scene, k, cfg, masks, frames=[s])
+            inst = Instances((cfg.height, cfg.width))
+            inst.pred_boxes = Boxes(boxes[s:s + 1])
+            inst.pred_planes = planes[s:s + 1]
+            inst.pred_rot_axis = rot_axis[s:s + 1]
+            inst.pred_tran_axis = tran_axis[s:s + 1]
+            geo = geometry.source_geometry(inst, 0, cfg, False)
+            p = engine.pack_masks(masks)
+            bits.append(p.bits)
+            srcs.append(n + s)
+            normals.append(geo.normal.numpy())
+            offsets.append(float(geo.offset))
+            pivots.append(geo.pivot)
+            dirs.append(geo.dir_vec)
+            n += T
+        if progress:
+            progress(v)
+    pool = engine.pool_from_bits(torch.cat(bits), cfg.height, cfg.width)
+    del bits
+    R = geometry.rotation_matrices(cfg.rot_cluster_grid, np.stack(dirs))             # (S,A,3,3)
+    xf = geometry.xforms_seq(R)
+    S = len(srcs)
+    batch = engine.build_batch(srcs, [_lib.MODE_SEQ] * S, normals, offsets, pivots, list(xf),
+                               [np.arange(i * T, (i + 1) * T, dtype=np.int32) for i in range(S)])
+    dbatch = engine.DeviceBatch(batch, device)
+    return PassInputs(cfg, pool, batch, dbatch, batch.units)
+
+
+def make_clip(wl: Workload, seed: int, tracks: int | None = None, frames: int | None = None,
+              kinds=None):
+    """Host-side clip of the workload's shape (list[Instances] with fp32 CPU masks)."""
+    cfg = wl.cfg()
+    tracks = tracks or wl.tracks
+    frames = frames or wl.frames
+    kinds = kinds if kinds is not None else [synth.KIND_ROT] * tracks
+    preds, _ = synth.make_video(seed, tracks, frames, cfg, kinds=kinds)
+    return preds, cfg

@@ -1,0 +1,149 @@
+/*
+ * a3d.h — C ABI of the B200-native temporal articulation optimizer hot path.
+ *
+ * Drop-in scope: the data-parallel part of JasonQSY/Articulation3D's
+ * post-detection temporal optimisation, i.e. everything inside
+ *     articulation3d/utils/opt_utils.py:382-682  optimize_planes_3dc
+ *     articulation3d/utils/opt_utils.py:685-959  optimize_planes_3d_trans
+ * that touches pixels:  get_pcd / project2D (articulation3d/utils/vis.py:62-102),
+ * the pytorch3d transform chain, the point-splat loops and the IoU/argmax loops.
+ * The reference has no FFI for this path: the host side that
+ * binds these symbols is articulation3d_b200/opt_utils.py, which keeps the
+ * reference's Python signatures (track_planes / optimize_planes).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative A3D_E* code on failure;
+ *     a3d_last_error_string() describes the last failure on the calling thread;
+ *   - all buffers are caller-owned DEVICE pointers unless marked HOST;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *     every call is asynchronous with respect to the host;
+ *   - no global state, re-entrant, no C++ exceptions cross the boundary.
+ *
+ * Bit-packed mask layout ("bits"): uint32 [n][H][pitch], pitch =
+ * a3d_pitch_words(W) = ceil(W/32) rounded up to a multiple of 4 words so that
+ * rows are 16-byte aligned (TMA / bulk-copy granularity); bit i of word j of
+ * row r is pixel (r, 32*j + i); padding bits are zero.
+ */
+#ifndef A3D_H_
+#define A3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define A3D_VERSION 100            /* 0.1.0 */
+
+enum {
+    A3D_OK = 0,
+    A3D_EINVAL = -1,               /* bad argument */
+    A3D_ECUDA = -2,                /* CUDA runtime error (see error string) */
+    A3D_ELIMIT = -3                /* shape exceeds what the kernels support */
+};
+
+/* mask element types accepted by a3d_pack_masks / produced by a3d_emit_masks */
+enum { A3D_F32 = 0, A3D_U8 = 1 };
+
+/* candidate transform modes (one per job) */
+enum {
+    A3D_MODE_SEQ = 0,        /* q=p-a; r=q*R; s=r+a  — cluster phase, opt_utils.py:433-435   */
+    A3D_MODE_COMPOSED = 1,   /* s=p*R+t            — final phase, opt_utils.py:571-572       */
+    A3D_MODE_TRANSLATE = 2   /* s=p+t              — translation tracks, opt_utils.py:726-728 */
+};
+
+/* Pinhole camera of get_pcd / project2D (vis.py:62-68, 86-95).  HOST struct. */
+typedef struct {
+    double  kinv[9];         /* row-major inverse intrinsics exactly as numpy.linalg.inv returns them */
+    float   f, cx, cy;       /* project2D: K = [[f,0,cx],[0,f,cy],[0,0,1]] in fp32 */
+    int32_t H, W;            /* mask size */
+} a3d_camera_t;
+
+/* One scoring job = one source frame of one track: its mask is unprojected onto
+ * its plane, moved by n_cand candidate transforms, re-projected, and every
+ * candidate is scored against n_tgt target masks (opt_utils.py:397-488). */
+typedef struct {
+    int32_t src_mask;        /* index into the source mask pool                         */
+    int32_t mode;            /* A3D_MODE_*                                               */
+    int32_t cand_begin;      /* first global candidate slot (xform / proj_* arrays)     */
+    int32_t n_cand;
+    int32_t tgt_begin;       /* first global target slot (tgt_index / best_* arrays)    */
+    int32_t n_tgt;
+    float   normal[3];       /* unit plane normal, camera frame (opt_utils.py:410)      */
+    float   offset;          /* plane offset                      (opt_utils.py:411)    */
+    float   pivot[3];        /* fp32 axis point a = Translate(verts_axis_3d[0]) (:420)  */
+    float   pad0;
+    int64_t tab_begin;       /* first element of this job's [n_tgt][n_cand] table       */
+} a3d_job_t;                 /* 64 bytes */
+
+int         a3d_version(void);
+const char* a3d_last_error_string(void);
+
+/* words per packed row for an image of width W */
+int a3d_pitch_words(int W);
+
+/* Largest number of candidates one projection CTA can hold in shared memory for
+ * an HxW mask on the current device (>=1), or A3D_ELIMIT. */
+int a3d_project_max_tile(int H, int W);
+
+/* (a7/a8 input stage) threshold + bit-pack.  Replaces the per-visit
+ * `(pred_mask > 0.5)` of opt_utils.py:471-473 and `pred_mask.nonzero()` of :409.
+ *   src      [n][H][W] of dtype (A3D_F32 | A3D_U8), contiguous
+ *   bits_gt  [n][H][pitch]  bit = src > thresh
+ *   bits_nz  [n][H][pitch]  bit = src != 0        (may be NULL)               */
+int a3d_pack_masks(const void* src, int dtype, int64_t n, int H, int W, float thresh,
+                   uint32_t* bits_gt, uint32_t* bits_nz, void* stream);
+
+/* population count and bounding box of packed masks.
+ *   popc [n];  bbox [n][4] = {row_min, row_max, word_min, word_max} inclusive,
+ *   {0,-1,0,-1} for an empty mask.                                             */
+int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W,
+                  int32_t* popc, int32_t* bbox, void* stream);
+
+/* (a4-a7) unproject + transform + project + splat.  Replaces get_pcd
+ * (vis.py:86-102), the Transform3d chain (opt_utils.py:420-435, 553-574,
+ * 724-728), project2D (vis.py:71-75) and the splat loop (opt_utils.py:438-457).
+ *   cam        HOST
+ *   jobs       [n_jobs] device
+ *   max_cand   max over jobs of n_cand
+ *   tile_cand  candidates per CTA, 1..a3d_project_max_tile(H,W) (0 = choose)
+ *   src_bits   source mask pool, src_bbox its a3d_mask_meta boxes
+ *   xform      [n_cand_total][12] fp32: rows 0-2 of R (row-vector convention,
+ *              p' = p*R), then t
+ *   proj_bits  [n_cand_total][H][pitch]; proj_popc [n_cand_total];
+ *   proj_bbox  [n_cand_total][4]                                               */
+int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
+                int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,
+                const float* xform, uint32_t* proj_bits, int32_t* proj_popc,
+                int32_t* proj_bbox, void* stream);
+
+/* (a8) mask-IoU scoring with fused arg-max over candidates.  Replaces the
+ * `for idx in id_list` loops of opt_utils.py:464-477, 600-612, 757-770, 892-904.
+ *   tgt_index  [n_tgt_total] indices into the target pool (tgt_bits/popc/bbox)
+ *   key_ws     [n_tgt_total] uint64 workspace
+ *   inter_tab  optional [sum n_tgt*n_cand] int32 table of intersections (NULL ok)
+ * outputs, per target slot:
+ *   best_cand  index of the first candidate with maximal IoU (NaN counts as max)
+ *   best_inter, best_union  integer counts at that candidate
+ *   best_iou   fp32 inter/union (IEEE division)                                */
+int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int max_cand,
+              int64_t n_tgt_total,
+              const uint32_t* tgt_bits, const int32_t* tgt_popc, const int32_t* tgt_bbox,
+              const int32_t* tgt_index,
+              const uint32_t* proj_bits, const int32_t* proj_popc, const int32_t* proj_bbox,
+              uint64_t* key_ws, int32_t* inter_tab,
+              int32_t* best_cand, int32_t* best_inter, int32_t* best_union, float* best_iou,
+              void* stream);
+
+/* (a11) materialise selected packed masks as dense images: out[i] =
+ * unpack(bits[index[i]]) as A3D_F32 (0.0/1.0) or A3D_U8 (0/1).  Replaces
+ * `proj_masks[angle_id].cpu()` of opt_utils.py:614, 906 (index may be NULL =
+ * identity).                                                                   */
+int a3d_emit_masks(const uint32_t* bits, const int32_t* index, int64_t n, int H, int W,
+                   int out_dtype, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A3D_H_ */

@@ -1,0 +1,326 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the
+committed golden fixtures.  Bit-exact for masks, pixel counts, inter/union and
+arg-max indices; 1e-4 relative for floats (BASELINE.json north_star)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from articulation3d_b200 import OptConfig, _lib, engine, geometry, opt_utils, synth
+from articulation3d_b200.structures import Boxes, Instances
+from oracle import restated
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _unpack(bits: torch.Tensor, W: int) -> np.ndarray:
+    """(n,H,pitch) int32 device -> (n,H,W) bool numpy"""
+    b = bits.cpu().numpy().view(np.uint32)
+    u8 = b.view(np.uint8).reshape(b.shape[0], b.shape[1], -1)
+    return np.unpackbits(u8, axis=-1, bitorder="little")[..., :W].astype(bool)
+
+
+def _bbox_ref(m: np.ndarray):
+    if not m.any():
+        return [0, -1, 0, -1]
+    rows = np.where(m.any(1))[0]
+    cols = np.where(m.any(0))[0]
+    return [rows[0], rows[-1], cols[0] // 32, cols[-1] // 32]
+
+
+@pytest.mark.parametrize("H,W,dtype", [(480, 640, torch.float32), (75, 100, torch.float32),
+                                       (33, 1, torch.float32), (17, 1057, torch.uint8),
+                                       (40, 64, torch.bool)])
+def test_pack_and_meta(H, W, dtype):
+    g = torch.Generator().manual_seed(H * W)
+    n = 7
+    dense = torch.rand(n, H, W, generator=g)
+    dense[0] = 0                                   # empty mask
+    dense[1] = 1                                   # full mask
+    dense[2, :, : W // 2] = 0
+    if dtype == torch.float32:
+        m = torch.where(dense > 0.7, dense, torch.zeros(()))   # non-binary: 0 or (0.7,1]
+        m[3] = torch.where(dense[3] > 0.5, 0.3, 0.0)           # nonzero but below threshold
+    else:
+        m = (dense > 0.7).to(dtype)
+    pool = engine.pack_masks(m.to(DEV), 0.5, with_nonzero=(dtype == torch.float32))
+    want = (m.float() > 0.5).numpy()
+    got = _unpack(pool.bits, W)
+    assert np.array_equal(got, want)
+    # padding bits are zero
+    raw = pool.bits.cpu().numpy().view(np.uint32)
+    assert raw.shape[2] == _lib.pitch_words(W)
+    full = np.unpackbits(raw.view(np.uint8).reshape(n, H, -1), axis=-1, bitorder="little")
+    assert not full[..., W:].any()
+    assert np.array_equal(pool.popc.cpu().numpy(), want.reshape(n, -1).sum(1))
+    assert pool.bbox.cpu().numpy().tolist() == [_bbox_ref(w) for w in want]
+    if dtype == torch.float32:
+        assert pool.bits_nz is not None
+        assert np.array_equal(_unpack(pool.bits_nz, W), (m != 0).numpy())
+    back = engine.emit_masks(pool.bits, None, H, W)
+    assert np.array_equal(back.cpu().numpy() > 0.5, want)
+    idx = torch.tensor([2, 0, 1], dtype=torch.int32, device=DEV)
+    assert np.array_equal(engine.emit_masks(pool.bits, idx, H, W, torch.uint8).cpu().numpy(),
+                          want[[2, 0, 1]].astype(np.uint8))
+
+
+def _oracle_job(preds, frame, box, ocfg, mode, grid):
+    name = {_lib.MODE_SEQ: "seq", _lib.MODE_COMPOSED: "composed", _lib.MODE_TRANSLATE: "translate"}[mode]
+    masks, _, g = restated.candidate_masks(preds[frame], box, ocfg, name, grid)
+    return masks.numpy() > 0.5
+
+
+def _device_job(preds, frame, box, cfg, mode, grid, pool, src_idx, targets, tile=None, want_table=True):
+    geo = geometry.source_geometry(preds[frame], box, cfg, mode == _lib.MODE_TRANSLATE)
+    if mode == _lib.MODE_TRANSLATE:
+        xf = geometry.xforms_translate(grid, geo.dir_vec)
+    else:
+        R = geometry.rotation_matrices(grid, geo.dir_vec)
+        xf = geometry.xforms_seq(R) if mode == _lib.MODE_SEQ else geometry.xforms_composed(R, geo.pivot)
+    batch = engine.build_batch([src_idx], [mode], [geo.normal.numpy()], [float(geo.offset)], [geo.pivot],
+                               [xf], [targets])
+    res = engine.run_pass(cfg, pool, engine.DeviceBatch(batch, DEV), want_table=want_table, tile_cand=tile)
+    torch.cuda.synchronize()
+    return res, batch
+
+
+def _check_pass(res, batch, proj_want, tgt_masks, W):
+    """proj_want (A,H,W) bool, tgt_masks (T,H,W) bool."""
+    A, T = proj_want.shape[0], tgt_masks.shape[0]
+    got = _unpack(res.proj_bits[:A], W)
+    assert got.shape == proj_want.shape
+    diff = int((got != proj_want).sum())
+    assert diff == 0, f"{diff} projected pixels differ"
+    assert np.array_equal(res.proj_popc[:A].cpu().numpy(), proj_want.reshape(A, -1).sum(1))
+    assert res.proj_bbox[:A].cpu().numpy().tolist() == [_bbox_ref(p) for p in proj_want]
+    inter = (tgt_masks[:, None] & proj_want[None]).reshape(T, A, -1).sum(-1)
+    union = (tgt_masks[:, None] | proj_want[None]).reshape(T, A, -1).sum(-1)
+    assert np.array_equal(res.inter_tab[:T * A].cpu().numpy().reshape(T, A), inter)
+    iou = torch.from_numpy(inter) / torch.from_numpy(union)            # int64/int64 -> fp32, as torch does
+    best = iou.argmax(1).numpy()
+    assert np.array_equal(res.best_cand[:T].cpu().numpy(), best)
+    assert np.array_equal(res.best_inter[:T].cpu().numpy(), inter[np.arange(T), best])
+    assert np.array_equal(res.best_union[:T].cpu().numpy(), union[np.arange(T), best])
+    assert np.array_equal(res.best_iou[:T].cpu().numpy(), iou.numpy()[np.arange(T), best], equal_nan=True)
+
+
+@pytest.mark.parametrize("mode", [_lib.MODE_SEQ, _lib.MODE_COMPOSED, _lib.MODE_TRANSLATE])
+@pytest.mark.parametrize("tile", [1, 4, None])
+def test_project_and_score_match_oracle(mode, tile):
+    cfg, ocfg = OptConfig(), restated.OracleConfig()
+    preds, _ = synth.make_video(77, 3, 10, kinds=[0, 1, 0])
+    box = 1 if mode == _lib.MODE_TRANSLATE else 0
+    grid = {_lib.MODE_SEQ: cfg.rot_cluster_grid, _lib.MODE_COMPOSED: cfg.rot_final_grid,
+            _lib.MODE_TRANSLATE: cfg.trans_grid}[mode]
+    T = len(preds)
+    masks = torch.stack([p.pred_masks[box] for p in preds])
+    pool = engine.pack_masks(masks.to(DEV))
+    for frame in (0, 6):
+        want = _oracle_job(preds, frame, box, ocfg, mode, grid)
+        res, batch = _device_job(preds, frame, box, cfg, mode, grid, pool, frame, list(range(T)), tile)
+        _check_pass(res, batch, want, masks.numpy() > 0.5, cfg.width)
+
+
+def test_odd_resolution_and_many_candidates():
+    """W not a multiple of 32, scaled intrinsics, a 97-candidate grid, ragged targets."""
+    H, W = 150, 200
+    cfg = OptConfig.scaled(W, H)
+    ocfg = restated.OracleConfig(height=H, width=W, focal_length=cfg.focal_length)
+    preds, _ = synth.make_video(5, 2, 9, cfg, kinds=[0, 0])
+    grid = np.linspace(-1.2, 2.0, 97)
+    masks = torch.cat([torch.stack([p.pred_masks[b] for p in preds]) for b in (0, 1)])
+    pool = engine.pack_masks(masks.to(DEV))
+    want = _oracle_job(preds, 4, 1, ocfg, _lib.MODE_SEQ, grid)
+    tg = [0, 3, 9, 10, 11, 17, 4]
+    res, batch = _device_job(preds, 4, 1, cfg, _lib.MODE_SEQ, grid, pool, 9 + 4, tg)
+    _check_pass(res, batch, want, (masks.numpy() > 0.5)[tg], W)
+
+
+def test_edge_cases_empty_source_degenerate_axis_behind_camera():
+    cfg, ocfg = OptConfig(), restated.OracleConfig()
+    preds, _ = synth.make_video(8, 1, 10, kinds=[0])
+    T = len(preds)
+    # (1) empty source mask: every candidate is empty, IoU = 0/|T|; with an empty target 0/0 = NaN -> index 0
+    p = synth.clone_preds(preds)
+    p[2].pred_masks[0].zero_()
+    p[3].pred_masks[0].zero_()
+    masks = torch.stack([q.pred_masks[0] for q in p])
+    pool = engine.pack_masks(masks.to(DEV))
+    want = _oracle_job(p, 2, 0, ocfg, _lib.MODE_SEQ, cfg.rot_cluster_grid)
+    assert not want.any()
+    res, batch = _device_job(p, 2, 0, cfg, _lib.MODE_SEQ, cfg.rot_cluster_grid, pool, 2, list(range(T)))
+    _check_pass(res, batch, want, masks.numpy() > 0.5, cfg.width)
+    assert np.isnan(res.best_iou[3].item()) and res.best_cand[3].item() == 0
+    # (2a) axis line that misses the image -> fallback end-points [0,0,1,1]
+    p = synth.clone_preds(preds)
+    p[1].pred_rot_axis[0] = torch.tensor([0.6, 0.8, 50.0])
+    geo = geometry.source_geometry(p[1], 0, cfg, False)
+    assert geo.pts[0].tolist() == [0, 0, 1, 1]
+    want = _oracle_job(p, 1, 0, ocfg, _lib.MODE_COMPOSED, cfg.rot_final_grid)
+    masks = torch.stack([q.pred_masks[0] for q in p])
+    pool = engine.pack_masks(masks.to(DEV))
+    res, batch = _device_job(p, 1, 0, cfg, _lib.MODE_COMPOSED, cfg.rot_final_grid, pool, 1, list(range(T)))
+    _check_pass(res, batch, want, masks.numpy() > 0.5, cfg.width)
+    # (2b) coincident end-points give a NaN direction, hence NaN transforms: every point
+    #      lands on pixel (0,0) (NaN -> INT64_MIN -> clamp 0); same for +-inf / huge entries
+    g = restated.source_geometry(p[0], 0, ocfg, False)
+    for bad in (np.nan, np.inf, 1e30):
+        xf = np.zeros((3, 12), np.float32)
+        xf[:, [0, 4, 8]] = 1.0
+        xf[1, :9] = bad
+        xf[2, 9:] = bad
+        pts = restated.transform_composed(g["pcd"], xf[:, :9].reshape(3, 3, 3), xf[:, 9:])
+        row, col = restated.project_pixels(pts, ocfg, cfg.height, cfg.width)
+        want = restated.splat(row, col, cfg.height, cfg.width).numpy() > 0.5
+        b = engine.build_batch([0], [_lib.MODE_COMPOSED], [g["normal"].numpy()], [float(g["offset"])],
+                               [np.zeros(3, np.float32)], [xf], [list(range(T))])
+        res = engine.run_pass(cfg, pool, engine.DeviceBatch(b, DEV), want_table=True)
+        _check_pass(res, b, want, masks.numpy() > 0.5, cfg.width)
+    # (3) plane nearly edge-on: points cross Z <= 0 and project mirrored / clamp to the border
+    p = synth.clone_preds(preds)
+    p[4].pred_planes[0] = torch.tensor([1.2, 0.05, 0.02])
+    for mode, grid in ((_lib.MODE_SEQ, cfg.rot_cluster_grid), (_lib.MODE_TRANSLATE, cfg.trans_grid)):
+        want = _oracle_job(p, 4, 0, ocfg, mode, grid)
+        res, batch = _device_job(p, 4, 0, cfg, mode, grid, pool, 4, list(range(T)))
+        _check_pass(res, batch, want, masks.numpy() > 0.5, cfg.width)
+
+
+def test_many_jobs_one_pass_equals_single_jobs():
+    cfg = OptConfig()
+    preds, _ = synth.make_video(13, 4, 12, kinds=[0, 0, 1, 0])
+    masks = torch.cat([torch.stack([p.pred_masks[b] for p in preds]) for b in range(4)])
+    pool = engine.pack_masks(masks.to(DEV))
+    specs, singles = [], []
+    rng = np.random.RandomState(0)
+    for b in range(4):
+        trans = (b == 2)
+        frame = int(rng.randint(12))
+        geo = geometry.source_geometry(preds[frame], b, cfg, trans)
+        if trans:
+            mode, xf = _lib.MODE_TRANSLATE, geometry.xforms_translate(cfg.trans_grid, geo.dir_vec)
+        else:
+            mode, xf = _lib.MODE_SEQ, geometry.xforms_seq(geometry.rotation_matrices(cfg.rot_cluster_grid, geo.dir_vec))
+        tg = sorted(rng.choice(12, size=int(rng.randint(1, 12)), replace=False) + 12 * b)
+        specs.append((12 * b + frame, mode, geo.normal.numpy(), float(geo.offset), geo.pivot, xf, list(tg)))
+    cols = list(zip(*specs))
+    batch = engine.build_batch(*cols)
+    res = engine.run_pass(cfg, pool, engine.DeviceBatch(batch, DEV), want_table=True)
+    all_cand, all_inter, all_tab = res.best_cand.cpu().numpy().copy(), res.best_inter.cpu().numpy().copy(), res.inter_tab.cpu().numpy().copy()
+    for j, s in enumerate(specs):
+        b1 = engine.build_batch(*[[c] for c in s])
+        r1 = engine.run_pass(cfg, pool, engine.DeviceBatch(b1, DEV), want_table=True)
+        a, n = int(batch.jobs[j]["tgt_begin"]), int(batch.jobs[j]["n_tgt"])
+        assert np.array_equal(all_cand[a:a + n], r1.best_cand.cpu().numpy())
+        assert np.array_equal(all_inter[a:a + n], r1.best_inter.cpu().numpy())
+        t0, tn = int(batch.jobs[j]["tab_begin"]), n * int(batch.jobs[j]["n_cand"])
+        assert np.array_equal(all_tab[t0:t0 + tn], r1.inter_tab.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", gu.golden_cases())
+def test_optimize_planes_matches_reference_golden(name):
+    """End to end through the drop-in API against outputs of the unmodified reference."""
+    z = gu.load(name)
+    preds = gu.arrays_to_preds(z, Instances, Boxes)
+    random.seed(int(z["seed"]))
+    planes = opt_utils.track_planes(preds)
+    stats = opt_utils.Stats()
+    out = opt_utils.optimize_planes(preds, planes, '3dc', device=DEV, stats=stats)
+    gu.check_against_golden(z, planes, out)
+    assert stats.units_visited > 0 and stats.units_computed >= stats.units_visited
+
+
+@pytest.mark.parametrize("seed,n_tracks,n_frames,drop", [(41, 4, 30, 0.0), (42, 5, 24, 0.1)])
+def test_optimize_planes_matches_oracle(seed, n_tracks, n_frames, drop):
+    preds, _ = synth.make_video(seed, n_tracks, n_frames, drop_prob=drop)
+    a, b = synth.clone_preds(preds), synth.clone_preds(preds)
+    random.seed(seed)
+    planes = opt_utils.track_planes(a)
+    out = opt_utils.optimize_planes(a, planes, '3dc', device=DEV)
+    random.seed(seed)
+    planes_o = restated.track_planes(b)
+    trace = []
+    out_o = restated.optimize_planes(b, planes_o, '3dc', trace=trace)
+    finals = {(t['kind'], t['track']): t for t in trace if t['phase'] == 'final'}
+    for cat in ("trans", "rot"):
+        assert len(planes[cat]) == len(planes_o[cat])
+        for i, (p, q) in enumerate(zip(planes[cat], planes_o[cat])):
+            assert p['ids'] == q['ids'] and p['has_rot'] == q['has_rot']
+            np.testing.assert_allclose(p['fit']['rsq'], q['rsqs'], rtol=1e-12, equal_nan=True)
+            if not p['has_rot']:
+                continue
+            assert torch.equal(torch.as_tensor(p['std_axis']), torch.as_tensor(q['std_axis']))
+            fin = finals[(cat, i)]
+            assert p['fit']['center_frame'] == fin['source']
+            assert [v['frame'] for v in fin['visits']] == p['fit']['frames']
+            for k, v in enumerate(fin['visits']):
+                assert p['fit']['angle_id'][k] == v['angle_id']
+                assert p['fit']['inter'][k] == v['inter'][v['angle_id']]
+                assert p['fit']['union'][k] == v['union'][v['angle_id']]
+                assert np.array_equal(p['fit']['iou'][k], v['iou'][v['angle_id']], equal_nan=True)
+            dense = p['reg_masks'].dense(torch.uint8).cpu().numpy().astype(bool)
+            for k, f in enumerate(p['fit']['frames']):
+                assert np.array_equal(dense[k], q['reg_masks'][f].numpy() > 0.5)
+            if 'reg_normals' in q:
+                for f in q['reg_normals']:
+                    np.testing.assert_allclose(p['reg_normals'][f].numpy(), q['reg_normals'][f].numpy(),
+                                               rtol=1e-4, atol=1e-6)
+    for x, y in zip(out, out_o):
+        assert np.array_equal(x.scores, y.scores)
+        np.testing.assert_allclose(x.pred_rot_axis.numpy(), y.pred_rot_axis.numpy(), rtol=1e-4, atol=1e-7)
+        np.testing.assert_allclose(x.pred_tran_axis.numpy(), y.pred_tran_axis.numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_legacy_and_average_methods_match_oracle():
+    preds, _ = synth.make_video(51, 2, 14, kinds=[0, 0])
+    for method in ("3d", "average"):
+        a, b = synth.clone_preds(preds), synth.clone_preds(preds)
+        random.seed(1)
+        pa = opt_utils.track_planes(a)['rot']
+        oa = opt_utils.optimize_planes(a, pa, method, device=DEV)
+        random.seed(1)
+        pb = restated.track_planes(b)['rot']
+        ob = restated.optimize_planes(b, pb, method)
+        for p, q in zip(pa, pb):
+            assert torch.equal(torch.as_tensor(p['std_axis']), torch.as_tensor(q['std_axis']))
+            if method == "3d":
+                assert p['has_rot'] == q['has_rot']
+                for f in q.get('reg_masks', {}):
+                    assert torch.equal(p['reg_masks'][f] > 0.5, q['reg_masks'][f] > 0.5)
+        for x, y in zip(oa, ob):
+            assert np.array_equal(np.asarray(x.scores), np.asarray(y.scores))
+            assert torch.equal(x.pred_rot_axis, y.pred_rot_axis)
+
+
+def test_optimize_videos_equals_per_video_calls():
+    vids, seeds = [], [5, 6, 7]
+    for s in seeds:
+        preds, _ = synth.make_video(100 + s, 3, 16, kinds=[0, 1, 0])
+        vids.append(preds)
+    singles = []
+    for s, preds in zip(seeds, vids):
+        p = synth.clone_preds(preds)
+        random.seed(s)
+        planes = opt_utils.track_planes(p)
+        singles.append((opt_utils.optimize_planes(p, planes, '3dc', device=DEV), planes))
+    batch_in = []
+    for preds in vids:
+        p = synth.clone_preds(preds)
+        batch_in.append((p, opt_utils.track_planes(p)))
+    stats = opt_utils.Stats()
+    outs = opt_utils.optimize_videos(batch_in, seeds, device=DEV, stats=stats)
+    assert stats.passes < sum(1 for _ in range(3)) * 40
+    for (o1, pl1), o2, (_, pl2) in zip(singles, outs, batch_in):
+        for cat in ("trans", "rot"):
+            for p, q in zip(pl1[cat], pl2[cat]):
+                assert p['has_rot'] == q['has_rot']
+                if p['has_rot']:
+                    assert np.array_equal(p['fit']['angle_id'], q['fit']['angle_id'])
+                    assert np.array_equal(p['fit']['inter'], q['fit']['inter'])
+        for x, y in zip(o1, o2):
+            assert np.array_equal(x.scores, y.scores)
+            assert torch.equal(x.pred_rot_axis, y.pred_rot_axis)
+            assert torch.equal(x.pred_tran_axis, y.pred_tran_axis)

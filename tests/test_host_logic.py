@@ -1,0 +1,161 @@
+"""CPU tests of the host-side logic and of the C-ABI library's surface (no GPU)."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from articulation3d_b200 import OptConfig, _lib, axis, engine, geometry, opt_utils, synth
+from articulation3d_b200.structures import Boxes, Instances, pairwise_iou
+from oracle import restated
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "a3d.h")).read()
+    declared = set(re.findall(r"\b(a3d_[a-z_0-9]+)\s*\(", header))
+    declared = {d for d in declared if not d.endswith("_t")}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.a3d_version() == 100
+    for W in (1, 31, 32, 33, 100, 640, 1024, 1025):
+        assert lib.a3d_pitch_words(W) == _lib.pitch_words(W)
+        assert _lib.pitch_words(W) % 4 == 0 and _lib.pitch_words(W) * 32 >= W
+    assert ctypes.sizeof(_lib.Camera) == 9 * 8 + 3 * 4 + 2 * 4 + 4   # padded to 8
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    preds, _ = synth.make_video(1, 1, 12, kinds=[0])
+    planes = opt_utils.track_planes(preds)
+    with pytest.raises(_lib.A3DError):
+        opt_utils.optimize_planes(preds, planes, '3dc')
+    with pytest.raises(_lib.A3DError):
+        engine.pack_masks(torch.zeros(1, 8, 8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "articulation3d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_axis_functions_match_oracle(seed):
+    g = torch.Generator().manual_seed(seed)
+    n = 64
+    ang = torch.rand(n, generator=g) * 2 * np.pi
+    ao = torch.stack([torch.sin(ang), torch.cos(ang), torch.rand(n, generator=g) * 3 - 0.5], 1)
+    ao[0, 0] = 0.0            # sin == 0 branch
+    ao[1, 1] = 0.0            # horizontal line
+    ao[2] = torch.tensor([0.6, 0.8, 50.0])   # misses the image -> fallback
+    ce = torch.rand(n, 2, generator=g) * torch.tensor([640.0, 480.0])
+    got = axis.angle_offset_to_axis(ao, ce)
+    want = restated.angle_offset_to_axis(ao.numpy(), ce.numpy())
+    assert torch.equal(got, want)
+    lines = got.tolist()
+    a = axis.axis_to_angle_offset(lines, ce)
+    b = restated.axis_to_angle_offset(lines, ce)
+    assert torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+
+
+def test_track_planes_matches_oracle():
+    for seed, drop in ((4, 0.0), (9, 0.15), (10, 0.3)):
+        preds, _ = synth.make_video(seed, 5, 26, drop_prob=drop)
+        a = opt_utils.track_planes(preds)
+        b = restated.track_planes(preds)
+        for cat in ("rot", "trans"):
+            assert [p['ids'] for p in a[cat]] == [p['ids'] for p in b[cat]]
+            assert [p['latest_frame'] for p in a[cat]] == [p['latest_frame'] for p in b[cat]]
+
+
+def test_pairwise_iou_and_instances():
+    b1 = Boxes(torch.tensor([[0., 0., 10., 10.], [5., 5., 6., 6.]]))
+    b2 = Boxes(torch.tensor([[5., 5., 15., 15.], [20., 20., 30., 30.]]))
+    iou = pairwise_iou(b1, b2)
+    assert iou.shape == (2, 2) and abs(iou[0, 0].item() - 25 / 175) < 1e-7 and iou[0, 1] == 0
+    inst = Instances((480, 640))
+    inst.scores = np.ones(2)
+    with pytest.raises(AssertionError):
+        inst.pred_classes = np.ones(3)
+    with pytest.raises(AttributeError):
+        inst.nope
+
+
+def test_source_geometry_and_transforms_match_oracle():
+    cfg, ocfg = OptConfig(), restated.OracleConfig()
+    preds, _ = synth.make_video(21, 3, 12, kinds=[0, 1, 0])
+    for frame, box, trans in ((0, 0, False), (5, 2, False), (7, 1, True)):
+        geo = geometry.source_geometry(preds[frame], box, cfg, trans)
+        ref = restated.source_geometry(preds[frame], box, ocfg, trans)
+        assert torch.equal(geo.normal, ref["normal"]) and torch.equal(geo.offset, ref["offset"])
+        assert torch.equal(geo.pts, ref["pts"])
+        assert np.array_equal(geo.axis3d, ref["axis3d"]) and np.array_equal(geo.dir_vec, ref["dir_vec"])
+        R = geometry.rotation_matrices(cfg.rot_cluster_grid, geo.dir_vec)
+        assert np.array_equal(R, restated.rotation_matrices(ocfg.rot_cluster_grid, ref["dir_vec"]))
+        a = ref["axis3d"][0].astype(np.float32)
+        xf = geometry.xforms_composed(R, geo.pivot)
+        assert np.array_equal(xf[:, 9:], restated.composed_last_row(a, R))
+        xt = geometry.xforms_translate(cfg.trans_grid, geo.dir_vec)
+        assert np.array_equal(xt[:, 9:], restated.translation_vectors(ocfg.trans_grid, ref["dir_vec"]))
+        assert torch.equal(geometry.transform_normals(geo.normal, R), restated.transform_normals(ref["normal"], R))
+    # batched form used by the benchmark: (S, A, ...) equals S single calls
+    d = np.stack([geometry.source_geometry(preds[f], 0, cfg, False).dir_vec for f in range(4)])
+    Rb = geometry.rotation_matrices(cfg.rot_final_grid, d)
+    for i in range(4):
+        assert np.array_equal(Rb[i], geometry.rotation_matrices(cfg.rot_final_grid, d[i]))
+    piv = np.random.RandomState(0).randn(4, 3).astype(np.float32)
+    xb = geometry.xforms_composed(Rb, piv)
+    for i in range(4):
+        assert np.array_equal(xb[i], geometry.xforms_composed(Rb[i], piv[i]))
+
+
+def test_build_batch_layout():
+    xf = [np.zeros((3, 12), np.float32), np.ones((5, 12), np.float32)]
+    b = engine.build_batch([7, 9], [0, 2], [np.arange(3), np.ones(3)], [1.5, 2.5],
+                           [np.zeros(3), np.ones(3)], xf, [[1, 2], [3, 4, 5, 6]])
+    assert b.jobs.dtype.itemsize == 64 and b.jobs.tobytes().__len__() == 128
+    assert list(b.jobs["cand_begin"]) == [0, 3] and list(b.jobs["tgt_begin"]) == [0, 2]
+    assert list(b.jobs["tab_begin"]) == [0, 6] and b.units == 3 * 2 + 5 * 4
+    assert b.xform.shape == (8, 12) and b.tgt_index.tolist() == [1, 2, 3, 4, 5, 6]
+    raw = np.frombuffer(b.jobs.tobytes(), dtype=np.int32).reshape(2, 16)
+    assert raw[1, 0] == 9 and raw[1, 1] == 2 and raw[1, 3] == 5 and raw[1, 5] == 4
+    assert np.frombuffer(b.jobs.tobytes(), dtype=np.float32).reshape(2, 16)[1, 9] == 2.5
+
+
+def test_removal_quirk_known_answer():
+    """App. A #18: with every visited frame an inlier a T-frame track is visited
+    ceil(n/2) times per round: 60 -> 30, 15, 8, 4, 2 = 59 visits."""
+    cfg = OptConfig()
+    T = 60
+    preds, _ = synth.make_video(2, 1, 12, kinds=[0])
+    preds = [preds[i % 12] for i in range(T)]
+    plane = {'ids': {i: 0 for i in range(T)}, 'bbox': None, 'latest_frame': T - 1}
+    stats = opt_utils.Stats()
+    pool_of = {(i, 0): i for i in range(T)}
+    gen = opt_utils._tracks_gen(preds, [plane], cfg, False, random.Random(0), pool_of, stats)
+    spec = next(gen)
+    visits = []
+    try:
+        while True:
+            n = len(spec.targets)
+            visits.append(n)
+            res = opt_utils.JobResult(np.arange(n, dtype=np.int32) % len(spec.xform),
+                                      np.full(n, 0.9, np.float32), np.ones(n, np.int32), np.ones(n, np.int32),
+                                      masks=torch.zeros(n, 1, 4, dtype=torch.int32))
+            spec = gen.send(res)
+    except StopIteration:
+        pass
+    assert visits[:5] == [60, 30, 15, 7, 3]          # id_list sizes handed to the device
+    A = len(cfg.rot_cluster_grid)
+    assert stats.units_visited == (30 + 15 + 8 + 4 + 2) * A + T * len(cfg.rot_final_grid)
