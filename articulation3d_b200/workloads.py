@@ -54,6 +54,8 @@ WORKLOADS = {
     # configs[2] per-GPU shard at 8 GPUs (256 videos / 8), and the whole thing on one GPU
     "c3_shard": Workload("c3_shard", "batched opt_arti shard: 32 videos x 8 tracks x 120 frames, 180-angle grid",
                          32, 8, 120, 180),
+    "c3_mini": Workload("c3_mini", "profiling slice: 8 videos x 8 tracks x 120 frames, 180-angle grid",
+                        8, 8, 120, 180),
     "c3": Workload("c3", "batched opt_arti: 256 videos x 8 tracks x 120 frames, 180-angle grid",
                    256, 8, 120, 180),
     # configs[3] per-GPU shard: 1024x768, 720 rotation candidates (translation candidates are a second pass)

@@ -159,3 +159,15 @@ def test_removal_quirk_known_answer():
     assert visits[:5] == [60, 30, 15, 7, 3]          # id_list sizes handed to the device
     A = len(cfg.rot_cluster_grid)
     assert stats.units_visited == (30 + 15 + 8 + 4 + 2) * A + T * len(cfg.rot_final_grid)
+
+
+def test_source_geometry_matches_oracle_at_other_resolutions():
+    for (W, H) in ((200, 150), (1024, 768)):
+        cfg = OptConfig.scaled(W, H)
+        ocfg = restated.OracleConfig(height=H, width=W, focal_length=cfg.focal_length)
+        preds, _ = synth.make_video(5, 2, 9, cfg, kinds=[0, 1])
+        for box, trans in ((0, False), (1, True)):
+            geo = geometry.source_geometry(preds[4], box, cfg, trans)
+            ref = restated.source_geometry(preds[4], box, ocfg, trans)
+            assert torch.equal(geo.pts, ref["pts"])
+            assert np.array_equal(geo.axis3d, ref["axis3d"]) and np.array_equal(geo.dir_vec, ref["dir_vec"])
