@@ -24,15 +24,15 @@ class Camera(C.Structure):
                 ("H", C.c_int32), ("W", C.c_int32)]
 
 
-# a3d_job_t as a numpy structured dtype (64 bytes, C layout)
+# a3d_job_t as a numpy structured dtype (72 bytes, C layout)
 JOB_DTYPE = np.dtype([
     ("src_mask", "<i4"), ("mode", "<i4"), ("cand_begin", "<i4"), ("n_cand", "<i4"),
     ("tgt_begin", "<i4"), ("n_tgt", "<i4"),
     ("normal", "<f4", (3,)), ("offset", "<f4"),
-    ("pivot", "<f4", (3,)), ("pad0", "<f4"),
-    ("tab_begin", "<i8"),
+    ("pivot", "<f4", (3,)), ("pcd_cap", "<i4"),
+    ("tab_begin", "<i8"), ("pcd_begin", "<i8"),
 ], align=True)
-assert JOB_DTYPE.itemsize == 64, JOB_DTYPE.itemsize
+assert JOB_DTYPE.itemsize == 72, JOB_DTYPE.itemsize
 
 # every symbol include/a3d.h declares
 EXPORTS = (
@@ -71,7 +71,7 @@ def load():
     lib.a3d_mask_meta.restype = C.c_int
     lib.a3d_mask_meta.argtypes = [vp, i64, i32, i32, vp, vp, vp]
     lib.a3d_project.restype = C.c_int
-    lib.a3d_project.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.a3d_project.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.a3d_score.restype = C.c_int
     lib.a3d_score.argtypes = [i32, i32, vp, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                               vp, vp, vp, vp, vp]

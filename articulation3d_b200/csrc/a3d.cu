@@ -151,8 +151,106 @@ __global__ void __launch_bounds__(256) k_mask_meta(const uint32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// project: unproject -> transform -> project -> splat, one CTA per
-// (job, candidate tile); the tile's bit-masks live in shared memory.
+// unproject: source mask -> compacted fp32 point cloud (get_pcd, vis.py:86-102).
+// One CTA per job.  Phase 1: exclusive prefix of the per-word popcounts of the
+// source bounding box (row-major = the reference's nonzero() order).  Phase 2:
+// one warp per word, one lane per pixel: float64 ray/plane intersection, one
+// rounding to fp32, store at prefix + rank.  Output slice of job j:
+// X | Y | Z planes of pcd_cap floats each, starting at 3 * pcd_begin.
+// ---------------------------------------------------------------------------
+constexpr int kUnprojThreads = 256;
+
+template <bool kSparseK>
+__global__ void __launch_bounds__(kUnprojThreads)
+k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* __restrict__ src_bits,
+            const int32_t* __restrict__ src_bbox, float* __restrict__ pcd, int32_t* __restrict__ pcd_count) {
+    extern __shared__ uint32_t prefix[];            // one entry per word of the source box
+    __shared__ uint32_t warp_sum[kUnprojThreads / 32];
+    __shared__ uint32_t total_s;
+    const a3d_job_t job = jobs[blockIdx.x];
+    const int pitch = cam.pitch;
+    const int32_t* sb = src_bbox + 4 * (size_t)job.src_mask;
+    const int r0 = sb[0], r1 = sb[1], w0 = sb[2], w1 = sb[3];
+    if (r1 < r0) {
+        if (threadIdx.x == 0) pcd_count[blockIdx.x] = 0;
+        return;
+    }
+    const uint32_t* src = src_bits + (size_t)job.src_mask * cam.H * pitch;
+    const int ncols = w1 - w0 + 1, nwords = (r1 - r0 + 1) * ncols;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // phase 1: block-wide exclusive scan, each thread owns a contiguous chunk of words
+    const int chunk = (nwords + kUnprojThreads - 1) / kUnprojThreads;
+    const int wb = min(nwords, (int)threadIdx.x * chunk), we = min(nwords, wb + chunk);
+    uint32_t mine = 0;
+    for (int w = wb; w < we; ++w) {
+        const int rr = w / ncols;
+        mine += __popc(src[(r0 + rr) * pitch + w0 + (w - rr * ncols)]);
+    }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t base = incl - mine;
+    for (int i = 0; i < warp; ++i) base += warp_sum[i];
+    if (threadIdx.x == kUnprojThreads - 1) total_s = base + mine;
+    for (int w = wb; w < we; ++w) {
+        const int rr = w / ncols;
+        prefix[w] = base;
+        base += __popc(src[(r0 + rr) * pitch + w0 + (w - rr * ncols)]);
+    }
+    __syncthreads();
+
+    // phase 2
+    const int cap = job.pcd_cap;
+    float* Xp = pcd + 3 * job.pcd_begin;
+    float* Yp = Xp + cap;
+    float* Zp = Yp + cap;
+    const double n0 = (double)job.normal[0], n1 = (double)job.normal[1], n2 = (double)job.normal[2];
+    const double off = (double)job.offset;
+    const float NaNf = __int_as_float(0x7fffffff);
+    for (int w = warp; w < nwords; w += kUnprojThreads / 32) {
+        const int rr = w / ncols;
+        const int row = r0 + rr, wc = w0 + (w - rr * ncols);
+        const uint32_t bits = src[row * pitch + wc];
+        if (!((bits >> lane) & 1u)) continue;
+        const int pos = (int)prefix[w] + __popc(bits & ((1u << lane) - 1u));
+        if (pos >= cap) continue;
+        const double xd = (double)(wc * 32 + lane), yd = (double)row;
+        double rx, ry, rz;
+        if (kSparseK) {
+            rx = __dadd_rn(__dmul_rn(cam.k[0], xd), cam.k[2]);
+            ry = __dadd_rn(__dmul_rn(cam.k[4], yd), cam.k[5]);
+            rz = 1.0;
+        } else {
+            rx = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[0], xd), __dmul_rn(cam.k[1], yd)), cam.k[2]);
+            ry = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[3], xd), __dmul_rn(cam.k[4], yd)), cam.k[5]);
+            rz = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[6], xd), __dmul_rn(cam.k[7], yd)), cam.k[8]);
+        }
+        const double dot = __dadd_rn(__dadd_rn(__dmul_rn(n0, rx), __dmul_rn(n1, ry)), __dmul_rn(n2, rz));
+        const double depth = __ddiv_rn(off, dot);
+        float x = __double2float_rn(__dmul_rn(depth, rx));
+        float y = __double2float_rn(__dmul_rn(depth, ry));
+        float z = __double2float_rn(__dmul_rn(depth, rz));
+        // a point with any non-finite coordinate leaves the first homogeneous transform
+        // all-NaN (every output mixes 0*coordinate terms)
+        if (!(fabsf(x) <= 3.402823466e38f && fabsf(y) <= 3.402823466e38f && fabsf(z) <= 3.402823466e38f)) {
+            x = NaNf; y = NaNf; z = NaNf;
+        }
+        Xp[pos] = x; Yp[pos] = y; Zp[pos] = z;
+    }
+    if (threadIdx.x == 0) pcd_count[blockIdx.x] = min((int)total_s, cap);
+}
+
+// ---------------------------------------------------------------------------
+// project: transform -> project -> splat, one CTA per (job, candidate tile); the
+// tile's bit-masks live in shared memory.  Each thread takes 8 consecutive points
+// of the compacted cloud (mostly one source row, so their images fall into one or
+// two destination words) and merges their bits in registers before one atomicOr.
 // ---------------------------------------------------------------------------
 
 // emulate `.long()` of an fp32 on x86 followed by the reference's clamp to
@@ -164,17 +262,18 @@ __device__ __forceinline__ int clamp_index(float v, int n) {
     return i;
 }
 
-constexpr int kProjThreads = 512;
+constexpr int kProjThreads = 1024;
+constexpr int kProjPX = 8;
 
-template <bool kSparseK>
 __global__ void __launch_bounds__(kProjThreads, 1)
-k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand,
-          const uint32_t* __restrict__ src_bits, const int32_t* __restrict__ src_bbox,
-          const float* __restrict__ xform, uint32_t* __restrict__ proj_bits,
+k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int tiles_per_job,
+          const float* __restrict__ xform, const float* __restrict__ pcd,
+          const int32_t* __restrict__ pcd_count, uint32_t* __restrict__ proj_bits,
           int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const a3d_job_t job = jobs[blockIdx.x];
-    const int c0 = blockIdx.y * tile_cand;
+    const int jid = blockIdx.x / tiles_per_job;
+    const a3d_job_t job = jobs[jid];
+    const int c0 = (blockIdx.x - jid * tiles_per_job) * tile_cand;
     const int nc = min(tile_cand, job.n_cand - c0);
     if (nc <= 0) return;
 
@@ -197,59 +296,28 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand,
     }
     __syncthreads();
 
-    const int32_t* sb = src_bbox + 4 * (size_t)job.src_mask;
-    const int r0 = sb[0], r1 = sb[1], w0 = sb[2], w1 = sb[3];
-    if (r1 >= r0) {
-        const uint32_t* src = src_bits + (size_t)job.src_mask * words;
-        const int ncols = w1 - w0 + 1;
-        const int nitems = (r1 - r0 + 1) * ncols * 4;       // one item = one byte = 8 pixels of a row
-        const double n0 = (double)job.normal[0], n1 = (double)job.normal[1], n2 = (double)job.normal[2];
-        const double off = (double)job.offset;
+    const int npts = pcd_count[jid];
+    if (npts > 0) {
+        const int cap = job.pcd_cap;
+        const float4* X4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin);
+        const float4* Y4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin + cap);
+        const float4* Z4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin + 2 * (size_t)cap);
         const float ax = job.pivot[0], ay = job.pivot[1], az = job.pivot[2];
         const int mode = job.mode;
-        const float NaNf = __int_as_float(0x7fffffff);
+        const int nitems = (npts + kProjPX - 1) / kProjPX;
 
         for (int item = threadIdx.x; item < nitems; item += kProjThreads) {
-            const int widx = item >> 2, byte = item & 3;
-            const int rr = widx / ncols;
-            const int row = r0 + rr, wc = w0 + (widx - rr * ncols);
-            const uint32_t bits8 = (src[row * pitch + wc] >> (8 * byte)) & 0xffu;
-            if (bits8 == 0) continue;
-
-            // ---- unproject 8 pixels (get_pcd, vis.py:96-100) in float64 -------------
-            float X[8], Y[8], Z[8];
-            const double yd = (double)row;
-            const int xbase = wc * 32 + byte * 8;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if ((bits8 >> k) & 1u) {
-                    const double xd = (double)(xbase + k);
-                    double rx, ry, rz;
-                    if (kSparseK) {
-                        rx = __dadd_rn(__dmul_rn(cam.k[0], xd), cam.k[2]);
-                        ry = __dadd_rn(__dmul_rn(cam.k[4], yd), cam.k[5]);
-                        rz = 1.0;
-                    } else {
-                        rx = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[0], xd), __dmul_rn(cam.k[1], yd)), cam.k[2]);
-                        ry = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[3], xd), __dmul_rn(cam.k[4], yd)), cam.k[5]);
-                        rz = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[6], xd), __dmul_rn(cam.k[7], yd)), cam.k[8]);
-                    }
-                    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(n0, rx), __dmul_rn(n1, ry)), __dmul_rn(n2, rz));
-                    const double depth = __ddiv_rn(off, dot);
-                    float x = __double2float_rn(__dmul_rn(depth, rx));
-                    float y = __double2float_rn(__dmul_rn(depth, ry));
-                    float z = __double2float_rn(__dmul_rn(depth, rz));
-                    // a point with any non-finite coordinate leaves the first homogeneous
-                    // transform all-NaN (every output mixes 0*coordinate terms)
-                    if (!(fabsf(x) <= 3.402823466e38f && fabsf(y) <= 3.402823466e38f &&
-                          fabsf(z) <= 3.402823466e38f)) { x = NaNf; y = NaNf; z = NaNf; }
-                    X[k] = x; Y[k] = y; Z[k] = z;
-                } else {
-                    X[k] = 0.f; Y[k] = 0.f; Z[k] = 0.f;
-                }
+            float X[kProjPX], Y[kProjPX], Z[kProjPX];
+            {
+                const float4 a = __ldg(X4 + 2 * item), b = __ldg(X4 + 2 * item + 1);
+                X[0] = a.x; X[1] = a.y; X[2] = a.z; X[3] = a.w; X[4] = b.x; X[5] = b.y; X[6] = b.z; X[7] = b.w;
+                const float4 c = __ldg(Y4 + 2 * item), d = __ldg(Y4 + 2 * item + 1);
+                Y[0] = c.x; Y[1] = c.y; Y[2] = c.z; Y[3] = c.w; Y[4] = d.x; Y[5] = d.y; Y[6] = d.z; Y[7] = d.w;
+                const float4 e = __ldg(Z4 + 2 * item), f = __ldg(Z4 + 2 * item + 1);
+                Z[0] = e.x; Z[1] = e.y; Z[2] = e.z; Z[3] = e.w; Z[4] = f.x; Z[5] = f.y; Z[6] = f.z; Z[7] = f.w;
             }
+            const int nvalid = min(kProjPX, npts - item * kProjPX);
 
-            // ---- every candidate of the tile ---------------------------------------
             for (int c = 0; c < nc; ++c) {
                 const float* m = xf + 12 * c;
                 const float R00 = m[0], R01 = m[1], R02 = m[2], R10 = m[3], R11 = m[4], R12 = m[5];
@@ -258,8 +326,8 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand,
                 int cur_wi = -1;
                 uint32_t cur_bits = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (!((bits8 >> k) & 1u)) continue;
+                for (int k = 0; k < kProjPX; ++k) {
+                    if (k >= nvalid) break;
                     float px = X[k], py = Y[k], pz = Z[k];
                     float sx, sy, sz;
                     if (mode == A3D_MODE_TRANSLATE) {
@@ -333,21 +401,26 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand,
 // (first maximum wins; NaN = 0/0 orders above every finite value, as in torch).
 // CTA = 8 warps = (2 target groups) x (4 candidate groups); each warp owns a
 // 4x4 register tile of (target, candidate) pairs and strides its lanes over the
-// words of the region.
+// words of the region, two words per step folded by a carry-save adder so that
+// one POPC (quarter-rate pipe) serves two words.  CTAs are ordered job-major so
+// one job's masks stay L2-resident while its tiles run.
 // ---------------------------------------------------------------------------
 constexpr int kScoreTT = 8;    // targets per CTA
 constexpr int kScoreCT = 16;   // candidates per CTA
 
 __global__ void __launch_bounds__(256)
-k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch,
+k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int ct_tiles,
         const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
         const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
         const uint32_t* __restrict__ proj_bits, const int32_t* __restrict__ proj_popc,
         const int32_t* __restrict__ proj_bbox, unsigned long long* __restrict__ key_ws,
         int32_t* __restrict__ inter_tab) {
-    const a3d_job_t job = jobs[blockIdx.x];
-    const int tb = blockIdx.y * kScoreTT;
-    const int cb = blockIdx.z * kScoreCT;
+    const int per_job = tt_tiles * ct_tiles;
+    const int jid = blockIdx.x / per_job;
+    const int rem = blockIdx.x - jid * per_job;
+    const a3d_job_t job = jobs[jid];
+    const int tb = (rem / ct_tiles) * kScoreTT;
+    const int cb = (rem % ct_tiles) * kScoreCT;
     if (tb >= job.n_tgt || cb >= job.n_cand) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = tb + (warp >> 2) * 4;
@@ -377,34 +450,54 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch,
     }
     const int ra = max(pr0, qr0), rb = min(pr1, qr1), ca = max(pc0, qc0), cbw = min(pc1, qc1);
 
-    int acc[4][4];
+    int acc2[4][4];           // number of carries (weight 2)
+    uint32_t ones[4][4];      // pending weight-1 bits
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[i][k] = 0;
+        for (int k = 0; k < 4; ++k) { acc2[i][k] = 0; ones[i][k] = 0u; }
 
     if (rb >= ra && cbw >= ca) {
         const int ncols = cbw - ca + 1;
         const int total = (rb - ra + 1) * ncols;
-        const int dr = 32 / ncols, dc = 32 - dr * ncols;
-        int r = lane / ncols, c = lane - r * ncols;
-        for (int idx = lane; idx < total; idx += 32) {
-            const int o = (ra + r) * pitch + ca + c;
-            uint32_t tw[4], pw[4];
+        // two word positions per step: idx and idx + 32, both advance by 64
+        const int dr = 64 / ncols, dc = 64 - dr * ncols;
+        int rA = lane / ncols, cA = lane - rA * ncols;
+        int rB = (lane + 32) / ncols, cB = (lane + 32) - rB * ncols;
+        for (int idx = lane; idx < total; idx += 64) {
+            const int oA = (ra + rA) * pitch + ca + cA;
+            const bool hasB = idx + 32 < total;
+            const int oB = hasB ? (ra + rB) * pitch + ca + cB : oA;
+            uint32_t tA[4], pA[4], tB[4], pB[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { tw[i] = __ldg(tp[i] + o); pw[i] = __ldg(pp[i] + o); }
+            for (int i = 0; i < 4; ++i) {
+                tA[i] = __ldg(tp[i] + oA); pA[i] = __ldg(pp[i] + oA);
+                tB[i] = __ldg(tp[i] + oB); pB[i] = __ldg(pp[i] + oB);
+            }
+            if (!hasB) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tB[i] = 0u;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[i][k] += __popc(tw[i] & pw[k]);
-            r += dr; c += dc;
-            if (c >= ncols) { c -= ncols; ++r; }
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t a = tA[i] & pA[k], b = tB[i] & pB[k], o = ones[i][k];
+                    ones[i][k] = o ^ a ^ b;                                   // sum   (LOP3)
+                    acc2[i][k] += __popc((o & a) | (o & b) | (a & b));        // carry (LOP3 + POPC)
+                }
+            rA += dr; cA += dc;
+            if (cA >= ncols) { cA -= ncols; ++rA; }
+            rB += dr; cB += dc;
+            if (cB >= ncols) { cB -= ncols; ++rB; }
         }
     }
+    int acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[i][k] = __reduce_add_sync(0xffffffffu, acc[i][k]);
+        for (int k = 0; k < 4; ++k)
+            acc[i][k] = __reduce_add_sync(0xffffffffu, 2 * acc2[i][k] + __popc(ones[i][k]));
 
     if (lane == 0) {
 #pragma unroll
@@ -555,11 +648,12 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W, int32_t* popc, 
 
 int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
                 int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,
-                const float* xform, uint32_t* proj_bits, int32_t* proj_popc,
-                int32_t* proj_bbox, void* stream) {
+                const float* xform, float* pcd_ws, int32_t* pcd_count,
+                uint32_t* proj_bits, int32_t* proj_popc, int32_t* proj_bbox, void* stream) {
     if (!cam || n_jobs < 0 || max_cand < 0) return fail(A3D_EINVAL, "a3d_project: bad argument");
     if (n_jobs == 0 || max_cand == 0) return A3D_OK;
-    if (!jobs || !src_bits || !src_bbox || !xform || !proj_bits || !proj_popc || !proj_bbox)
+    if (!jobs || !src_bits || !src_bbox || !xform || !pcd_ws || !pcd_count || !proj_bits || !proj_popc ||
+        !proj_bbox)
         return fail(A3D_EINVAL, "a3d_project: null pointer");
     const int max_tile = a3d_project_max_tile(cam->H, cam->W);
     if (max_tile < 0) return max_tile;
@@ -573,19 +667,29 @@ int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int 
     c.f = cam->f; c.cx = cam->cx; c.cy = cam->cy;
     c.H = cam->H; c.W = cam->W; c.pitch = pitch_words(cam->W);
     c.sparse = (c.k[1] == 0.0 && c.k[3] == 0.0 && c.k[6] == 0.0 && c.k[7] == 0.0 && c.k[8] == 1.0);
-
-    const size_t smem = project_smem_bytes(c.H, c.pitch, tile_cand);
-    const dim3 grid((unsigned)n_jobs, (unsigned)((max_cand + tile_cand - 1) / tile_cand));
     cudaStream_t s = (cudaStream_t)stream;
+
+    // 1. source pixels -> compacted point clouds
+    const size_t usmem = (size_t)c.H * c.pitch * sizeof(uint32_t);
+    if (usmem > (size_t)device_smem_optin())
+        return fail(A3D_ELIMIT, "a3d_project: %dx%d mask does not fit shared memory", c.H, c.W);
     if (c.sparse) {
-        A3D_CUDA_TRY(cudaFuncSetAttribute(k_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_project<true><<<grid, kProjThreads, smem, s>>>(c, jobs, tile_cand, src_bits, src_bbox, xform,
-                                                         proj_bits, proj_popc, proj_bbox);
+        A3D_CUDA_TRY(cudaFuncSetAttribute(k_unproject<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+        k_unproject<true><<<(unsigned)n_jobs, kUnprojThreads, usmem, s>>>(c, jobs, src_bits, src_bbox, pcd_ws, pcd_count);
     } else {
-        A3D_CUDA_TRY(cudaFuncSetAttribute(k_project<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_project<false><<<grid, kProjThreads, smem, s>>>(c, jobs, tile_cand, src_bits, src_bbox, xform,
-                                                          proj_bits, proj_popc, proj_bbox);
+        A3D_CUDA_TRY(cudaFuncSetAttribute(k_unproject<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+        k_unproject<false><<<(unsigned)n_jobs, kUnprojThreads, usmem, s>>>(c, jobs, src_bits, src_bbox, pcd_ws, pcd_count);
     }
+    A3D_CUDA_TRY(cudaGetLastError());
+
+    // 2. candidates
+    const size_t smem = project_smem_bytes(c.H, c.pitch, tile_cand);
+    const int tiles_per_job = (max_cand + tile_cand - 1) / tile_cand;
+    const long long nblocks = (long long)n_jobs * tiles_per_job;
+    if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_project: too many (job, tile) blocks");
+    A3D_CUDA_TRY(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_project<<<(unsigned)nblocks, kProjThreads, smem, s>>>(c, jobs, tile_cand, tiles_per_job, xform, pcd_ws,
+                                                           pcd_count, proj_bits, proj_popc, proj_bbox);
     A3D_CUDA_TRY(cudaGetLastError());
     return A3D_OK;
 }
@@ -608,11 +712,12 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
     const int pitch = pitch_words(W);
     cudaStream_t s = (cudaStream_t)stream;
     A3D_CUDA_TRY(cudaMemsetAsync(key_ws, 0, sizeof(uint64_t) * (size_t)n_tgt_total, s));
-    const dim3 grid((unsigned)n_jobs, (unsigned)((max_tgt + kScoreTT - 1) / kScoreTT),
-                    (unsigned)((max_cand + kScoreCT - 1) / kScoreCT));
-    if (grid.y > 65535 || grid.z > 65535) return fail(A3D_ELIMIT, "a3d_score: too many targets/candidates per job");
-    k_score<<<grid, 256, 0, s>>>(jobs, H, pitch, tgt_bits, tgt_popc, tgt_bbox, tgt_index, proj_bits,
-                                 proj_popc, proj_bbox, (unsigned long long*)key_ws, inter_tab);
+    const int tt_tiles = (max_tgt + kScoreTT - 1) / kScoreTT, ct_tiles = (max_cand + kScoreCT - 1) / kScoreCT;
+    const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
+    if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
+    k_score<<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc, tgt_bbox,
+                                              tgt_index, proj_bits, proj_popc, proj_bbox,
+                                              (unsigned long long*)key_ws, inter_tab);
     A3D_CUDA_TRY(cudaGetLastError());
     const dim3 fgrid((unsigned)n_jobs, (unsigned)((max_tgt + 7) / 8 < 64 ? (max_tgt + 7) / 8 : 64));
     k_finalize<<<fgrid, 256, 0, s>>>(jobs, H, pitch, tgt_bits, tgt_popc, tgt_index, proj_bits, proj_popc,

@@ -50,9 +50,20 @@ class MaskPool:
     W: int
     bits_nz: torch.Tensor | None = None   # bit = mask != 0 (source pixel lists), if it differs
     bbox_nz: torch.Tensor | None = None
+    popc_nz: torch.Tensor | None = None
+    _src_points: np.ndarray | None = None
 
     def __len__(self):
         return self.bits.shape[0]
+
+    @property
+    def source_points(self) -> np.ndarray:
+        """Host copy of the source-pixel counts (sizes the point-cloud workspace); one
+        D2H per pool, cached."""
+        if self._src_points is None:
+            t = self.popc if self.popc_nz is None else self.popc_nz
+            self._src_points = t.cpu().numpy().astype(np.int64)
+        return self._src_points
 
     @property
     def source_bits(self):
@@ -103,7 +114,7 @@ def pack_masks(masks: torch.Tensor, thresh: float = 0.5, with_nonzero: bool = Fa
             popc_nz, bbox_nz = mask_meta(nz, H, W)
             # identical for binary masks (the contract); keep the second copy only if needed
             if not torch.equal(popc_nz, popc):
-                pool.bits_nz, pool.bbox_nz = nz, bbox_nz
+                pool.bits_nz, pool.bbox_nz, pool.popc_nz = nz, bbox_nz, popc_nz
     return pool
 
 
@@ -133,14 +144,15 @@ class JobBatch:
         return int((self.jobs["n_cand"].astype(np.int64) * self.jobs["n_tgt"]).sum())
 
 
-def build_batch(sources, modes, normals, offsets, pivots, xforms, targets) -> JobBatch:
+def build_batch(sources, modes, normals, offsets, pivots, xforms, targets, src_points) -> JobBatch:
     """Assemble a JobBatch from per-job python/numpy pieces.
 
     sources[i] pool index; modes[i] MODE_*; normals[i] (3,), offsets[i], pivots[i] (3,);
-    xforms[i] (A_i, 12) fp32; targets[i] sequence of pool indices."""
+    xforms[i] (A_i, 12) fp32; targets[i] sequence of pool indices; src_points = per-mask
+    source pixel counts of the pool (``MaskPool.source_points``)."""
     n = len(sources)
     jobs = np.zeros(n, dtype=_lib.JOB_DTYPE)
-    cand = tgt = tab = 0
+    cand = tgt = tab = pcd = 0
     for i in range(n):
         a, t = len(xforms[i]), len(targets[i])
         jobs[i]["src_mask"] = sources[i]
@@ -151,6 +163,9 @@ def build_batch(sources, modes, normals, offsets, pivots, xforms, targets) -> Jo
         jobs[i]["offset"] = np.float32(offsets[i])
         jobs[i]["pivot"] = np.asarray(pivots[i], dtype=np.float32)
         jobs[i]["tab_begin"] = tab
+        cap = (int(src_points[sources[i]]) + 31) & ~31
+        jobs[i]["pcd_begin"], jobs[i]["pcd_cap"] = pcd, cap
+        pcd += cap
         cand += a
         tgt += t
         tab += a * t
@@ -184,6 +199,7 @@ class DeviceBatch:
         self.max_cand = int(batch.jobs["n_cand"].max()) if self.n_jobs else 0
         self.max_tgt = int(batch.jobs["n_tgt"].max()) if self.n_jobs else 0
         self.tab_total = int((batch.jobs["n_cand"].astype(np.int64) * batch.jobs["n_tgt"]).sum())
+        self.pcd_total = int(batch.jobs["pcd_cap"].astype(np.int64).sum())
         self.jobs = torch.from_numpy(batch.jobs.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
         self.xform = torch.from_numpy(batch.xform).to(device, non_blocking=True)
         self.tgt_index = torch.from_numpy(batch.tgt_index).to(device, non_blocking=True)
@@ -229,6 +245,8 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
         proj_bits = ws.get("proj_bits", (nc, H, pitch), torch.int32)
         proj_popc = ws.get("proj_popc", (nc,), torch.int32)
         proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
+        pcd_ws = ws.get("pcd_ws", (3 * dbatch.pcd_total,), torch.float32)
+        pcd_count = ws.get("pcd_count", (dbatch.n_jobs,), torch.int32)
         key_ws = ws.get("key_ws", (nt,), torch.int64)
         best_cand = ws.get("best_cand", (nt,), torch.int32)
         best_inter = ws.get("best_inter", (nt,), torch.int32)
@@ -242,8 +260,9 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
         tile = tile_cand if tile_cand is not None else choose_tile(cfg, nc)
         _lib.check(lib.a3d_project(C.byref(cam), dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_cand, tile,
                                    pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(),
-                                   dbatch.xform.data_ptr(), proj_bits.data_ptr(), proj_popc.data_ptr(),
-                                   proj_bbox.data_ptr(), stream), "a3d_project")
+                                   dbatch.xform.data_ptr(), pcd_ws.data_ptr(), pcd_count.data_ptr(),
+                                   proj_bits.data_ptr(), proj_popc.data_ptr(), proj_bbox.data_ptr(), stream),
+                   "a3d_project")
         _lib.check(lib.a3d_score(H, W, dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_tgt, dbatch.max_cand, nt,
                                  pool.bits.data_ptr(), pool.popc.data_ptr(), pool.bbox.data_ptr(),
                                  dbatch.tgt_index.data_ptr(), proj_bits.data_ptr(), proj_popc.data_ptr(),

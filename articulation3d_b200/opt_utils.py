@@ -355,7 +355,7 @@ class _Session:
         batch = engine.build_batch([s.source for s in specs], [s.mode for s in specs],
                                    [s.normal for s in specs], [s.offset for s in specs],
                                    [s.pivot for s in specs], [s.xform for s in specs],
-                                   [s.targets for s in specs])
+                                   [s.targets for s in specs], self.pool.source_points)
         dbatch = engine.DeviceBatch(batch, self.device)
         res = engine.run_pass(self.cfg, self.pool, dbatch, self.ws)
         packed = torch.stack([res.best_cand, res.best_inter, res.best_union,

@@ -109,7 +109,8 @@ def build_pass(wl: Workload, seed0: int, device, source_frame: int | None = None
     xf = geometry.xforms_seq(R)
     S = len(srcs)
     batch = engine.build_batch(srcs, [_lib.MODE_SEQ] * S, normals, offsets, pivots, list(xf),
-                               [np.arange(i * T, (i + 1) * T, dtype=np.int32) for i in range(S)])
+                               [np.arange(i * T, (i + 1) * T, dtype=np.int32) for i in range(S)],
+                               pool.source_points)
     dbatch = engine.DeviceBatch(batch, device)
     return PassInputs(cfg, pool, batch, dbatch, batch.units)
 

@@ -290,7 +290,7 @@ def gpu_arm(args, wl):
                        "l2": "flushed between steps (256 MiB write)" if flush is not None else "inputs exceed L2",
                        "parallelism": f"videos sharded x{world}, all_gather of 12 B/track-frame records" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 3 * args.steps, "clocks": clocks, "wall_s": wall,
+            "gpu_launches": 4 * args.steps, "clocks": clocks, "wall_s": wall,
         }
         print(json.dumps(line), flush=True)
     if dist:
@@ -312,6 +312,8 @@ def _run_split(engine, inp, ws, evs):
     proj_bits = ws.get("proj_bits", (nc, H, pitch), torch.int32)
     proj_popc = ws.get("proj_popc", (nc,), torch.int32)
     proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
+    pcd_ws = ws.get("pcd_ws", (3 * db.pcd_total,), torch.float32)
+    pcd_count = ws.get("pcd_count", (db.n_jobs,), torch.int32)
     key_ws = ws.get("key_ws", (nt,), torch.int64)
     outs = [ws.get(n, (nt,), dt) for n, dt in (("best_cand", torch.int32), ("best_inter", torch.int32),
                                                ("best_union", torch.int32), ("best_iou", torch.float32))]
@@ -320,6 +322,7 @@ def _run_split(engine, inp, ws, evs):
     tile = engine.choose_tile(cfg, nc)
     _lib.check(lib.a3d_project(C.byref(cam), db.jobs.data_ptr(), db.n_jobs, db.max_cand, tile,
                                pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(), db.xform.data_ptr(),
+                               pcd_ws.data_ptr(), pcd_count.data_ptr(),
                                proj_bits.data_ptr(), proj_popc.data_ptr(), proj_bbox.data_ptr(), stream),
                "a3d_project")
     if evs:

@@ -73,9 +73,11 @@ typedef struct {
     float   normal[3];       /* unit plane normal, camera frame (opt_utils.py:410)      */
     float   offset;          /* plane offset                      (opt_utils.py:411)    */
     float   pivot[3];        /* fp32 axis point a = Translate(verts_axis_3d[0]) (:420)  */
-    float   pad0;
+    int32_t pcd_cap;         /* capacity (points, multiple of 32) of this job's slice of
+                                the point-cloud workspace; >= popcount of the source    */
     int64_t tab_begin;       /* first element of this job's [n_tgt][n_cand] table       */
-} a3d_job_t;                 /* 64 bytes */
+    int64_t pcd_begin;       /* first point of this job's slice (multiple of 32)        */
+} a3d_job_t;                 /* 72 bytes */
 
 int         a3d_version(void);
 const char* a3d_last_error_string(void);
@@ -104,6 +106,8 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W,
 /* (a4-a7) unproject + transform + project + splat.  Replaces get_pcd
  * (vis.py:86-102), the Transform3d chain (opt_utils.py:420-435, 553-574,
  * 724-728), project2D (vis.py:71-75) and the splat loop (opt_utils.py:438-457).
+ * Two launches: k_unproject (source pixels -> compacted fp32 point cloud, float64
+ * ray/plane intersection) and k_project (transform, project, splat per candidate).
  *   cam        HOST
  *   jobs       [n_jobs] device
  *   max_cand   max over jobs of n_cand
@@ -111,12 +115,14 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W,
  *   src_bits   source mask pool, src_bbox its a3d_mask_meta boxes
  *   xform      [n_cand_total][12] fp32: rows 0-2 of R (row-vector convention,
  *              p' = p*R), then t
+ *   pcd_ws     workspace, 3 * sum(pcd_cap) floats (X|Y|Z planes per job slice)
+ *   pcd_count  workspace, [n_jobs] int32 (points actually produced per job)
  *   proj_bits  [n_cand_total][H][pitch]; proj_popc [n_cand_total];
  *   proj_bbox  [n_cand_total][4]                                               */
 int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
                 int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,
-                const float* xform, uint32_t* proj_bits, int32_t* proj_popc,
-                int32_t* proj_bbox, void* stream);
+                const float* xform, float* pcd_ws, int32_t* pcd_count,
+                uint32_t* proj_bits, int32_t* proj_popc, int32_t* proj_bbox, void* stream);
 
 /* (a8) mask-IoU scoring with fused arg-max over candidates.  Replaces the
  * `for idx in id_list` loops of opt_utils.py:464-477, 600-612, 757-770, 892-904.

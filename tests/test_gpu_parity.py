@@ -82,7 +82,7 @@ def _device_job(preds, frame, box, cfg, mode, grid, pool, src_idx, targets, tile
         R = geometry.rotation_matrices(grid, geo.dir_vec)
         xf = geometry.xforms_seq(R) if mode == _lib.MODE_SEQ else geometry.xforms_composed(R, geo.pivot)
     batch = engine.build_batch([src_idx], [mode], [geo.normal.numpy()], [float(geo.offset)], [geo.pivot],
-                               [xf], [targets])
+                               [xf], [targets], pool.source_points)
     res = engine.run_pass(cfg, pool, engine.DeviceBatch(batch, DEV), want_table=want_table, tile_cand=tile)
     torch.cuda.synchronize()
     return res, batch
@@ -177,7 +177,7 @@ def test_edge_cases_empty_source_degenerate_axis_behind_camera():
         row, col = restated.project_pixels(pts, ocfg, cfg.height, cfg.width)
         want = restated.splat(row, col, cfg.height, cfg.width).numpy() > 0.5
         b = engine.build_batch([0], [_lib.MODE_COMPOSED], [g["normal"].numpy()], [float(g["offset"])],
-                               [np.zeros(3, np.float32)], [xf], [list(range(T))])
+                               [np.zeros(3, np.float32)], [xf], [list(range(T))], pool.source_points)
         res = engine.run_pass(cfg, pool, engine.DeviceBatch(b, DEV), want_table=True)
         _check_pass(res, b, want, masks.numpy() > 0.5, cfg.width)
     # (3) plane nearly edge-on: points cross Z <= 0 and project mirrored / clamp to the border
@@ -207,11 +207,11 @@ def test_many_jobs_one_pass_equals_single_jobs():
         tg = sorted(rng.choice(12, size=int(rng.randint(1, 12)), replace=False) + 12 * b)
         specs.append((12 * b + frame, mode, geo.normal.numpy(), float(geo.offset), geo.pivot, xf, list(tg)))
     cols = list(zip(*specs))
-    batch = engine.build_batch(*cols)
+    batch = engine.build_batch(*cols, pool.source_points)
     res = engine.run_pass(cfg, pool, engine.DeviceBatch(batch, DEV), want_table=True)
     all_cand, all_inter, all_tab = res.best_cand.cpu().numpy().copy(), res.best_inter.cpu().numpy().copy(), res.inter_tab.cpu().numpy().copy()
     for j, s in enumerate(specs):
-        b1 = engine.build_batch(*[[c] for c in s])
+        b1 = engine.build_batch(*[[c] for c in s], pool.source_points)
         r1 = engine.run_pass(cfg, pool, engine.DeviceBatch(b1, DEV), want_table=True)
         a, n = int(batch.jobs[j]["tgt_begin"]), int(batch.jobs[j]["n_tgt"])
         assert np.array_equal(all_cand[a:a + n], r1.best_cand.cpu().numpy())
