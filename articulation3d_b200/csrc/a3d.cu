@@ -172,7 +172,7 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
     const int32_t* sb = src_bbox + 4 * (size_t)job.src_mask;
     const int r0 = sb[0], r1 = sb[1], w0 = sb[2], w1 = sb[3];
     if (r1 < r0) {
-        if (threadIdx.x == 0) pcd_count[blockIdx.x] = 0;
+        if (threadIdx.x == 0 && blockIdx.y == 0) pcd_count[blockIdx.x] = 0;
         return;
     }
     const uint32_t* src = src_bits + (size_t)job.src_mask * cam.H * pitch;
@@ -213,7 +213,9 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
     const double n0 = (double)job.normal[0], n1 = (double)job.normal[1], n2 = (double)job.normal[2];
     const double off = (double)job.offset;
     const float NaNf = __int_as_float(0x7fffffff);
-    for (int w = warp; w < nwords; w += kUnprojThreads / 32) {
+    // the words of the box are dealt round-robin to the warps of the gridDim.y CTAs of this job
+    const int wstride = (kUnprojThreads / 32) * gridDim.y;
+    for (int w = blockIdx.y * (kUnprojThreads / 32) + warp; w < nwords; w += wstride) {
         const int rr = w / ncols;
         const int row = r0 + rr, wc = w0 + (w - rr * ncols);
         const uint32_t bits = src[row * pitch + wc];
@@ -243,7 +245,7 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
         }
         Xp[pos] = x; Yp[pos] = y; Zp[pos] = z;
     }
-    if (threadIdx.x == 0) pcd_count[blockIdx.x] = min((int)total_s, cap);
+    if (threadIdx.x == 0 && blockIdx.y == 0) pcd_count[blockIdx.x] = min((int)total_s, cap);
 }
 
 // ---------------------------------------------------------------------------
@@ -256,14 +258,100 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
 // emulate `.long()` of an fp32 on x86 followed by the reference's clamp to
 // [0, n-1] (opt_utils.py:445-450): truncation toward zero; NaN, +-inf and
 // |v| >= 2^63 become INT64_MIN, which clamps to 0.
-__device__ __forceinline__ int clamp_index(float v, int n) {
-    int i = 0;
-    if (v >= 0.f) i = (v < (float)n) ? (int)v : ((v < 9.2233720368547758e18f) ? n - 1 : 0);
-    return i;
+__device__ __forceinline__ int clamp_index(float v, float n_minus_1) {
+    // fmaxf/fminf drop NaN operands: NaN -> 0; negatives -> 0; [n, 2^63) -> n-1.
+    float c = fminf(fmaxf(v, 0.f), n_minus_1);
+    c = (v < 9.2233720368547758e18f) ? c : 0.f;      // >= 2^63, +inf (and NaN, already 0) -> 0
+    return __float2int_rz(c);
 }
 
 constexpr int kProjThreads = 1024;
 constexpr int kProjPX = 8;
+
+// One candidate applied to up to 8 points held in registers; kMode is a compile-time
+// constant so the per-point code is straight-line.
+template <int kMode, bool kFull>
+__device__ __forceinline__ void splat_points(const float (&X)[kProjPX], const float (&Y)[kProjPX],
+                                             const float (&Z)[kProjPX], int nvalid, const float* __restrict__ m,
+                                             float ax, float ay, float az, float f, float cx, float cy,
+                                             float wmax, float hmax, int pitch, uint32_t* __restrict__ cm) {
+    const float R00 = m[0], R01 = m[1], R02 = m[2], R10 = m[3], R11 = m[4], R12 = m[5];
+    const float R20 = m[6], R21 = m[7], R22 = m[8], t0 = m[9], t1 = m[10], t2 = m[11];
+    int cur_wi = -1;
+    uint32_t cur_bits = 0;
+#pragma unroll
+    for (int k = 0; k < kProjPX; ++k) {
+        if (!kFull && k >= nvalid) break;
+        float px = X[k], py = Y[k], pz = Z[k];
+        float sx, sy, sz;
+        if (kMode == A3D_MODE_TRANSLATE) {
+            sx = __fadd_rn(px, t0); sy = __fadd_rn(py, t1); sz = __fadd_rn(pz, t2);
+        } else {
+            if (kMode == A3D_MODE_SEQ) {
+                px = __fsub_rn(px, ax); py = __fsub_rn(py, ay); pz = __fsub_rn(pz, az);
+            }
+            sx = __fadd_rn(__fadd_rn(__fmul_rn(px, R00), __fmul_rn(py, R10)), __fmul_rn(pz, R20));
+            sy = __fadd_rn(__fadd_rn(__fmul_rn(px, R01), __fmul_rn(py, R11)), __fmul_rn(pz, R21));
+            sz = __fadd_rn(__fadd_rn(__fmul_rn(px, R02), __fmul_rn(py, R12)), __fmul_rn(pz, R22));
+            if (kMode == A3D_MODE_SEQ) {
+                sx = __fadd_rn(sx, ax); sy = __fadd_rn(sy, ay); sz = __fadd_rn(sz, az);
+            } else {
+                sx = __fadd_rn(sx, t0); sy = __fadd_rn(sy, t1); sz = __fadd_rn(sz, t2);
+            }
+        }
+        // project2D (vis.py:72-75): K@p, then /w.  The 0*X, 0*Y terms only matter for
+        // non-finite inputs; keeping them in w reproduces those cases exactly.
+        const float u = __fadd_rn(__fmul_rn(f, sx), __fmul_rn(cx, sz));
+        const float v = __fadd_rn(__fmul_rn(f, sy), __fmul_rn(cy, sz));
+        const float w = __fadd_rn(__fmaf_rn(0.f, sx, __fmul_rn(0.f, sy)), sz);   // (0*X + 0*Y) is exactly 0 or NaN
+        const int col = clamp_index(__fdiv_rn(u, w), wmax);
+        const int rw = clamp_index(__fdiv_rn(v, w), hmax);
+        const int wi = rw * pitch + (col >> 5);
+        const uint32_t bm = 1u << (col & 31);
+        if (wi != cur_wi) {
+            if (cur_bits) atomicOr(cm + cur_wi, cur_bits);
+            cur_wi = wi;
+            cur_bits = bm;
+        } else {
+            cur_bits |= bm;
+        }
+    }
+    if (cur_bits) atomicOr(cm + cur_wi, cur_bits);
+}
+
+template <int kMode>
+__device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, int npts, int nc,
+                                          const float* __restrict__ pcd, const float* __restrict__ xf,
+                                          uint32_t* __restrict__ masks, int words) {
+    const int cap = job.pcd_cap;
+    const float4* X4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin);
+    const float4* Y4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin + cap);
+    const float4* Z4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin + 2 * (size_t)cap);
+    const float ax = job.pivot[0], ay = job.pivot[1], az = job.pivot[2];
+    const float wmax = (float)(cam.W - 1), hmax = (float)(cam.H - 1);
+    const int nitems = (npts + kProjPX - 1) / kProjPX;
+    for (int item = threadIdx.x; item < nitems; item += kProjThreads) {
+        float X[kProjPX], Y[kProjPX], Z[kProjPX];
+        {
+            const float4 a = __ldg(X4 + 2 * item), b = __ldg(X4 + 2 * item + 1);
+            X[0] = a.x; X[1] = a.y; X[2] = a.z; X[3] = a.w; X[4] = b.x; X[5] = b.y; X[6] = b.z; X[7] = b.w;
+            const float4 c = __ldg(Y4 + 2 * item), d = __ldg(Y4 + 2 * item + 1);
+            Y[0] = c.x; Y[1] = c.y; Y[2] = c.z; Y[3] = c.w; Y[4] = d.x; Y[5] = d.y; Y[6] = d.z; Y[7] = d.w;
+            const float4 e = __ldg(Z4 + 2 * item), g = __ldg(Z4 + 2 * item + 1);
+            Z[0] = e.x; Z[1] = e.y; Z[2] = e.z; Z[3] = e.w; Z[4] = g.x; Z[5] = g.y; Z[6] = g.z; Z[7] = g.w;
+        }
+        const int nvalid = npts - item * kProjPX;
+        if (nvalid >= kProjPX) {
+            for (int c = 0; c < nc; ++c)
+                splat_points<kMode, true>(X, Y, Z, kProjPX, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
+                                          wmax, hmax, cam.pitch, masks + (size_t)c * words);
+        } else {
+            for (int c = 0; c < nc; ++c)
+                splat_points<kMode, false>(X, Y, Z, nvalid, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
+                                           wmax, hmax, cam.pitch, masks + (size_t)c * words);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kProjThreads, 1)
 k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int tiles_per_job,
@@ -277,7 +365,7 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
     const int nc = min(tile_cand, job.n_cand - c0);
     if (nc <= 0) return;
 
-    const int H = cam.H, W = cam.W, pitch = cam.pitch;
+    const int H = cam.H, pitch = cam.pitch;
     const int words = H * pitch;
     uint32_t* masks = smem;                                        // [tile_cand][words]
     float* xf = reinterpret_cast<float*>(smem + (size_t)tile_cand * words);   // [tile_cand][12]
@@ -298,73 +386,9 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
 
     const int npts = pcd_count[jid];
     if (npts > 0) {
-        const int cap = job.pcd_cap;
-        const float4* X4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin);
-        const float4* Y4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin + cap);
-        const float4* Z4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin + 2 * (size_t)cap);
-        const float ax = job.pivot[0], ay = job.pivot[1], az = job.pivot[2];
-        const int mode = job.mode;
-        const int nitems = (npts + kProjPX - 1) / kProjPX;
-
-        for (int item = threadIdx.x; item < nitems; item += kProjThreads) {
-            float X[kProjPX], Y[kProjPX], Z[kProjPX];
-            {
-                const float4 a = __ldg(X4 + 2 * item), b = __ldg(X4 + 2 * item + 1);
-                X[0] = a.x; X[1] = a.y; X[2] = a.z; X[3] = a.w; X[4] = b.x; X[5] = b.y; X[6] = b.z; X[7] = b.w;
-                const float4 c = __ldg(Y4 + 2 * item), d = __ldg(Y4 + 2 * item + 1);
-                Y[0] = c.x; Y[1] = c.y; Y[2] = c.z; Y[3] = c.w; Y[4] = d.x; Y[5] = d.y; Y[6] = d.z; Y[7] = d.w;
-                const float4 e = __ldg(Z4 + 2 * item), f = __ldg(Z4 + 2 * item + 1);
-                Z[0] = e.x; Z[1] = e.y; Z[2] = e.z; Z[3] = e.w; Z[4] = f.x; Z[5] = f.y; Z[6] = f.z; Z[7] = f.w;
-            }
-            const int nvalid = min(kProjPX, npts - item * kProjPX);
-
-            for (int c = 0; c < nc; ++c) {
-                const float* m = xf + 12 * c;
-                const float R00 = m[0], R01 = m[1], R02 = m[2], R10 = m[3], R11 = m[4], R12 = m[5];
-                const float R20 = m[6], R21 = m[7], R22 = m[8], t0 = m[9], t1 = m[10], t2 = m[11];
-                uint32_t* cm = masks + (size_t)c * words;
-                int cur_wi = -1;
-                uint32_t cur_bits = 0;
-#pragma unroll
-                for (int k = 0; k < kProjPX; ++k) {
-                    if (k >= nvalid) break;
-                    float px = X[k], py = Y[k], pz = Z[k];
-                    float sx, sy, sz;
-                    if (mode == A3D_MODE_TRANSLATE) {
-                        sx = __fadd_rn(px, t0); sy = __fadd_rn(py, t1); sz = __fadd_rn(pz, t2);
-                    } else {
-                        if (mode == A3D_MODE_SEQ) {
-                            px = __fsub_rn(px, ax); py = __fsub_rn(py, ay); pz = __fsub_rn(pz, az);
-                        }
-                        sx = __fadd_rn(__fadd_rn(__fmul_rn(px, R00), __fmul_rn(py, R10)), __fmul_rn(pz, R20));
-                        sy = __fadd_rn(__fadd_rn(__fmul_rn(px, R01), __fmul_rn(py, R11)), __fmul_rn(pz, R21));
-                        sz = __fadd_rn(__fadd_rn(__fmul_rn(px, R02), __fmul_rn(py, R12)), __fmul_rn(pz, R22));
-                        if (mode == A3D_MODE_SEQ) {
-                            sx = __fadd_rn(sx, ax); sy = __fadd_rn(sy, ay); sz = __fadd_rn(sz, az);
-                        } else {
-                            sx = __fadd_rn(sx, t0); sy = __fadd_rn(sy, t1); sz = __fadd_rn(sz, t2);
-                        }
-                    }
-                    // project2D (vis.py:72-75): K@p, then /w.  The 0*X, 0*Y terms only matter
-                    // for non-finite inputs; keeping them in w reproduces those cases exactly.
-                    const float u = __fadd_rn(__fmul_rn(cam.f, sx), __fmul_rn(cam.cx, sz));
-                    const float v = __fadd_rn(__fmul_rn(cam.f, sy), __fmul_rn(cam.cy, sz));
-                    const float w = __fadd_rn(__fadd_rn(__fmul_rn(0.f, sx), __fmul_rn(0.f, sy)), sz);
-                    const int col = clamp_index(__fdiv_rn(u, w), W);
-                    const int rw = clamp_index(__fdiv_rn(v, w), H);
-                    const int wi = rw * pitch + (col >> 5);
-                    const uint32_t bm = 1u << (col & 31);
-                    if (wi != cur_wi) {
-                        if (cur_bits) atomicOr(cm + cur_wi, cur_bits);
-                        cur_wi = wi;
-                        cur_bits = bm;
-                    } else {
-                        cur_bits |= bm;
-                    }
-                }
-                if (cur_bits) atomicOr(cm + cur_wi, cur_bits);
-            }
-        }
+        if (job.mode == A3D_MODE_SEQ) splat_job<A3D_MODE_SEQ>(cam, job, npts, nc, pcd, xf, masks, words);
+        else if (job.mode == A3D_MODE_COMPOSED) splat_job<A3D_MODE_COMPOSED>(cam, job, npts, nc, pcd, xf, masks, words);
+        else splat_job<A3D_MODE_TRANSLATE>(cam, job, npts, nc, pcd, xf, masks, words);
     }
     __syncthreads();
 
@@ -673,12 +697,16 @@ int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int 
     const size_t usmem = (size_t)c.H * c.pitch * sizeof(uint32_t);
     if (usmem > (size_t)device_smem_optin())
         return fail(A3D_ELIMIT, "a3d_project: %dx%d mask does not fit shared memory", c.H, c.W);
+    // few jobs: spread each job's phase 2 over several CTAs so all SMs have work
+    int usplit = (2 * 148 + n_jobs - 1) / n_jobs;
+    usplit = usplit < 1 ? 1 : (usplit > 32 ? 32 : usplit);
+    const dim3 ugrid((unsigned)n_jobs, (unsigned)usplit);
     if (c.sparse) {
         A3D_CUDA_TRY(cudaFuncSetAttribute(k_unproject<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
-        k_unproject<true><<<(unsigned)n_jobs, kUnprojThreads, usmem, s>>>(c, jobs, src_bits, src_bbox, pcd_ws, pcd_count);
+        k_unproject<true><<<ugrid, kUnprojThreads, usmem, s>>>(c, jobs, src_bits, src_bbox, pcd_ws, pcd_count);
     } else {
         A3D_CUDA_TRY(cudaFuncSetAttribute(k_unproject<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
-        k_unproject<false><<<(unsigned)n_jobs, kUnprojThreads, usmem, s>>>(c, jobs, src_bits, src_bbox, pcd_ws, pcd_count);
+        k_unproject<false><<<ugrid, kUnprojThreads, usmem, s>>>(c, jobs, src_bits, src_bbox, pcd_ws, pcd_count);
     }
     A3D_CUDA_TRY(cudaGetLastError());
 

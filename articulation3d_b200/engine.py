@@ -245,7 +245,7 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
         proj_bits = ws.get("proj_bits", (nc, H, pitch), torch.int32)
         proj_popc = ws.get("proj_popc", (nc,), torch.int32)
         proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
-        pcd_ws = ws.get("pcd_ws", (3 * dbatch.pcd_total,), torch.float32)
+        pcd_ws = ws.get("pcd_ws", (max(3 * dbatch.pcd_total, 32),), torch.float32)
         pcd_count = ws.get("pcd_count", (dbatch.n_jobs,), torch.int32)
         key_ws = ws.get("key_ws", (nt,), torch.int64)
         best_cand = ws.get("best_cand", (nt,), torch.int32)

@@ -40,7 +40,6 @@ from scipy.stats import linregress
 from . import _lib, engine, geometry
 from .axis import angle_offset_to_axis, axis_to_angle_offset
 from .config import OptConfig
-from .structures import pairwise_iou
 
 __all__ = ["track_planes", "optimize_planes", "optimize_planes_3dc", "optimize_planes_3d_trans",
            "optimize_planes_3d", "optimize_planes_average", "optimize_videos", "RegMasks"]
@@ -49,34 +48,54 @@ __all__ = ["track_planes", "optimize_planes", "optimize_planes_3dc", "optimize_p
 # ---------------------------------------------------------------------------
 # tracker (host only; reference utils/opt_utils.py:1156-1208)
 # ---------------------------------------------------------------------------
+def _box_iou_f32(a, b) -> float:
+    """IoU of two XYXY boxes with every operation rounded to fp32, in the order
+    detectron2's ``pairwise_iou`` evaluates it on 1x1 inputs (area1 + area2 - inter)."""
+    f = np.float32
+    iw = f(min(a[2], b[2]) - max(a[0], b[0]))
+    ih = f(min(a[3], b[3]) - max(a[1], b[1]))
+    if not (iw > 0 and ih > 0):
+        return 0.0
+    inter = f(iw * ih)
+    area_a = f(f(a[2] - a[0]) * f(a[3] - a[1]))
+    area_b = f(f(b[2] - b[0]) * f(b[3] - b[1]))
+    return float(f(inter / f(f(area_a + area_b) - inter)))
+
+
 def track_planes(preds, cfg: OptConfig | None = None):
     """Greedy online box tracker -> {'rot': [...], 'trans': [...]}; each track is
     {'bbox', 'ids': {frame: box_id}, 'latest_frame'}.  A box joins the FIRST live
     track of its class (class 1 -> 'trans') whose latest box overlaps it with
     IoU > 0.5 and whose gap is <= 5 frames; tracks shorter than 10 frames are
-    dropped."""
+    dropped.  Box IoUs are evaluated on fp32 scalars (same roundings as the
+    reference's tensor ops) instead of one tiny tensor program per pair."""
     cfg = cfg or OptConfig()
     planes = {'rot': [], 'trans': []}
     for idx, p_instance in enumerate(preds):
         pred_classes = p_instance.pred_classes
         pred_boxes = p_instance.pred_boxes
-        for box_id in range(pred_boxes.tensor.shape[0]):
-            current_box = pred_boxes[box_id]
+        rows = pred_boxes.tensor.detach().cpu().numpy().astype(np.float32, copy=False)
+        for box_id in range(rows.shape[0]):
+            cur = rows[box_id]
             cat = 'trans' if pred_classes[box_id] == 1 else 'rot'
             matched = False
             for plane in planes[cat]:
                 if idx - plane['latest_frame'] > cfg.track_max_gap:
                     continue
-                if pairwise_iou(current_box, plane['bbox']).item() > cfg.track_iou:
+                if _box_iou_f32(cur, plane['_row']) > cfg.track_iou:
                     plane['ids'][idx] = box_id
-                    plane['bbox'] = current_box
+                    plane['bbox'] = pred_boxes[box_id]
+                    plane['_row'] = cur
                     plane['latest_frame'] = idx
                     matched = True
                     break
             if not matched:
-                planes[cat].append({'bbox': current_box, 'ids': {idx: box_id}, 'latest_frame': idx})
+                planes[cat].append({'bbox': pred_boxes[box_id], 'ids': {idx: box_id}, 'latest_frame': idx,
+                                    '_row': cur})
     for cat in planes:
         planes[cat] = [p for p in planes[cat] if len(p['ids']) >= cfg.track_min_len]
+        for p in planes[cat]:
+            del p['_row']
     return planes
 
 

@@ -312,7 +312,7 @@ def _run_split(engine, inp, ws, evs):
     proj_bits = ws.get("proj_bits", (nc, H, pitch), torch.int32)
     proj_popc = ws.get("proj_popc", (nc,), torch.int32)
     proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
-    pcd_ws = ws.get("pcd_ws", (3 * db.pcd_total,), torch.float32)
+    pcd_ws = ws.get("pcd_ws", (max(3 * db.pcd_total, 32),), torch.float32)
     pcd_count = ws.get("pcd_count", (db.n_jobs,), torch.int32)
     key_ws = ws.get("key_ws", (nt,), torch.int64)
     outs = [ws.get(n, (nt,), dt) for n, dt in (("best_cand", torch.int32), ("best_inter", torch.int32),

@@ -1,0 +1,37 @@
+"""cProfile of the public API on a workload-shaped clip (host-side overheads)."""
+import cProfile
+import os
+import pstats
+import random
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from articulation3d_b200 import opt_utils, workloads  # noqa: E402
+
+wl = workloads.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
+preds, cfg = workloads.make_clip(wl, 2020)
+for p in preds:
+    p.pred_masks = p.pred_masks.pin_memory()
+
+
+def run():
+    random.seed(2020)
+    planes = opt_utils.track_planes(preds, cfg)
+    st = opt_utils.Stats()
+    opt_utils.optimize_planes(preds, planes, "3dc", cfg=cfg, device="cuda:0", stats=st)
+    torch.cuda.synchronize()
+    return st
+
+
+run()
+t0 = time.perf_counter()
+st = run()
+print("wall ms", 1e3 * (time.perf_counter() - t0), st.passes, st.units_visited, st.units_computed)
+pr = cProfile.Profile()
+pr.enable()
+run()
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
