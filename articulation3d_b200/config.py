@@ -72,7 +72,11 @@ class OptConfig:
         """float64 inverse exactly as numpy returns it (utils/vis.py:95): it is
         passed to the device as data, never re-derived in closed form
         (SURVEY.md App. A #17: the two differ by one ulp in [0,2])."""
-        return np.linalg.inv(self.K())
+        key = (self.focal_length, self.width, self.height)
+        if getattr(self, "_kinv_key", None) != key:
+            object.__setattr__(self, "_kinv", np.linalg.inv(self.K()))
+            object.__setattr__(self, "_kinv_key", key)
+        return self._kinv
 
     @staticmethod
     def scaled(width: int, height: int, **kw) -> "OptConfig":

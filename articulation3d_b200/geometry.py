@@ -48,7 +48,11 @@ def unproject_points(verts_xy, normal: torch.Tensor, offset: torch.Tensor, cfg: 
         return np.stack([depth * rx, depth * ry, depth * rz], axis=1)
 
 
-def source_geometry(p_instance, box_id: int, cfg: OptConfig, translation: bool) -> SourceGeometry:
+def source_geometry(p_instance, box_id: int, cfg: OptConfig, translation: bool,
+                    all_boxes: bool = False) -> SourceGeometry:
+    """``pts`` holds the integer axis end-points; the reference computes them for every box
+    of the frame and uses row ``box_id`` (all rows only in the legacy method's ``std_axis``),
+    so by default only that row is computed (the others are zero)."""
     plane = p_instance.pred_planes[box_id:(box_id + 1)].clone()
     plane[:, [1, 2]] = plane[:, [2, 1]]            # [a, b, c] -> [a, -c, b]
     plane[:, 1] = -plane[:, 1]
@@ -60,7 +64,12 @@ def source_geometry(p_instance, box_id: int, cfg: OptConfig, translation: bool) 
         axis = torch.cat((axis, torch.zeros(len(axis), 1)), 1)     # offset column = 0
     else:
         axis = p_instance.pred_rot_axis
-    pts = angle_offset_to_axis(axis, centers, H=cfg.height, W=cfg.width)
+    if all_boxes:
+        pts = angle_offset_to_axis(axis, centers, H=cfg.height, W=cfg.width)
+    else:
+        pts = torch.zeros(len(axis), 4, dtype=torch.int64)
+        pts[box_id] = angle_offset_to_axis(axis[box_id:box_id + 1], centers[box_id:box_id + 1],
+                                           H=cfg.height, W=cfg.width)[0]
     axis3d = unproject_points(pts[box_id].reshape(-1, 2).numpy(), normal, offset, cfg)
     with np.errstate(all="ignore"):
         d = axis3d[1] - axis3d[0]

@@ -35,7 +35,11 @@ from dataclasses import dataclass, field
 
 import numpy as np
 import torch
-from scipy.stats import linregress
+from scipy.stats import linregress as _scipy_linregress
+
+# scipy wraps linregress in an axis/nan-policy decorator that costs more than the regression;
+# for 1-D finite inputs it forwards unchanged to this inner function (tests/test_host_logic.py).
+linregress = getattr(_scipy_linregress, "__wrapped__", _scipy_linregress)
 
 from . import _lib, engine, geometry
 from .axis import angle_offset_to_axis, axis_to_angle_offset
@@ -242,7 +246,7 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
         select_idx = final_cluster['center_id']
         box_id = ids[select_idx]
         p_instance = preds[select_idx]
-        geo = geometry.source_geometry(p_instance, box_id, cfg, translation)
+        geo = geometry.source_geometry(p_instance, box_id, cfg, translation, all_boxes=legacy)
         xf, angles, R = _candidates(geo, fgrid, fmode)
         frames = list(ids.keys())
         res = yield JobSpec(pool_of[(select_idx, box_id)], fmode, geo.normal.numpy(), float(geo.offset),
@@ -288,6 +292,19 @@ def _rebuild(p_instance, scores):
 
 def _write_back(preds, planes, cfg: OptConfig, kind: str):
     """kind: 'rot' | 'trans' | 'legacy'."""
+    # rotation tracks: the fitted axis re-expressed relative to every frame's box centre.  The
+    # reference does this one (frame, track) at a time (:646-651); the arithmetic is elementwise
+    # fp32, so one call per track over all its frames gives the same bits.
+    new_axis = {}
+    if kind == 'rot':
+        for ti, plane in enumerate(planes):
+            if not plane['has_rot'] or not plane['ids']:
+                continue
+            frames = list(plane['ids'].keys())
+            centers = torch.stack([preds[f].pred_boxes.tensor[plane['ids'][f]] for f in frames])
+            centers = (centers[:, :2] + centers[:, 2:]) / 2
+            line = plane['std_axis'].unsqueeze(0).numpy().tolist()
+            new_axis[ti] = dict(zip(frames, axis_to_angle_offset(line * len(frames), centers)[:, :3]))
     opt_preds = []
     for idx, p_instance in enumerate(preds):
         pred_boxes = p_instance.pred_boxes
@@ -301,7 +318,7 @@ def _write_back(preds, planes, cfg: OptConfig, kind: str):
         if kind == 'rot':
             p_instance.pred_rot_axis = p_instance.pred_rot_axis.clone()
             p_instance.pred_planes = p_instance.pred_planes.clone()
-        for plane in planes:
+        for ti, plane in enumerate(planes):
             if idx not in plane['ids']:
                 continue
             box_id = plane['ids'][idx]
@@ -310,9 +327,7 @@ def _write_back(preds, planes, cfg: OptConfig, kind: str):
                 continue
             chosen[box_id] = True
             if kind == 'rot':
-                centers = pred_boxes.get_centers()[box_id:(box_id + 1)]
-                std_axis = axis_to_angle_offset(plane['std_axis'].unsqueeze(0).numpy().tolist(), centers)
-                p_instance.pred_rot_axis[box_id] = std_axis[0, :3]
+                p_instance.pred_rot_axis[box_id] = new_axis[ti][idx]
             elif kind == 'trans':
                 p_instance.pred_tran_axis[box_id] = plane['std_axis']     # in place, like the reference
         chosen = np.array(chosen, dtype=bool)

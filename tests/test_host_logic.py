@@ -96,10 +96,12 @@ def test_source_geometry_and_transforms_match_oracle():
     cfg, ocfg = OptConfig(), restated.OracleConfig()
     preds, _ = synth.make_video(21, 3, 12, kinds=[0, 1, 0])
     for frame, box, trans in ((0, 0, False), (5, 2, False), (7, 1, True)):
-        geo = geometry.source_geometry(preds[frame], box, cfg, trans)
+        geo = geometry.source_geometry(preds[frame], box, cfg, trans, all_boxes=True)
         ref = restated.source_geometry(preds[frame], box, ocfg, trans)
         assert torch.equal(geo.normal, ref["normal"]) and torch.equal(geo.offset, ref["offset"])
         assert torch.equal(geo.pts, ref["pts"])
+        one = geometry.source_geometry(preds[frame], box, cfg, trans)          # only the needed row
+        assert torch.equal(one.pts[box], ref["pts"][box]) and np.array_equal(one.dir_vec, geo.dir_vec)
         assert np.array_equal(geo.axis3d, ref["axis3d"]) and np.array_equal(geo.dir_vec, ref["dir_vec"])
         R = geometry.rotation_matrices(cfg.rot_cluster_grid, geo.dir_vec)
         assert np.array_equal(R, restated.rotation_matrices(ocfg.rot_cluster_grid, ref["dir_vec"]))
@@ -173,5 +175,16 @@ def test_source_geometry_matches_oracle_at_other_resolutions():
         for box, trans in ((0, False), (1, True)):
             geo = geometry.source_geometry(preds[4], box, cfg, trans)
             ref = restated.source_geometry(preds[4], box, ocfg, trans)
-            assert torch.equal(geo.pts, ref["pts"])
+            assert torch.equal(geo.pts[box], ref["pts"][box])
             assert np.array_equal(geo.axis3d, ref["axis3d"]) and np.array_equal(geo.dir_vec, ref["dir_vec"])
+
+
+def test_linregress_inner_function_equals_scipy():
+    from scipy.stats import linregress as sp
+    rng = np.random.RandomState(0)
+    for n in (5, 8, 30, 120):
+        for y in (rng.rand(n).astype(np.float32), np.full(n, 0.1047, np.float32),
+                  (np.arange(n) * 0.1047).astype(np.float32)):
+            a = sp(range(n), torch.from_numpy(y))
+            b = opt_utils.linregress(range(n), torch.from_numpy(y))
+            assert (a.rvalue == b.rvalue) or (np.isnan(a.rvalue) and np.isnan(b.rvalue))
