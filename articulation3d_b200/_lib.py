@@ -73,7 +73,7 @@ def load():
     lib.a3d_project.restype = C.c_int
     lib.a3d_project.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.a3d_score.restype = C.c_int
-    lib.a3d_score.argtypes = [i32, i32, vp, i32, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+    lib.a3d_score.argtypes = [i32, i32, vp, i32, i32, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                               vp, vp, vp, vp, vp]
     lib.a3d_emit_masks.restype = C.c_int
     lib.a3d_emit_masks.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp]

@@ -9,11 +9,13 @@
 // built with -fmad=false.
 #include "a3d.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -545,6 +547,204 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
     }
 }
 
+// ---------------------------------------------------------------------------
+// score, TMA-staged.  Same arithmetic as k_score above; CTA = (job, 16 targets,
+// 8 candidates), 8 warps = 4 target groups x 2 candidate groups, each warp a
+// 4x4 register tile.  The CTA walks the overlap box of its masks in chunks of
+// R rows x bw words (R*bw <= 256 words = 1 KB per mask); warp 0 stages the 24
+// mask tiles of the NEXT chunk with cp.async.bulk.tensor.2d (TMA, completion on
+// an mbarrier) while all warps AND/POPC the current one out of shared memory.
+// Tensor maps: uint32 [n_masks*H][pitch] with boxes {bw, R}; out-of-range
+// columns are zero-filled by the TMA unit.
+// ---------------------------------------------------------------------------
+constexpr int kTmaTT = 16, kTmaCT = 8, kTmaMasks = kTmaTT + kTmaCT;
+constexpr int kTmaTileWords = 256;
+constexpr int kTmaStages = 2;
+constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * kTmaMasks * kTmaTileWords * 4 + 64;
+
+struct TmaMaps {
+    CUtensorMap t[4];     // target pool, box widths bw[0..3]
+    CUtensorMap p[4];     // projected masks
+    int bw[4];            // words per box row
+    int rows[4];          // rows per box
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ jobs, int H, int pitch,
+            int tt_tiles, int ct_tiles, const int32_t* __restrict__ tgt_popc,
+            const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
+            const int32_t* __restrict__ proj_popc, const int32_t* __restrict__ proj_bbox,
+            unsigned long long* __restrict__ key_ws, int32_t* __restrict__ inter_tab) {
+    extern __shared__ __align__(1024) uint32_t tiles[];      // [stage][mask][256 words]
+    __shared__ int s_mask_row0[kTmaMasks];                   // first tensor row of every mask of the tile
+    __shared__ int s_box[8];                                 // union boxes: cand r0,r1,c0,c1 | tgt r0,r1,c0,c1
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kTmaStages * kTmaMasks * kTmaTileWords);
+
+    const int per_job = tt_tiles * ct_tiles;
+    const int jid = blockIdx.x / per_job;
+    const int rem = blockIdx.x - jid * per_job;
+    const a3d_job_t job = jobs[jid];
+    const int tb = (rem / ct_tiles) * kTmaTT;
+    const int cb = (rem % ct_tiles) * kTmaCT;
+    if (tb >= job.n_tgt || cb >= job.n_cand) return;           // whole CTA leaves together
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntile_t = min(kTmaTT, job.n_tgt - tb), ntile_c = min(kTmaCT, job.n_cand - cb);
+
+    if (threadIdx.x < 8) s_box[threadIdx.x] = (threadIdx.x & 1) ? -1 : 0x7fffffff;
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bars[0]), 1);
+        mbar_init(smem_u32(&bars[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < kTmaMasks) {
+        const int m = threadIdx.x;
+        const int32_t* b;
+        int base;
+        if (m < kTmaTT) {
+            const int ti = tgt_index[job.tgt_begin + tb + min(m, ntile_t - 1)];
+            s_mask_row0[m] = ti * H;
+            b = tgt_bbox + 4 * (size_t)ti;
+            base = 4;
+        } else {
+            const int g = job.cand_begin + cb + min(m - kTmaTT, ntile_c - 1);
+            s_mask_row0[m] = g * H;
+            b = proj_bbox + 4 * (size_t)g;
+            base = 0;
+        }
+        if (b[1] >= b[0]) {
+            atomicMin(&s_box[base + 0], b[0]); atomicMax(&s_box[base + 1], b[1]);
+            atomicMin(&s_box[base + 2], b[2]); atomicMax(&s_box[base + 3], b[3]);
+        }
+    }
+    __syncthreads();
+    const int ra = max(s_box[0], s_box[4]), rb = min(s_box[1], s_box[5]);
+    const int ca = max(s_box[2], s_box[6]), cbw = min(s_box[3], s_box[7]);
+
+    // this warp's 4 targets x 4 candidates inside the tile
+    const int tw = (warp >> 1) * 4, cw = (warp & 1) * 4;
+    const bool active = tw < ntile_t && cw < ntile_c;
+    int acc2[4][4];
+    uint32_t ones[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc2[i][k] = 0; ones[i][k] = 0u; }
+
+    if (rb >= ra && cbw >= ca) {
+        const int ncols = cbw - ca + 1;
+        const int sel = ncols <= maps.bw[0] ? 0 : (ncols <= maps.bw[1] ? 1 : (ncols <= maps.bw[2] ? 2 : 3));
+        const int bw = maps.bw[sel], R = maps.rows[sel];
+        const int ncb = (ncols + bw - 1) / bw;                 // column blocks (1 unless pitch > 32 words)
+        const int nrc = (rb - ra + R) / R;                     // row chunks
+        const int nchunks = ncb * nrc;
+        const uint32_t tile_bytes = (uint32_t)(R * bw * 4);
+        const CUtensorMap* mt = &maps.t[sel];
+        const CUtensorMap* mp = &maps.p[sel];
+        const uint32_t tiles_s = smem_u32(tiles);
+
+        auto issue = [&](int chunk) {                           // executed by warp 0
+            const int st = chunk & 1;
+            const int r = ra + (chunk / ncb) * R, c = ca + (chunk % ncb) * bw;
+            const uint32_t bar = smem_u32(&bars[st]);
+            if (lane == 0) mbar_expect_tx(bar, tile_bytes * kTmaMasks);
+            __syncwarp();
+            if (lane < kTmaMasks)
+                tma_load_2d(tiles_s + (uint32_t)((st * kTmaMasks + lane) * kTmaTileWords * 4),
+                            lane < kTmaTT ? mt : mp, c, s_mask_row0[lane] + r, bar);
+        };
+
+        if (warp == 0) issue(0);
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+            if (warp == 0 && chunk + 1 < nchunks) issue(chunk + 1);
+            mbar_wait(smem_u32(&bars[chunk & 1]), (uint32_t)((chunk >> 1) & 1));
+            if (active) {
+                const int r = ra + (chunk / ncb) * R;
+                const int nv = min(R, H - r) * bw;              // rows past the image belong to another mask
+                const uint32_t* st = tiles + (size_t)(chunk & 1) * kTmaMasks * kTmaTileWords;
+                const uint32_t* tbase = st + (size_t)tw * kTmaTileWords;
+                const uint32_t* pbase = st + (size_t)(kTmaTT + cw) * kTmaTileWords;
+#pragma unroll
+                for (int it = 0; it < kTmaTileWords / 64; ++it) {
+                    const int w = 2 * lane + 64 * it;
+                    if (w < nv) {
+                        uint2 t[4], q[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            t[i] = *reinterpret_cast<const uint2*>(tbase + i * kTmaTileWords + w);
+                            q[i] = *reinterpret_cast<const uint2*>(pbase + i * kTmaTileWords + w);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t a = t[i].x & q[k].x, b = t[i].y & q[k].y, o = ones[i][k];
+                                ones[i][k] = o ^ a ^ b;
+                                acc2[i][k] += __popc((o & a) | (o & b) | (a & b));
+                            }
+                    }
+                }
+            }
+            __syncthreads();                                    // stage may be refilled by the next issue
+        }
+    }
+    if (!active) return;
+
+    int acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            acc[i][k] = __reduce_add_sync(0xffffffffu, 2 * acc2[i][k] + __popc(ones[i][k]));
+
+    if (lane == 0) {
+        const int t0 = tb + tw, c0 = cb + cw;
+        const int nt = min(4, job.n_tgt - t0), ncd = min(4, job.n_cand - c0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i >= nt) break;
+            const int pt = tgt_popc[tgt_index[job.tgt_begin + t0 + i]];
+            unsigned long long best = 0ull;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k >= ncd) break;
+                const int inter = acc[i][k];
+                const int uni = pt + proj_popc[(size_t)job.cand_begin + c0 + k] - inter;
+                const float iou = __fdiv_rn((float)inter, (float)uni);
+                const unsigned long long key =
+                    ((unsigned long long)__float_as_uint(iou) << 32) | (unsigned)(~(unsigned)(c0 + k));
+                best = key > best ? key : best;
+                if (inter_tab) inter_tab[job.tab_begin + (int64_t)(t0 + i) * job.n_cand + c0 + k] = inter;
+            }
+            atomicMax(key_ws + job.tgt_begin + t0 + i, best);
+        }
+    }
+}
+
 // one warp per target: decode the winning candidate and recompute its counts
 __global__ void __launch_bounds__(256)
 k_finalize(const a3d_job_t* __restrict__ jobs, int H, int pitch,
@@ -600,6 +800,39 @@ k_emit(const uint32_t* __restrict__ bits, const int32_t* __restrict__ index, int
         const int r = p / W, x = p - r * W;
         o[p] = (T)((b[r * pitch + (x >> 5)] >> (x & 31)) & 1u);
     }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// uint32 [rows][pitch] tensor with a {bw, box_rows} box
+int encode_mask_map(CUtensorMap* map, const void* base, uint64_t rows, int pitch, int bw, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(A3D_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(A3D_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu pitch=%d box=%dx%d", (int)r,
+                    (unsigned long long)rows, pitch, bw, box_rows);
+    return A3D_OK;
 }
 
 int device_smem_optin() {
@@ -723,14 +956,15 @@ int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int 
 }
 
 int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int max_cand,
-              int64_t n_tgt_total,
+              int64_t n_tgt_total, int64_t n_pool_masks, int64_t n_cand_total,
               const uint32_t* tgt_bits, const int32_t* tgt_popc, const int32_t* tgt_bbox,
               const int32_t* tgt_index,
               const uint32_t* proj_bits, const int32_t* proj_popc, const int32_t* proj_bbox,
               uint64_t* key_ws, int32_t* inter_tab,
               int32_t* best_cand, int32_t* best_inter, int32_t* best_union, float* best_iou,
               void* stream) {
-    if (H <= 0 || W <= 0 || n_jobs < 0 || max_tgt < 0 || max_cand < 0 || n_tgt_total < 0)
+    if (H <= 0 || W <= 0 || n_jobs < 0 || max_tgt < 0 || max_cand < 0 || n_tgt_total < 0 || n_pool_masks < 0 ||
+        n_cand_total < 0)
         return fail(A3D_EINVAL, "a3d_score: bad argument");
     if (n_jobs == 0 || max_tgt == 0 || n_tgt_total == 0) return A3D_OK;
     if (max_cand == 0) return fail(A3D_EINVAL, "a3d_score: jobs need at least one candidate");
@@ -740,12 +974,41 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
     const int pitch = pitch_words(W);
     cudaStream_t s = (cudaStream_t)stream;
     A3D_CUDA_TRY(cudaMemsetAsync(key_ws, 0, sizeof(uint64_t) * (size_t)n_tgt_total, s));
-    const int tt_tiles = (max_tgt + kScoreTT - 1) / kScoreTT, ct_tiles = (max_cand + kScoreCT - 1) / kScoreCT;
-    const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
-    if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
-    k_score<<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc, tgt_bbox,
-                                              tgt_index, proj_bits, proj_popc, proj_bbox,
-                                              (unsigned long long*)key_ws, inter_tab);
+
+    static const int use_ldg = [] {
+        const char* e = getenv("A3D_SCORE_KERNEL");
+        return (e && !strcmp(e, "ldg")) ? 1 : 0;
+    }();
+    const bool tma_ok = !use_ldg && (n_pool_masks * H < 0x7fffffffLL) && (n_cand_total * H < 0x7fffffffLL);
+    if (tma_ok) {
+        // mask tiles staged by TMA: one tensor map per (array, box width)
+        TmaMaps maps;
+        const int widths[4] = {4, 8, 16, 32};
+        for (int i = 0; i < 4; ++i) {
+            const int bw = widths[i] < pitch ? widths[i] : pitch;
+            const int rows = kTmaTileWords / bw;
+            maps.bw[i] = bw;
+            maps.rows[i] = rows;
+            int rc = encode_mask_map(&maps.t[i], tgt_bits, (uint64_t)n_pool_masks * H, pitch, bw, rows);
+            if (rc) return rc;
+            rc = encode_mask_map(&maps.p[i], proj_bits, (uint64_t)n_cand_total * H, pitch, bw, rows);
+            if (rc) return rc;
+        }
+        const int tt_tiles = (max_tgt + kTmaTT - 1) / kTmaTT, ct_tiles = (max_cand + kTmaCT - 1) / kTmaCT;
+        const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
+        if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
+        A3D_CUDA_TRY(cudaFuncSetAttribute(k_score_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
+        k_score_tma<<<(unsigned)nblocks, 256, kTmaSmemBytes, s>>>(maps, jobs, H, pitch, tt_tiles, ct_tiles, tgt_popc,
+                                                                  tgt_bbox, tgt_index, proj_popc, proj_bbox,
+                                                                  (unsigned long long*)key_ws, inter_tab);
+    } else {
+        const int tt_tiles = (max_tgt + kScoreTT - 1) / kScoreTT, ct_tiles = (max_cand + kScoreCT - 1) / kScoreCT;
+        const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
+        if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
+        k_score<<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc, tgt_bbox,
+                                                  tgt_index, proj_bits, proj_popc, proj_bbox,
+                                                  (unsigned long long*)key_ws, inter_tab);
+    }
     A3D_CUDA_TRY(cudaGetLastError());
     const dim3 fgrid((unsigned)n_jobs, (unsigned)((max_tgt + 7) / 8 < 64 ? (max_tgt + 7) / 8 : 64));
     k_finalize<<<fgrid, 256, 0, s>>>(jobs, H, pitch, tgt_bits, tgt_popc, tgt_index, proj_bits, proj_popc,

@@ -264,7 +264,7 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
                                    proj_bits.data_ptr(), proj_popc.data_ptr(), proj_bbox.data_ptr(), stream),
                    "a3d_project")
         _lib.check(lib.a3d_score(H, W, dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_tgt, dbatch.max_cand, nt,
-                                 pool.bits.data_ptr(), pool.popc.data_ptr(), pool.bbox.data_ptr(),
+                                 len(pool), nc, pool.bits.data_ptr(), pool.popc.data_ptr(), pool.bbox.data_ptr(),
                                  dbatch.tgt_index.data_ptr(), proj_bits.data_ptr(), proj_popc.data_ptr(),
                                  proj_bbox.data_ptr(), key_ws.data_ptr(),
                                  inter_tab.data_ptr() if inter_tab is not None else None,

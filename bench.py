@@ -328,7 +328,7 @@ def _run_split(engine, inp, ws, evs):
     if evs:
         evs[1].record()
     _lib.check(lib.a3d_score(H, W, db.jobs.data_ptr(), db.n_jobs, db.max_tgt, db.max_cand, nt,
-                             pool.bits.data_ptr(), pool.popc.data_ptr(), pool.bbox.data_ptr(),
+                             len(pool), nc, pool.bits.data_ptr(), pool.popc.data_ptr(), pool.bbox.data_ptr(),
                              db.tgt_index.data_ptr(), proj_bits.data_ptr(), proj_popc.data_ptr(),
                              proj_bbox.data_ptr(), key_ws.data_ptr(), None, outs[0].data_ptr(),
                              outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), stream), "a3d_score")

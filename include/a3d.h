@@ -126,6 +126,7 @@ int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int 
 
 /* (a8) mask-IoU scoring with fused arg-max over candidates.  Replaces the
  * `for idx in id_list` loops of opt_utils.py:464-477, 600-612, 757-770, 892-904.
+ *   n_pool_masks, n_cand_total  sizes of the target pool / of proj_* (TMA tensor extents)
  *   tgt_index  [n_tgt_total] indices into the target pool (tgt_bits/popc/bbox)
  *   key_ws     [n_tgt_total] uint64 workspace
  *   inter_tab  optional [sum n_tgt*n_cand] int32 table of intersections (NULL ok)
@@ -134,7 +135,7 @@ int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int 
  *   best_inter, best_union  integer counts at that candidate
  *   best_iou   fp32 inter/union (IEEE division)                                */
 int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int max_cand,
-              int64_t n_tgt_total,
+              int64_t n_tgt_total, int64_t n_pool_masks, int64_t n_cand_total,
               const uint32_t* tgt_bits, const int32_t* tgt_popc, const int32_t* tgt_bbox,
               const int32_t* tgt_index,
               const uint32_t* proj_bits, const int32_t* proj_popc, const int32_t* proj_bbox,
