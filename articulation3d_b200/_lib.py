@@ -38,6 +38,7 @@ assert JOB_DTYPE.itemsize == 72, JOB_DTYPE.itemsize
 EXPORTS = (
     "a3d_version", "a3d_last_error_string", "a3d_pitch_words", "a3d_project_max_tile",
     "a3d_pack_masks", "a3d_mask_meta", "a3d_project", "a3d_score", "a3d_emit_masks",
+    "a3d_rle_to_bits", "a3d_plane_offsets",
 )
 
 _lib = None
@@ -77,6 +78,10 @@ def load():
                               vp, vp, vp, vp, vp]
     lib.a3d_emit_masks.restype = C.c_int
     lib.a3d_emit_masks.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp]
+    lib.a3d_rle_to_bits.restype = C.c_int
+    lib.a3d_rle_to_bits.argtypes = [vp, vp, i64, i32, i32, vp, vp]
+    lib.a3d_plane_offsets.restype = C.c_int
+    lib.a3d_plane_offsets.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp]
     _lib = lib
     return lib
 

@@ -643,7 +643,9 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
     }
     __syncthreads();
     const int ra = max(s_box[0], s_box[4]), rb = min(s_box[1], s_box[5]);
-    const int ca = max(s_box[2], s_box[6]), cbw = min(s_box[3], s_box[7]);
+    // TMA needs the box to start on a 16-byte boundary in global memory (measured on B200:
+    // an inner coordinate that is not a multiple of 4 words raises an illegal instruction)
+    const int ca = max(s_box[2], s_box[6]) & ~3, cbw = min(s_box[3], s_box[7]);
 
     // this warp's 4 targets x 4 candidates inside the tile
     const int tw = (warp >> 1) * 4, cw = (warp & 1) * 4;
@@ -671,11 +673,16 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
             const int st = chunk & 1;
             const int r = ra + (chunk / ncb) * R, c = ca + (chunk % ncb) * bw;
             const uint32_t bar = smem_u32(&bars[st]);
-            if (lane == 0) mbar_expect_tx(bar, tile_bytes * kTmaMasks);
+            if (lane == 0) {
+                mbar_expect_tx(bar, tile_bytes * kTmaMasks);
+                for (int m = 0; m < kTmaTT; ++m)
+                    tma_load_2d(tiles_s + (uint32_t)((st * kTmaMasks + m) * kTmaTileWords * 4), mt, c,
+                                s_mask_row0[m] + r, bar);
+                for (int m = kTmaTT; m < kTmaMasks; ++m)
+                    tma_load_2d(tiles_s + (uint32_t)((st * kTmaMasks + m) * kTmaTileWords * 4), mp, c,
+                                s_mask_row0[m] + r, bar);
+            }
             __syncwarp();
-            if (lane < kTmaMasks)
-                tma_load_2d(tiles_s + (uint32_t)((st * kTmaMasks + lane) * kTmaTileWords * 4),
-                            lane < kTmaTT ? mt : mp, c, s_mask_row0[lane] + r, bar);
         };
 
         if (warp == 0) issue(0);
@@ -784,6 +791,117 @@ k_finalize(const a3d_job_t* __restrict__ jobs, int H, int pitch,
             best_union[slot] = uni;
             best_iou[slot] = __fdiv_rn((float)inter, (float)uni);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// rle_to_bits: COCO run-length masks (column-major runs, alternating 0/1, starting
+// with 0) -> row-major bit-packed masks, one CTA per mask.  The packed image is
+// assembled in shared memory: runs are taken 256 at a time (block prefix sum of the
+// lengths), each warp then paints whole runs, one lane per pixel.
+// Replaces pycocotools' mask_util.decode in create_instances (utils/arti_vis.py:182).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rle_to_bits(const uint32_t* __restrict__ counts, const int64_t* __restrict__ begin, int H, int W, int pitch,
+              uint32_t* __restrict__ bits) {
+    extern __shared__ __align__(16) uint32_t img[];          // [H][pitch]
+    __shared__ unsigned long long s_start[256];
+    __shared__ uint32_t s_len[256];
+    __shared__ unsigned long long s_warp[8];
+    __shared__ unsigned long long s_base;
+    const int words = H * pitch;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < words; i += 256) img[i] = 0u;
+    if (threadIdx.x == 0) s_base = 0ull;
+    __syncthreads();
+    const int64_t b0 = begin[blockIdx.x], nruns = begin[blockIdx.x + 1] - b0;
+    const unsigned long long npix = (unsigned long long)H * W;
+    for (int64_t c0 = 0; c0 < nruns; c0 += 256) {
+        const int64_t r = c0 + threadIdx.x;
+        const uint32_t len = r < nruns ? counts[b0 + r] : 0u;
+        unsigned long long incl = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long off = s_base;
+        for (int i = 0; i < warp; ++i) off += s_warp[i];
+        s_start[threadIdx.x] = off + incl - len;
+        s_len[threadIdx.x] = (r & 1) ? len : 0u;             // odd runs are the ones
+        __syncthreads();
+        for (int k = warp; k < 256; k += 8) {
+            const uint32_t L = s_len[k];
+            if (L == 0) continue;
+            const unsigned long long st = s_start[k];
+            for (unsigned long long i = st + lane; i < st + L && i < npix; i += 32) {
+                const int x = (int)(i / (unsigned)H), y = (int)(i - (unsigned long long)x * H);
+                atomicOr(&img[y * pitch + (x >> 5)], 1u << (x & 31));
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 255) s_base = off + incl;
+        __syncthreads();
+    }
+    uint32_t* out = bits + (size_t)blockIdx.x * words;
+    for (int i = threadIdx.x; i < words; i += 256) out[i] = img[i];
+}
+
+// ---------------------------------------------------------------------------
+// plane_offsets: per instance, mean over the mask of n . (ray * depth) — the plane
+// offset the detector's depth map implies (override_depth, utils/arti_vis.py:125-149).
+// One CTA per instance walks the mask's bounding box, one warp per packed word, one
+// lane per pixel; X = ray_x*depth etc. are fp32 products as in depth2XYZ (:90-99),
+// the dot product is separately rounded fp32, the sum is carried in fp64.
+// Streams depth (4 B/px) + the ray table (12 B/px, L2-resident) once per instance.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_plane_offsets(const float* __restrict__ depth, const float* __restrict__ rays, int H, int W, int pitch,
+                const uint32_t* __restrict__ bits, const int32_t* __restrict__ bbox,
+                const int32_t* __restrict__ inst_mask, const int32_t* __restrict__ inst_frame,
+                const float* __restrict__ normals, float* __restrict__ offset_out, int32_t* __restrict__ count_out) {
+    __shared__ double s_sum[8];
+    __shared__ int s_cnt[8];
+    const int inst = blockIdx.x;
+    const int m = inst_mask[inst];
+    const int32_t* b = bbox + 4 * (size_t)m;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double sum = 0.0;
+    int cnt = 0;
+    if (b[1] >= b[0]) {
+        const uint32_t* mb = bits + (size_t)m * H * pitch;
+        const size_t plane = (size_t)H * W;
+        const float* d = depth ? depth + (size_t)inst_frame[inst] * plane : nullptr;
+        const float n0 = normals[3 * inst], n1 = normals[3 * inst + 1], n2 = normals[3 * inst + 2];
+        const int ncols = b[3] - b[2] + 1, nwords = (b[1] - b[0] + 1) * ncols;
+        for (int w = warp; w < nwords; w += 8) {
+            const int rr = w / ncols;
+            const int row = b[0] + rr, wc = b[2] + (w - rr * ncols);
+            const uint32_t word = mb[row * pitch + wc];
+            const int x = wc * 32 + lane;
+            if (((word >> lane) & 1u) && x < W) {
+                const size_t o = (size_t)row * W + x;
+                const float dz = d ? d[o] : 1.0f;
+                const float X = __fmul_rn(rays[o], dz), Y = __fmul_rn(rays[plane + o], dz),
+                            Z = __fmul_rn(rays[2 * plane + o], dz);
+                sum += (double)__fadd_rn(__fadd_rn(__fmul_rn(n0, X), __fmul_rn(n1, Y)), __fmul_rn(n2, Z));
+                ++cnt;
+            }
+        }
+    }
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, dlt);
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) { s_sum[warp] = sum; s_cnt[warp] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        int c = 0;
+        for (int i = 0; i < 8; ++i) { t += s_sum[i]; c += s_cnt[i]; }
+        count_out[inst] = c;
+        offset_out[inst] = c > 0 ? (float)(t / (double)c) : 0.f;
     }
 }
 
@@ -1034,6 +1152,38 @@ int a3d_emit_masks(const uint32_t* bits, const int32_t* index, int64_t n, int H,
         k_emit<unsigned char><<<grid, 256, 0, s>>>(bits, index, H, W, pitch, (unsigned char*)out);
     else
         return fail(A3D_EINVAL, "a3d_emit_masks: unknown dtype %d", out_dtype);
+    A3D_CUDA_TRY(cudaGetLastError());
+    return A3D_OK;
+}
+
+int a3d_rle_to_bits(const uint32_t* counts, const int64_t* begin, int64_t n, int H, int W, uint32_t* bits,
+                    void* stream) {
+    if (n < 0 || H <= 0 || W <= 0) return fail(A3D_EINVAL, "a3d_rle_to_bits: bad shape");
+    if (n == 0) return A3D_OK;
+    if (!counts || !begin || !bits) return fail(A3D_EINVAL, "a3d_rle_to_bits: null pointer");
+    if (n > 0x7fffffff) return fail(A3D_ELIMIT, "a3d_rle_to_bits: n too large");
+    const int pitch = pitch_words(W);
+    const size_t smem = (size_t)H * pitch * 4;
+    if (smem > (size_t)device_smem_optin() - 8192)
+        return fail(A3D_ELIMIT, "a3d_rle_to_bits: %dx%d mask does not fit shared memory", H, W);
+    A3D_CUDA_TRY(cudaFuncSetAttribute(k_rle_to_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_rle_to_bits<<<(unsigned)n, 256, smem, (cudaStream_t)stream>>>(counts, begin, H, W, pitch, bits);
+    A3D_CUDA_TRY(cudaGetLastError());
+    return A3D_OK;
+}
+
+int a3d_plane_offsets(const float* depth, const float* rays, int H, int W, const uint32_t* bits,
+                      const int32_t* bbox, const int32_t* inst_mask, const int32_t* inst_frame,
+                      const float* normals, int64_t n_inst, float* offset_out, int32_t* count_out,
+                      void* stream) {
+    if (n_inst < 0 || H <= 0 || W <= 0) return fail(A3D_EINVAL, "a3d_plane_offsets: bad shape");
+    if (n_inst == 0) return A3D_OK;
+    if (!rays || !bits || !bbox || !inst_mask || !normals || !offset_out || !count_out || (depth && !inst_frame))
+        return fail(A3D_EINVAL, "a3d_plane_offsets: null pointer");
+    if (n_inst > 0x7fffffff) return fail(A3D_ELIMIT, "a3d_plane_offsets: too many instances");
+    k_plane_offsets<<<(unsigned)n_inst, 256, 0, (cudaStream_t)stream>>>(depth, rays, H, W, pitch_words(W), bits, bbox,
+                                                                         inst_mask, inst_frame, normals, offset_out,
+                                                                         count_out);
     A3D_CUDA_TRY(cudaGetLastError());
     return A3D_OK;
 }

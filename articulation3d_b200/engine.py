@@ -289,3 +289,63 @@ def emit_masks(bits: torch.Tensor, index: torch.Tensor | None, H: int, W: int,
             _lib.check(lib.a3d_emit_masks(src.data_ptr(), idx_ptr, hi - lo, H, W, code,
                                           out[lo:hi].data_ptr(), _stream_ptr()), "a3d_emit_masks")
     return out
+
+
+def rle_to_pool(rles, H: int, W: int, device) -> MaskPool:
+    """COCO RLE dicts -> MaskPool, decoded on the device straight into packed bits
+    (no dense mask is ever materialised).  ``rles``: sequence of
+    ``{'size': [H, W], 'counts': bytes | str | list}``."""
+    from . import rle as _rle
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.A3DError("rle_to_pool needs a CUDA device (the hot path has no CPU fallback)")
+    runs = []
+    for r in rles:
+        if list(r["size"]) != [H, W]:
+            raise ValueError(f"RLE size {r['size']} != {[H, W]}")
+        c = _rle.rle_counts(r)
+        if int(c.astype(np.int64).sum()) != H * W:
+            raise ValueError("RLE run lengths do not cover the mask")
+        runs.append(c)
+    n = len(runs)
+    begin = np.zeros(n + 1, dtype=np.int64)
+    begin[1:] = np.cumsum([len(c) for c in runs])
+    flat = np.concatenate(runs).astype(np.uint32) if n else np.zeros(0, np.uint32)
+    pitch = _lib.pitch_words(W)
+    with torch.cuda.device(device):
+        d_counts = torch.from_numpy(flat.view(np.int32)).to(device)
+        d_begin = torch.from_numpy(begin).to(device)
+        bits = torch.empty(n, H, pitch, dtype=torch.int32, device=device)
+        _lib.check(lib.a3d_rle_to_bits(d_counts.data_ptr(), d_begin.data_ptr(), n, H, W, bits.data_ptr(),
+                                       _stream_ptr()), "a3d_rle_to_bits")
+    return pool_from_bits(bits, H, W)
+
+
+def plane_offsets(pool: MaskPool, inst_mask: torch.Tensor, normals: torch.Tensor, rays: torch.Tensor,
+                  depth: torch.Tensor | None = None, inst_frame: torch.Tensor | None = None):
+    """Per instance: mean over its mask of ``normal . (rays * depth)`` and the pixel count.
+
+    rays (3,H,W) fp32; depth (F,H,W) fp32 or None (``rays`` already holds XYZ);
+    inst_mask / inst_frame (n,) int32; normals (n,3) fp32.  All on the device."""
+    lib = _lib.load()
+    for t, name in ((pool.bits, "pool"), (inst_mask, "inst_mask"), (normals, "normals"), (rays, "rays")):
+        _require_cuda(t, name)
+    n = int(inst_mask.numel())
+    dev = pool.bits.device
+    off = torch.empty(n, dtype=torch.float32, device=dev)
+    cnt = torch.empty(n, dtype=torch.int32, device=dev)
+    rays = rays.contiguous().float()
+    normals = normals.contiguous().float()
+    inst_mask = inst_mask.contiguous().to(torch.int32)
+    if depth is not None:
+        depth = depth.contiguous().float()
+        inst_frame = inst_frame.contiguous().to(torch.int32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.a3d_plane_offsets(depth.data_ptr() if depth is not None else None, rays.data_ptr(),
+                                         pool.H, pool.W, pool.bits.data_ptr(), pool.bbox.data_ptr(),
+                                         inst_mask.data_ptr(),
+                                         inst_frame.data_ptr() if depth is not None else None,
+                                         normals.data_ptr(), n, off.data_ptr(), cnt.data_ptr(), _stream_ptr()),
+                   "a3d_plane_offsets")
+    return off, cnt

@@ -285,9 +285,16 @@ def _rebuild(p_instance, scores):
     out.pred_planes = p_instance.pred_planes
     out.pred_rot_axis = p_instance.pred_rot_axis
     out.pred_tran_axis = p_instance.pred_tran_axis
-    out.pred_masks = p_instance.pred_masks
+    if _has(p_instance, 'pred_masks'):
+        out.pred_masks = p_instance.pred_masks
+    if _has(p_instance, 'pred_rle'):
+        out.pred_rle = p_instance.pred_rle
     out.pred_classes = p_instance.pred_classes
     return out
+
+
+def _has(p_instance, name: str) -> bool:
+    return p_instance.has(name) if hasattr(p_instance, 'has') else hasattr(p_instance, name)
 
 
 def _write_back(preds, planes, cfg: OptConfig, kind: str):
@@ -349,7 +356,7 @@ class _Session:
         self.device = torch.device(device)
         self.ws = engine.Workspace(self.device)
         self.pool_of = []                   # per video: {(frame, box_id): pool index}
-        chunks, n = [], 0
+        chunks, rles, n = [], [], 0
         for preds, plane_lists in videos:
             need = {}
             for planes in plane_lists:
@@ -359,11 +366,14 @@ class _Session:
             index = {}
             for f in sorted(need):
                 boxes = sorted(need[f])
-                m = preds[f].pred_masks
-                sel = m if len(boxes) == m.shape[0] else m[boxes]
-                if tuple(sel.shape[1:]) != (cfg.height, cfg.width):
-                    raise ValueError(f"mask shape {tuple(sel.shape[1:])} != camera {cfg.height}x{cfg.width}")
-                chunks.append(sel)
+                if _has(preds[f], 'pred_masks'):
+                    m = preds[f].pred_masks
+                    sel = m if len(boxes) == m.shape[0] else m[boxes]
+                    if tuple(sel.shape[1:]) != (cfg.height, cfg.width):
+                        raise ValueError(f"mask shape {tuple(sel.shape[1:])} != camera {cfg.height}x{cfg.width}")
+                    chunks.append(sel)
+                else:                        # run-length masks, decoded on the device
+                    rles.extend(preds[f].pred_rle[b] for b in boxes)
                 for b in boxes:
                     index[(f, b)] = n
                     n += 1
@@ -371,6 +381,12 @@ class _Session:
         self.h2d_bytes = 0
         if n == 0:
             self.pool = None
+            return
+        if rles:
+            if chunks:
+                raise ValueError("mixing dense pred_masks and pred_rle frames is not supported")
+            self.pool = engine.rle_to_pool(rles, cfg.height, cfg.width, self.device)
+            self.h2d_bytes += sum(len(r["counts"]) for r in rles)
             return
         dev_chunks = []
         for c in chunks:

@@ -150,6 +150,28 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
 int a3d_emit_masks(const uint32_t* bits, const int32_t* index, int64_t n, int H, int W,
                    int out_dtype, void* out, void* stream);
 
+/* (f2) COCO RLE -> packed masks on the device.  Replaces
+ * pycocotools mask_util.decode in create_instances (utils/arti_vis.py:182) and
+ * override_depth (:135).
+ *   counts  concatenated run lengths of all masks (runs alternate 0/1, start with 0,
+ *           column-major order); begin [n+1] offsets into counts
+ *   bits    [n][H][pitch]                                                          */
+int a3d_rle_to_bits(const uint32_t* counts, const int64_t* begin, int64_t n, int H, int W,
+                    uint32_t* bits, void* stream);
+
+/* (f1) plane offset implied by the depth map: for every instance the mean
+ * over its mask of normal . (rays * depth).  Replaces the per-instance loop of
+ * override_depth (utils/arti_vis.py:125-149) and depth2XYZ (:90-99).
+ *   depth     [n_frames][H][W] fp32, or NULL when `rays` already holds XYZ
+ *   rays      [3][H][W] fp32  K^-1 [x y 1] table (get_K_inv_dot_xy_1, :101-122)
+ *   bits/bbox mask pool and its a3d_mask_meta boxes
+ *   inst_mask [n_inst] pool index, inst_frame [n_inst] depth frame, normals [n_inst][3]
+ *   offset_out [n_inst] fp32 mean (0 when the mask is empty), count_out [n_inst] pixels */
+int a3d_plane_offsets(const float* depth, const float* rays, int H, int W, const uint32_t* bits,
+                      const int32_t* bbox, const int32_t* inst_mask, const int32_t* inst_frame,
+                      const float* normals, int64_t n_inst, float* offset_out, int32_t* count_out,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif
