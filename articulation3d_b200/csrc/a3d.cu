@@ -557,7 +557,7 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
 // Tensor maps: uint32 [n_masks*H][pitch] with boxes {bw, R}; out-of-range
 // columns are zero-filled by the TMA unit.
 // ---------------------------------------------------------------------------
-constexpr int kTmaTT = 16, kTmaCT = 8, kTmaMasks = kTmaTT + kTmaCT;
+constexpr int kTmaTT = 8, kTmaCT = 16, kTmaMasks = kTmaTT + kTmaCT;
 constexpr int kTmaTileWords = 256;
 constexpr int kTmaStages = 2;
 constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * kTmaMasks * kTmaTileWords * 4 + 64;
@@ -593,7 +593,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ jobs, int H, int pitch,
             int tt_tiles, int ct_tiles, const int32_t* __restrict__ tgt_popc,
             const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
@@ -601,7 +601,8 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
             unsigned long long* __restrict__ key_ws, int32_t* __restrict__ inter_tab) {
     extern __shared__ __align__(1024) uint32_t tiles[];      // [stage][mask][256 words]
     __shared__ int s_mask_row0[kTmaMasks];                   // first tensor row of every mask of the tile
-    __shared__ int s_box[8];                                 // union boxes: cand r0,r1,c0,c1 | tgt r0,r1,c0,c1
+    __shared__ int s_mbox[kTmaMasks][4];                     // bounding box of every mask of the tile
+    __shared__ int s_wbox[8][4];                             // per-warp region
     uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + kTmaStages * kTmaMasks * kTmaTileWords);
 
     const int per_job = tt_tiles * ct_tiles;
@@ -614,42 +615,59 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntile_t = min(kTmaTT, job.n_tgt - tb), ntile_c = min(kTmaCT, job.n_cand - cb);
 
-    if (threadIdx.x < 8) s_box[threadIdx.x] = (threadIdx.x & 1) ? -1 : 0x7fffffff;
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&bars[0]), 1);
         mbar_init(smem_u32(&bars[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
     if (threadIdx.x < kTmaMasks) {
         const int m = threadIdx.x;
         const int32_t* b;
-        int base;
         if (m < kTmaTT) {
             const int ti = tgt_index[job.tgt_begin + tb + min(m, ntile_t - 1)];
             s_mask_row0[m] = ti * H;
             b = tgt_bbox + 4 * (size_t)ti;
-            base = 4;
         } else {
             const int g = job.cand_begin + cb + min(m - kTmaTT, ntile_c - 1);
             s_mask_row0[m] = g * H;
             b = proj_bbox + 4 * (size_t)g;
-            base = 0;
         }
-        if (b[1] >= b[0]) {
-            atomicMin(&s_box[base + 0], b[0]); atomicMax(&s_box[base + 1], b[1]);
-            atomicMin(&s_box[base + 2], b[2]); atomicMax(&s_box[base + 3], b[3]);
-        }
+        s_mbox[m][0] = b[0]; s_mbox[m][1] = b[1]; s_mbox[m][2] = b[2]; s_mbox[m][3] = b[3];
     }
     __syncthreads();
-    const int ra = max(s_box[0], s_box[4]), rb = min(s_box[1], s_box[5]);
+
+    // this warp's 4 targets x 4 candidates inside the tile, and its own overlap box:
+    // (union of its candidate boxes) ∩ (union of its target boxes)
+    const int tw = (warp >> 2) * 4, cw = (warp & 3) * 4;
+    const bool active = tw < ntile_t && cw < ntile_c;
+    int wra = 0, wrb = -1, wca = 0, wcb = -1;
+    if (active) {
+        int pr0 = 0x7fffffff, pr1 = -1, pc0 = 0x7fffffff, pc1 = -1;
+        int qr0 = 0x7fffffff, qr1 = -1, qc0 = 0x7fffffff, qc1 = -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int* t = s_mbox[min(tw + i, ntile_t - 1)];
+            if (t[1] >= t[0]) { qr0 = min(qr0, t[0]); qr1 = max(qr1, t[1]); qc0 = min(qc0, t[2]); qc1 = max(qc1, t[3]); }
+            const int* c = s_mbox[kTmaTT + min(cw + i, ntile_c - 1)];
+            if (c[1] >= c[0]) { pr0 = min(pr0, c[0]); pr1 = max(pr1, c[1]); pc0 = min(pc0, c[2]); pc1 = max(pc1, c[3]); }
+        }
+        wra = max(pr0, qr0); wrb = min(pr1, qr1); wca = max(pc0, qc0); wcb = min(pc1, qc1);
+        if (wrb < wra || wcb < wca) { wra = 0; wrb = -1; wca = 0; wcb = -1; }
+    }
+    if (lane == 0) { s_wbox[warp][0] = wra; s_wbox[warp][1] = wrb; s_wbox[warp][2] = wca; s_wbox[warp][3] = wcb; }
+    __syncthreads();
+    // staged box of the CTA = hull of the warps' regions
+    int ra = 0x7fffffff, rb = -1, ca = 0x7fffffff, cbw = -1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (s_wbox[i][1] >= s_wbox[i][0]) {
+            ra = min(ra, s_wbox[i][0]); rb = max(rb, s_wbox[i][1]);
+            ca = min(ca, s_wbox[i][2]); cbw = max(cbw, s_wbox[i][3]);
+        }
     // TMA needs the box to start on a 16-byte boundary in global memory (measured on B200:
     // an inner coordinate that is not a multiple of 4 words raises an illegal instruction)
-    const int ca = max(s_box[2], s_box[6]) & ~3, cbw = min(s_box[3], s_box[7]);
+    ca &= ~3;
 
-    // this warp's 4 targets x 4 candidates inside the tile
-    const int tw = (warp >> 1) * 4, cw = (warp & 1) * 4;
-    const bool active = tw < ntile_t && cw < ntile_c;
     int acc2[4][4];
     uint32_t ones[4][4];
 #pragma unroll
@@ -657,7 +675,7 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 4; ++k) { acc2[i][k] = 0; ones[i][k] = 0u; }
 
-    if (rb >= ra && cbw >= ca) {
+    if (rb >= ra) {
         const int ncols = cbw - ca + 1;
         const int sel = ncols <= maps.bw[0] ? 0 : (ncols <= maps.bw[1] ? 1 : (ncols <= maps.bw[2] ? 2 : 3));
         const int bw = maps.bw[sel], R = maps.rows[sel];
@@ -689,31 +707,45 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
         for (int chunk = 0; chunk < nchunks; ++chunk) {
             if (warp == 0 && chunk + 1 < nchunks) issue(chunk + 1);
             mbar_wait(smem_u32(&bars[chunk & 1]), (uint32_t)((chunk >> 1) & 1));
-            if (active) {
-                const int r = ra + (chunk / ncb) * R;
-                const int nv = min(R, H - r) * bw;              // rows past the image belong to another mask
+            // this warp's rows / columns inside the staged box (rows past the image belong to another mask)
+            const int r0 = ra + (chunk / ncb) * R, c0 = ca + (chunk % ncb) * bw;
+            const int ya = max(wra, r0), yb = min(min(wrb, r0 + R - 1), H - 1);
+            const int xa = max(wca, c0), xb = min(wcb, c0 + bw - 1);
+            if (yb >= ya && xb >= xa) {
+                const int ncw = xb - xa + 1;
+                const int total = (yb - ya + 1) * ncw;
                 const uint32_t* st = tiles + (size_t)(chunk & 1) * kTmaMasks * kTmaTileWords;
-                const uint32_t* tbase = st + (size_t)tw * kTmaTileWords;
-                const uint32_t* pbase = st + (size_t)(kTmaTT + cw) * kTmaTileWords;
+                const uint32_t* tbase = st + (size_t)tw * kTmaTileWords + (ya - r0) * bw + (xa - c0);
+                const uint32_t* pbase = st + (size_t)(kTmaTT + cw) * kTmaTileWords + (ya - r0) * bw + (xa - c0);
+                const int dr = 64 / ncw, dc = 64 - dr * ncw;
+                int rA = lane / ncw, cA = lane - rA * ncw;
+                int rB = (lane + 32) / ncw, cB = (lane + 32) - rB * ncw;
+                for (int idx = lane; idx < total; idx += 64) {
+                    const int oA = rA * bw + cA;
+                    const bool hasB = idx + 32 < total;
+                    const int oB = hasB ? rB * bw + cB : oA;
+                    uint32_t tA[4], pA[4], tB[4], pB[4];
 #pragma unroll
-                for (int it = 0; it < kTmaTileWords / 64; ++it) {
-                    const int w = 2 * lane + 64 * it;
-                    if (w < nv) {
-                        uint2 t[4], q[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            t[i] = *reinterpret_cast<const uint2*>(tbase + i * kTmaTileWords + w);
-                            q[i] = *reinterpret_cast<const uint2*>(pbase + i * kTmaTileWords + w);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t a = t[i].x & q[k].x, b = t[i].y & q[k].y, o = ones[i][k];
-                                ones[i][k] = o ^ a ^ b;
-                                acc2[i][k] += __popc((o & a) | (o & b) | (a & b));
-                            }
+                    for (int i = 0; i < 4; ++i) {
+                        tA[i] = tbase[i * kTmaTileWords + oA]; pA[i] = pbase[i * kTmaTileWords + oA];
+                        tB[i] = tbase[i * kTmaTileWords + oB]; pB[i] = pbase[i * kTmaTileWords + oB];
                     }
+                    if (!hasB) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) tB[i] = 0u;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t a = tA[i] & pA[k], b = tB[i] & pB[k], o = ones[i][k];
+                            ones[i][k] = o ^ a ^ b;
+                            acc2[i][k] += __popc((o & a) | (o & b) | (a & b));
+                        }
+                    rA += dr; cA += dc;
+                    if (cA >= ncw) { cA -= ncw; ++rA; }
+                    rB += dr; cB += dc;
+                    if (cB >= ncw) { cB -= ncw; ++rB; }
                 }
             }
             __syncthreads();                                    // stage may be refilled by the next issue
@@ -1093,10 +1125,9 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
     cudaStream_t s = (cudaStream_t)stream;
     A3D_CUDA_TRY(cudaMemsetAsync(key_ws, 0, sizeof(uint64_t) * (size_t)n_tgt_total, s));
 
-    static const int use_ldg = [] {
-        const char* e = getenv("A3D_SCORE_KERNEL");
-        return (e && !strcmp(e, "ldg")) ? 1 : 0;
-    }();
+    // A3D_SCORE_KERNEL=ldg selects the direct-load kernel (kept for A/B measurements)
+    const char* env_kernel = getenv("A3D_SCORE_KERNEL");
+    const bool use_ldg = env_kernel && !strcmp(env_kernel, "ldg");
     const bool tma_ok = !use_ldg && (n_pool_masks * H < 0x7fffffffLL) && (n_cand_total * H < 0x7fffffffLL);
     if (tma_ok) {
         // mask tiles staged by TMA: one tensor map per (array, box width)

@@ -110,7 +110,9 @@ def _check_pass(res, batch, proj_want, tgt_masks, W):
 
 @pytest.mark.parametrize("mode", [_lib.MODE_SEQ, _lib.MODE_COMPOSED, _lib.MODE_TRANSLATE])
 @pytest.mark.parametrize("tile", [1, 4, None])
-def test_project_and_score_match_oracle(mode, tile):
+@pytest.mark.parametrize("kernel", ["tma", "ldg"])
+def test_project_and_score_match_oracle(mode, tile, kernel, monkeypatch):
+    monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
     cfg, ocfg = OptConfig(), restated.OracleConfig()
     preds, _ = synth.make_video(77, 3, 10, kinds=[0, 1, 0])
     box = 1 if mode == _lib.MODE_TRANSLATE else 0
@@ -125,8 +127,10 @@ def test_project_and_score_match_oracle(mode, tile):
         _check_pass(res, batch, want, masks.numpy() > 0.5, cfg.width)
 
 
-def test_odd_resolution_and_many_candidates():
+@pytest.mark.parametrize("kernel", ["tma", "ldg"])
+def test_odd_resolution_and_many_candidates(kernel, monkeypatch):
     """W not a multiple of 32, scaled intrinsics, a 97-candidate grid, ragged targets."""
+    monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
     H, W = 150, 200
     cfg = OptConfig.scaled(W, H)
     ocfg = restated.OracleConfig(height=H, width=W, focal_length=cfg.focal_length)
@@ -140,7 +144,9 @@ def test_odd_resolution_and_many_candidates():
     _check_pass(res, batch, want, (masks.numpy() > 0.5)[tg], W)
 
 
-def test_edge_cases_empty_source_degenerate_axis_behind_camera():
+@pytest.mark.parametrize("kernel", ["tma", "ldg"])
+def test_edge_cases_empty_source_degenerate_axis_behind_camera(kernel, monkeypatch):
+    monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
     cfg, ocfg = OptConfig(), restated.OracleConfig()
     preds, _ = synth.make_video(8, 1, 10, kinds=[0])
     T = len(preds)
