@@ -434,7 +434,8 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
 constexpr int kScoreTT = 8;    // targets per CTA
 constexpr int kScoreCT = 16;   // candidates per CTA
 
-__global__ void __launch_bounds__(256)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int ct_tiles,
         const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
         const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
@@ -1125,10 +1126,12 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
     cudaStream_t s = (cudaStream_t)stream;
     A3D_CUDA_TRY(cudaMemsetAsync(key_ws, 0, sizeof(uint64_t) * (size_t)n_tgt_total, s));
 
-    // A3D_SCORE_KERNEL=ldg selects the direct-load kernel (kept for A/B measurements)
+    // Two scoring kernels with identical results.  Default: k_score (direct loads, per-warp
+    // regions; the masks of one job are L1/L2 resident) — measured faster on B200 than the
+    // TMA-staged k_score_tma (profiles/r1_*), which A3D_SCORE_KERNEL=tma selects.
     const char* env_kernel = getenv("A3D_SCORE_KERNEL");
-    const bool use_ldg = env_kernel && !strcmp(env_kernel, "ldg");
-    const bool tma_ok = !use_ldg && (n_pool_masks * H < 0x7fffffffLL) && (n_cand_total * H < 0x7fffffffLL);
+    const bool use_tma = env_kernel && !strcmp(env_kernel, "tma");
+    const bool tma_ok = use_tma && (n_pool_masks * H < 0x7fffffffLL) && (n_cand_total * H < 0x7fffffffLL);
     if (tma_ok) {
         // mask tiles staged by TMA: one tensor map per (array, box width)
         TmaMaps maps;
@@ -1154,9 +1157,15 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
         const int tt_tiles = (max_tgt + kScoreTT - 1) / kScoreTT, ct_tiles = (max_cand + kScoreCT - 1) / kScoreCT;
         const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
         if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
-        k_score<<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc, tgt_bbox,
-                                                  tgt_index, proj_bits, proj_popc, proj_bbox,
-                                                  (unsigned long long*)key_ws, inter_tab);
+        const char* occ = getenv("A3D_SCORE_OCC");
+        if (occ && occ[0] == '3')
+            k_score<3><<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc, tgt_bbox,
+                                                         tgt_index, proj_bits, proj_popc, proj_bbox,
+                                                         (unsigned long long*)key_ws, inter_tab);
+        else
+            k_score<2><<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc, tgt_bbox,
+                                                         tgt_index, proj_bits, proj_popc, proj_bbox,
+                                                         (unsigned long long*)key_ws, inter_tab);
     }
     A3D_CUDA_TRY(cudaGetLastError());
     const dim3 fgrid((unsigned)n_jobs, (unsigned)((max_tgt + 7) / 8 < 64 ? (max_tgt + 7) / 8 : 64));

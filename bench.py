@@ -180,24 +180,11 @@ def reference_arm(args, wl):
 # --------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------
-def gpu_arm(args, wl):
-    from articulation3d_b200 import engine, opt_utils, workloads
+def measure_pass(wl, steps, warmup, dev, rank, world, dist, sample_clocks=True):
+    """Device-resident scoring passes of one workload: K timed steps with CUDA events on the
+    launching stream -> dict(value, ms, roofline, ...).  Every rank runs its own workload."""
+    from articulation3d_b200 import engine, workloads
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback "
-                         "(use --impl reference for the CPU oracle port)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-        dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
-
-    # ---- device-resident pass ------------------------------------------------------
     inp = workloads.build_pass(wl, seed0=2020 + 1000 * rank, device=dev)
     ws = engine.Workspace(dev)
     packed_bytes = inp.pool.bits.numel() * 4
@@ -237,19 +224,19 @@ def gpu_arm(args, wl):
             evs[2].record()
         return res
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         one_step()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank).start() if rank == 0 else None
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(dev.index).start() if (rank == 0 and sample_clocks) else None
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     wall0 = time.perf_counter()
     # Let the host run ahead of the device: the GPU spins ~40 ms while all K steps are
     # enqueued, so the event intervals below contain kernel time only, never launch gaps.
     torch.cuda._sleep(int(0.04 * 1.9e9))
-    for k in range(args.steps):
+    for k in range(steps):
         one_step(events[k])
     torch.cuda.synchronize()
     if dist:
@@ -257,13 +244,13 @@ def gpu_arm(args, wl):
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
-    t_proj = sum(e[0].elapsed_time(e[1]) for e in events) / args.steps          # ms
-    t_score = sum(e[1].elapsed_time(e[2]) for e in events) / args.steps
-    t_step = sum(e[0].elapsed_time(e[2]) for e in events) / args.steps
+    t_proj = sum(e[0].elapsed_time(e[1]) for e in events) / steps          # ms
+    t_score = sum(e[1].elapsed_time(e[2]) for e in events) / steps
+    t_step = sum(e[0].elapsed_time(e[2]) for e in events) / steps
     if world > 1:
         # exposed tail of the last (un-overlapped) gather, amortised over the K steps
         last = comm_done[(step_no[0] - 1) & 1]
-        t_step += max(0.0, events[-1][2].elapsed_time(last)) / args.steps
+        t_step += max(0.0, events[-1][2].elapsed_time(last)) / steps
         t = torch.tensor([t_step, t_proj, t_score], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_step, t_proj, t_score = t.tolist()
@@ -273,19 +260,55 @@ def gpu_arm(args, wl):
     # ---- roofline of the dominant kernel ---------------------------------------------
     peak, peak_src = _peaks()
     alg = wl.alg_bytes_per_pass()
-    dom, t_dom = ("a3d_project (k_project)", t_proj) if t_proj >= t_score else ("a3d_score (k_score+k_finalize)", t_score)
+    proj_dom = t_proj >= t_score
+    dom, t_dom = ("a3d_project (k_unproject + k_project)", t_proj) if proj_dom else \
+                 ("a3d_score (k_score + k_finalize)", t_score)
     achieved = alg / (t_dom * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(wl.name, {}).get("k_project" if t_proj >= t_score else "k_score")
+            traffic = json.load(f).get(wl.name, {}).get("k_project" if proj_dom else "k_score")
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg, "kernel_ms": t_dom,
                 "kernels_ms": {"project": t_proj, "score": t_score, "step": t_step},
-                "note": "bit-packed masks make the pass ALU-bound (popcount / fp32 splat), not HBM-bound; "
+                "note": "bit-packed masks make the pass ALU-bound (fp32 splat / AND+POPC), not HBM-bound; "
                         "achieved = SURVEY 8d algorithmic bytes / dominant-kernel time"}
+    del inp, ws
+    torch.cuda.empty_cache()
+    return {"value": value, "ms_per_step": t_step, "roofline": roofline, "units_per_step_per_gpu": units_all // world,
+            "packed_mask_bytes_per_gpu": packed_bytes,
+            "l2": "flushed between steps (256 MiB write)" if flush is not None else "inputs exceed L2",
+            "clocks": clocks, "wall_s": wall}
+
+
+def gpu_arm(args, wl):
+    from articulation3d_b200 import opt_utils, workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    m = measure_pass(wl, args.steps, args.warmup, dev, rank, world, dist)
+    # the same pass at throughput scale (one 8-GPU shard of configs[2]) rides along as context
+    batched = None
+    if args.batched and wl.name == "c2":
+        wb = workloads.WORKLOADS["c3_shard"]
+        mb = measure_pass(wb, max(3, min(args.steps, 10)), 3, dev, rank, world, dist, sample_clocks=False)
+        batched = {"workload": wb.description, "value": mb["value"], "unit": UNIT, "ms_per_step": mb["ms_per_step"],
+                   "units_per_step_per_gpu": mb["units_per_step_per_gpu"], "l2": mb["l2"],
+                   "roofline": mb["roofline"]}
 
     line = None
     if rank == 0:
@@ -301,17 +324,17 @@ def gpu_arm(args, wl):
             cpu = {"value": u / dt, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{tr} track(s) x {fr} frames of {wl.name}, optimize_planes('3dc'), {dt:.1f} s"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": t_step, "higher_is_better": True,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 popcount / fp32+fp64 geometry",
             "data": "synthetic",
             "config": {"workload": wl.description, "name": wl.name, "per_gpu": True,
-                       "units_per_step_per_gpu": inp.units, "packed_mask_bytes_per_gpu": packed_bytes,
-                       "l2": "flushed between steps (256 MiB write)" if flush is not None else "inputs exceed L2",
+                       "units_per_step_per_gpu": m["units_per_step_per_gpu"],
+                       "packed_mask_bytes_per_gpu": m["packed_mask_bytes_per_gpu"], "l2": m["l2"],
                        "parallelism": (f"videos sharded x{world}; per step one NCCL all_gather of 12 B/track-frame "
                                        f"records on a side stream (overlaps the next step)") if world > 1 else "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 4 * args.steps, "clocks": clocks, "wall_s": wall,
+            "roofline": m["roofline"], "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": 4 * args.steps, "clocks": m["clocks"], "wall_s": m["wall_s"], "batched": batched,
         }
         print(json.dumps(line), flush=True)
     if dist:
@@ -414,6 +437,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", dest="batched", action="store_false",
+                    help="skip the extra c3_shard measurement reported under 'batched'")
     args = ap.parse_args()
     from articulation3d_b200 import workloads
     wl = workloads.WORKLOADS[args.workload]
