@@ -431,6 +431,15 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
 // one POPC (quarter-rate pipe) serves two words.  CTAs are ordered job-major so
 // one job's masks stay L2-resident while its tiles run.
 // ---------------------------------------------------------------------------
+// arg-max key: IoU bits in the high word (IoU >= 0 or NaN, so unsigned order = float order with
+// NaN on top, as torch.argmax), then the candidate index inverted so the FIRST maximum wins.
+// When candidates < 4096 and the mask has < 2^20 pixels the intersection count rides in the low
+// 20 bits ("packed"), so the winner's counts need no recomputation.
+__device__ __forceinline__ unsigned long long make_key(float iou, int cand, int inter, int packed) {
+    const unsigned lo = packed ? (((0xfffu - (unsigned)cand) << 20) | (unsigned)inter) : ~(unsigned)cand;
+    return ((unsigned long long)__float_as_uint(iou) << 32) | lo;
+}
+
 constexpr int kScoreTT = 8;    // targets per CTA
 constexpr int kScoreCT = 16;   // candidates per CTA
 
@@ -441,7 +450,7 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
         const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
         const uint32_t* __restrict__ proj_bits, const int32_t* __restrict__ proj_popc,
         const int32_t* __restrict__ proj_bbox, unsigned long long* __restrict__ key_ws,
-        int32_t* __restrict__ inter_tab) {
+        int32_t* __restrict__ inter_tab, int packed) {
     const int per_job = tt_tiles * ct_tiles;
     const int jid = blockIdx.x / per_job;
     const int rem = blockIdx.x - jid * per_job;
@@ -538,8 +547,7 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
                 const int inter = acc[i][k];
                 const int uni = pt + proj_popc[(size_t)job.cand_begin + c0 + k] - inter;
                 const float iou = __fdiv_rn((float)inter, (float)uni);
-                const unsigned long long key =
-                    ((unsigned long long)__float_as_uint(iou) << 32) | (unsigned)(~(unsigned)(c0 + k));
+                const unsigned long long key = make_key(iou, c0 + k, inter, packed);
                 best = key > best ? key : best;
                 if (inter_tab) inter_tab[job.tab_begin + (int64_t)(t0 + i) * job.n_cand + c0 + k] = inter;
             }
@@ -599,7 +607,7 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
             int tt_tiles, int ct_tiles, const int32_t* __restrict__ tgt_popc,
             const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
             const int32_t* __restrict__ proj_popc, const int32_t* __restrict__ proj_bbox,
-            unsigned long long* __restrict__ key_ws, int32_t* __restrict__ inter_tab) {
+            unsigned long long* __restrict__ key_ws, int32_t* __restrict__ inter_tab, int packed) {
     extern __shared__ __align__(1024) uint32_t tiles[];      // [stage][mask][256 words]
     __shared__ int s_mask_row0[kTmaMasks];                   // first tensor row of every mask of the tile
     __shared__ int s_mbox[kTmaMasks][4];                     // bounding box of every mask of the tile
@@ -775,8 +783,7 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
                 const int inter = acc[i][k];
                 const int uni = pt + proj_popc[(size_t)job.cand_begin + c0 + k] - inter;
                 const float iou = __fdiv_rn((float)inter, (float)uni);
-                const unsigned long long key =
-                    ((unsigned long long)__float_as_uint(iou) << 32) | (unsigned)(~(unsigned)(c0 + k));
+                const unsigned long long key = make_key(iou, c0 + k, inter, packed);
                 best = key > best ? key : best;
                 if (inter_tab) inter_tab[job.tab_begin + (int64_t)(t0 + i) * job.n_cand + c0 + k] = inter;
             }
@@ -785,7 +792,8 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
     }
 }
 
-// one warp per target: decode the winning candidate and recompute its counts
+// decode the winning candidate of every target.  Packed keys carry the intersection count
+// (one thread per target); otherwise one warp per target recomputes it over the candidate's box.
 __global__ void __launch_bounds__(256)
 k_finalize(const a3d_job_t* __restrict__ jobs, int H, int pitch,
            const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
@@ -793,8 +801,21 @@ k_finalize(const a3d_job_t* __restrict__ jobs, int H, int pitch,
            const int32_t* __restrict__ proj_popc, const int32_t* __restrict__ proj_bbox,
            const unsigned long long* __restrict__ key_ws, int32_t* __restrict__ best_cand,
            int32_t* __restrict__ best_inter, int32_t* __restrict__ best_union,
-           float* __restrict__ best_iou) {
+           float* __restrict__ best_iou, int packed) {
     const a3d_job_t job = jobs[blockIdx.x];
+    if (packed) {
+        for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < job.n_tgt; t += gridDim.y * blockDim.x) {
+            const size_t slot = (size_t)job.tgt_begin + t;
+            const unsigned lo = (unsigned)(key_ws[slot] & 0xffffffffull);
+            const int cand = (int)(0xfffu - (lo >> 20)), inter = (int)(lo & 0xfffffu);
+            const int uni = tgt_popc[tgt_index[slot]] + proj_popc[(size_t)job.cand_begin + cand] - inter;
+            best_cand[slot] = cand;
+            best_inter[slot] = inter;
+            best_union[slot] = uni;
+            best_iou[slot] = __fdiv_rn((float)inter, (float)uni);
+        }
+        return;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const size_t words = (size_t)H * pitch;
     for (int t = blockIdx.y * nw + warp; t < job.n_tgt; t += gridDim.y * nw) {
@@ -1125,6 +1146,9 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
     const int pitch = pitch_words(W);
     cudaStream_t s = (cudaStream_t)stream;
     A3D_CUDA_TRY(cudaMemsetAsync(key_ws, 0, sizeof(uint64_t) * (size_t)n_tgt_total, s));
+    // the winner's intersection count fits the key when candidates < 4096 and pixels < 2^20
+    const char* env_key = getenv("A3D_SCORE_KEY");
+    const int packed = (max_cand <= 4096 && (long long)H * W < (1 << 20) && !(env_key && !strcmp(env_key, "wide"))) ? 1 : 0;
 
     // Two scoring kernels with identical results.  Default: k_score (direct loads, per-warp
     // regions; the masks of one job are L1/L2 resident) — measured faster on B200 than the
@@ -1152,20 +1176,21 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
         A3D_CUDA_TRY(cudaFuncSetAttribute(k_score_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
         k_score_tma<<<(unsigned)nblocks, 256, kTmaSmemBytes, s>>>(maps, jobs, H, pitch, tt_tiles, ct_tiles, tgt_popc,
                                                                   tgt_bbox, tgt_index, proj_popc, proj_bbox,
-                                                                  (unsigned long long*)key_ws, inter_tab);
+                                                                  (unsigned long long*)key_ws, inter_tab, packed);
     } else {
         const int tt_tiles = (max_tgt + kScoreTT - 1) / kScoreTT, ct_tiles = (max_cand + kScoreCT - 1) / kScoreCT;
         const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
         if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
         k_score<<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc, tgt_bbox,
                                                   tgt_index, proj_bits, proj_popc, proj_bbox,
-                                                  (unsigned long long*)key_ws, inter_tab);
+                                                  (unsigned long long*)key_ws, inter_tab, packed);
     }
     A3D_CUDA_TRY(cudaGetLastError());
-    const dim3 fgrid((unsigned)n_jobs, (unsigned)((max_tgt + 7) / 8 < 64 ? (max_tgt + 7) / 8 : 64));
+    const int fy = packed ? (max_tgt + 255) / 256 : ((max_tgt + 7) / 8 < 64 ? (max_tgt + 7) / 8 : 64);
+    const dim3 fgrid((unsigned)n_jobs, (unsigned)fy);
     k_finalize<<<fgrid, 256, 0, s>>>(jobs, H, pitch, tgt_bits, tgt_popc, tgt_index, proj_bits, proj_popc,
                                      proj_bbox, (const unsigned long long*)key_ws, best_cand, best_inter,
-                                     best_union, best_iou);
+                                     best_union, best_iou, packed);
     A3D_CUDA_TRY(cudaGetLastError());
     return A3D_OK;
 }

@@ -221,13 +221,20 @@ class Workspace:
         return buf[:n].view(*shape)
 
 
-def choose_tile(cfg: OptConfig, n_cand_total: int, sm_count: int = 148) -> int:
-    """Candidates per projection CTA: as many as shared memory holds, fewer when
-    the batch would otherwise leave SMs idle."""
+def choose_tile(cfg: OptConfig, n_cand_total: int, n_jobs: int = 1, sm_count: int = 148) -> int:
+    """Candidates per projection CTA.  Large batches take as many as shared memory holds (the
+    point cloud is read once per CTA); small batches pick the tile that minimises
+    waves x (per-CTA overhead + tile) so no SM runs two CTAs while others idle."""
     lib = _lib.load()
     max_tile = _lib.check(lib.a3d_project_max_tile(cfg.height, cfg.width), "a3d_project_max_tile")
-    want = max(1, -(-n_cand_total // (2 * sm_count)))
-    return int(min(max_tile, want))
+    per_job = -(-n_cand_total // max(n_jobs, 1))
+    best, best_cost = max_tile, None
+    for tile in range(max_tile, 0, -1):
+        ctas = n_jobs * -(-per_job // tile)
+        cost = -(-ctas // sm_count) * (0.3 + tile)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = tile, cost
+    return int(best)
 
 
 def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace | None = None,
@@ -257,7 +264,7 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
             return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab)
         cam = camera_struct(cfg)
         stream = _stream_ptr()
-        tile = tile_cand if tile_cand is not None else choose_tile(cfg, nc)
+        tile = tile_cand if tile_cand is not None else choose_tile(cfg, nc, dbatch.n_jobs)
         _lib.check(lib.a3d_project(C.byref(cam), dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_cand, tile,
                                    pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(),
                                    dbatch.xform.data_ptr(), pcd_ws.data_ptr(), pcd_count.data_ptr(),

@@ -363,7 +363,7 @@ def _run_split(engine, inp, ws, evs):
                                                ("best_union", torch.int32), ("best_iou", torch.float32))]
     cam = engine.camera_struct(cfg)
     stream = torch.cuda.current_stream().cuda_stream
-    tile = engine.choose_tile(cfg, nc)
+    tile = engine.choose_tile(cfg, nc, db.n_jobs)
     _lib.check(lib.a3d_project(C.byref(cam), db.jobs.data_ptr(), db.n_jobs, db.max_cand, tile,
                                pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(), db.xform.data_ptr(),
                                pcd_ws.data_ptr(), pcd_count.data_ptr(),

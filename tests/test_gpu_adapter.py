@@ -90,3 +90,32 @@ def test_optimize_planes_from_rle_masks_equals_dense():
                 assert np.array_equal(p['fit']['union'], q['fit']['union'])
     for x, y in zip(oa, ob):
         assert np.array_equal(x.scores, y.scores) and torch.equal(x.pred_rot_axis, y.pred_rot_axis)
+
+
+def test_opt_arti_tool_end_to_end(tmp_path):
+    """synthetic .pth in -> optimised .pth + tracks.json + .obj out, equal to the API run on dense masks."""
+    import json
+    import random
+    from articulation3d_b200 import io, opt_utils
+    from articulation3d_b200.tools import opt_arti
+    inp, out = str(tmp_path / "pred.pth"), str(tmp_path / "out")
+    opt_arti.main(["--input", inp, "--output", out, "--synthetic", "2", "--tracks", "3", "--frames", "14",
+                   "--seed", "2020", "--save-obj", "--device", DEV])
+    for v in range(2):
+        vid = f"synthetic{v:02d}"
+        tracks = json.load(open(f"{out}/{vid}_tracks.json"))
+        recs = torch.load(f"{out}/{vid}_predictions_opt.pth", weights_only=False)
+        assert len(recs) == 14 and any(f.endswith(".obj") for f in __import__("os").listdir(out))
+        preds, _ = synth.make_video(2020 + v, 3, 14)
+        random.seed(2020 + v)
+        planes = opt_utils.track_planes(preds)
+        ref = opt_utils.optimize_planes(preds, planes, '3dc', device=DEV)
+        want = io.tracks_summary(planes)
+        assert [t["has_rot"] for t in tracks] == [t["has_rot"] for t in want]
+        for a, b in zip(tracks, want):
+            if a["has_rot"]:
+                assert [x["angle_id"] for x in a["angle_track"]] == [x["angle_id"] for x in b["angle_track"]]
+                assert [x["inter"] for x in a["angle_track"]] == [x["inter"] for x in b["angle_track"]]
+        for r, p in zip(recs, ref):
+            assert torch.equal(r["pred_rot_axis"], p.pred_rot_axis)
+            assert [i["score"] for i in r["instances"]] == list(p.scores)

@@ -127,10 +127,11 @@ def test_project_and_score_match_oracle(mode, tile, kernel, monkeypatch):
         _check_pass(res, batch, want, masks.numpy() > 0.5, cfg.width)
 
 
-@pytest.mark.parametrize("kernel", ["tma", "ldg"])
-def test_odd_resolution_and_many_candidates(kernel, monkeypatch):
+@pytest.mark.parametrize("kernel,key", [("tma", "packed"), ("ldg", "packed"), ("ldg", "wide"), ("tma", "wide")])
+def test_odd_resolution_and_many_candidates(kernel, key, monkeypatch):
     """W not a multiple of 32, scaled intrinsics, a 97-candidate grid, ragged targets."""
     monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
+    monkeypatch.setenv("A3D_SCORE_KEY", key)
     H, W = 150, 200
     cfg = OptConfig.scaled(W, H)
     ocfg = restated.OracleConfig(height=H, width=W, focal_length=cfg.focal_length)
@@ -195,7 +196,9 @@ def test_edge_cases_empty_source_degenerate_axis_behind_camera(kernel, monkeypat
         _check_pass(res, batch, want, masks.numpy() > 0.5, cfg.width)
 
 
-def test_many_jobs_one_pass_equals_single_jobs():
+@pytest.mark.parametrize("key", ["packed", "wide"])
+def test_many_jobs_one_pass_equals_single_jobs(key, monkeypatch):
+    monkeypatch.setenv("A3D_SCORE_KEY", key)        # "wide": arg-max key without the packed count
     cfg = OptConfig()
     preds, _ = synth.make_video(13, 4, 12, kinds=[0, 0, 1, 0])
     masks = torch.cat([torch.stack([p.pred_masks[b] for p in preds]) for b in range(4)])
