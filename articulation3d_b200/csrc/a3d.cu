@@ -81,6 +81,66 @@ __global__ void __launch_bounds__(256) k_pack(const T* __restrict__ src, int64_t
     }
 }
 
+// Vector variant for row strides that are multiples of 16 bytes (W % 4 == 0 for fp32, W % 16 == 0
+// for u8): every lane loads 4 pixels per access (LDG.128 / LDG.32), 4 accesses in flight, and the
+// 8 lanes of a 32-pixel word combine their nibbles with three shuffles.  128 pixels per warp step.
+__device__ __forceinline__ void load4(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load4(const unsigned char* p, float (&v)[4]) {
+    const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p));
+    v[0] = (float)t.x; v[1] = (float)t.y; v[2] = (float)t.z; v[3] = (float)t.w;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack_vec(const T* __restrict__ src, int64_t n_rows, int W, int pitch,
+                                                  float thresh, uint32_t* __restrict__ gt,
+                                                  uint32_t* __restrict__ nz) {
+    constexpr int kUnroll = 4;
+    const int lane = threadIdx.x & 31;
+    const int segs = (W + 127) >> 7;                         // 128-pixel segments per row
+    const int64_t total = n_rows * segs;
+    const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t it = warp0 * kUnroll; it < total; it += nwarps * kUnroll) {
+        float v[kUnroll][4];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t s = it + u;
+            const int64_t row = s / segs;
+            const int px = (int)(s - row * segs) * 128 + lane * 4;
+            if (s < total && px < W) load4(src + row * (int64_t)W + px, v[u]);
+            else { v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t s = it + u;
+            if (s >= total) break;
+            const int64_t row = s / segs;
+            const int seg = (int)(s - row * segs);
+            uint32_t g = 0, z = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                g |= (uint32_t)(v[u][k] > thresh) << k;
+                z |= (uint32_t)(v[u][k] != 0.f) << k;
+            }
+            const int sh = (lane & 7) * 4;
+            g <<= sh; z <<= sh;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                g |= __shfl_xor_sync(0xffffffffu, g, d);
+                z |= __shfl_xor_sync(0xffffffffu, z, d);
+            }
+            const int word = seg * 4 + (lane >> 3);
+            if ((lane & 7) == 0 && word < pitch) {
+                gt[row * pitch + word] = g;
+                if (nz) nz[row * pitch + word] = z;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // block-level reduction helpers (popcount sum + bounding box)
 // ---------------------------------------------------------------------------
@@ -1054,12 +1114,28 @@ int a3d_pack_masks(const void* src, int dtype, int64_t n, int H, int W, float th
     const int64_t want = (rows + 7) / 8;
     const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
     cudaStream_t s = (cudaStream_t)stream;
-    if (dtype == A3D_F32)
+    if (dtype != A3D_F32 && dtype != A3D_U8) return fail(A3D_EINVAL, "a3d_pack_masks: unknown dtype %d", dtype);
+    const size_t esz = dtype == A3D_F32 ? 4 : 1;
+    const bool vec = ((size_t)W * esz) % 16 == 0 && ((uintptr_t)src % 16) == 0;
+    if (vec) {
+        // words past ceil(W/32) up to the pitch are padding: the vector kernel writes every word it owns,
+        // the remainder (pitch not a multiple of 4 segments) is cleared here
+        const int64_t segs = (W + 127) / 128;
+        if (segs * 4 < pitch) {
+            A3D_CUDA_TRY(cudaMemsetAsync(bits_gt, 0, (size_t)rows * pitch * 4, s));
+            if (bits_nz) A3D_CUDA_TRY(cudaMemsetAsync(bits_nz, 0, (size_t)rows * pitch * 4, s));
+        }
+        const int64_t wantv = (rows * segs + 31) / 32;
+        const int gridv = (int)(wantv < 148 * 16 ? (wantv > 0 ? wantv : 1) : 148 * 16);
+        if (dtype == A3D_F32)
+            k_pack_vec<float><<<gridv, 256, 0, s>>>((const float*)src, rows, W, pitch, thresh, bits_gt, bits_nz);
+        else
+            k_pack_vec<unsigned char><<<gridv, 256, 0, s>>>((const unsigned char*)src, rows, W, pitch, thresh, bits_gt, bits_nz);
+    } else if (dtype == A3D_F32) {
         k_pack<float><<<grid, 256, 0, s>>>((const float*)src, rows, W, pitch, thresh, bits_gt, bits_nz);
-    else if (dtype == A3D_U8)
+    } else {
         k_pack<unsigned char><<<grid, 256, 0, s>>>((const unsigned char*)src, rows, W, pitch, thresh, bits_gt, bits_nz);
-    else
-        return fail(A3D_EINVAL, "a3d_pack_masks: unknown dtype %d", dtype);
+    }
     A3D_CUDA_TRY(cudaGetLastError());
     return A3D_OK;
 }

@@ -312,6 +312,7 @@ def gpu_arm(args, wl):
 
     line = None
     if rank == 0:
+        pack = _pack_stream(dev)
         # ---- e2e through the public API with host buffers ------------------------------
         e2e = _e2e(wl, dev, opt_utils, workloads, steps=max(1, min(args.steps, 5)))
         # ---- CPU port on a bounded sample (N=1 only) -----------------------------------
@@ -334,13 +335,39 @@ def gpu_arm(args, wl):
                        "parallelism": (f"videos sharded x{world}; per step one NCCL all_gather of 12 B/track-frame "
                                        f"records on a side stream (overlaps the next step)") if world > 1 else "single GPU"},
             "roofline": m["roofline"], "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 4 * args.steps, "clocks": m["clocks"], "wall_s": m["wall_s"], "batched": batched,
+            "gpu_launches": 4 * args.steps, "clocks": m["clocks"], "wall_s": m["wall_s"], "batched": batched, "pack": pack,
         }
         print(json.dumps(line), flush=True)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
     return line
+
+
+def _pack_stream(dev, n_masks=1024, H=480, W=640, iters=5):
+    """The one pure HBM stream of the path: fp32 (n,H,W) -> packed bits (a3d_pack_masks), timed
+    alone with CUDA events; input (1.26 GB) exceeds L2.  Reported against the measured HBM peak."""
+    from articulation3d_b200 import _lib
+    lib = _lib.load()
+    src = (torch.rand(n_masks, H, W, device=dev) > 0.7).float()
+    pitch = _lib.pitch_words(W)
+    bits = torch.empty(n_masks, H, pitch, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * iters)]
+    for k in range(3 + iters):
+        if k >= 3:
+            ev[2 * (k - 3)].record()
+        _lib.check(lib.a3d_pack_masks(src.data_ptr(), _lib.A3D_F32, n_masks, H, W, 0.5, bits.data_ptr(), None, stream),
+                   "a3d_pack_masks")
+        if k >= 3:
+            ev[2 * (k - 3) + 1].record()
+    torch.cuda.synchronize()
+    ms = min(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(iters))
+    nbytes = src.numel() * 4 + bits.numel() * 4
+    peak, src_name = _peaks()
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "a3d_pack_masks (k_pack_vec<float>)", "bytes": nbytes, "ms": ms, "achieved": gbs, "unit": "GB/s",
+            "peak": peak, "frac": gbs / peak, "peak_source": src_name, "bound": "hbm"}
 
 
 def _run_split(engine, inp, ws, evs):
