@@ -392,26 +392,38 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
     const float ax = job.pivot[0], ay = job.pivot[1], az = job.pivot[2];
     const float wmax = (float)(cam.W - 1), hmax = (float)(cam.H - 1);
     const int nitems = (npts + kProjPX - 1) / kProjPX;
-    for (int item = threadIdx.x; item < nitems; item += kProjThreads) {
+    auto load_item = [&](int item, float (&X)[kProjPX], float (&Y)[kProjPX], float (&Z)[kProjPX]) {
+        const float4 a = __ldg(X4 + 2 * item), b = __ldg(X4 + 2 * item + 1);
+        X[0] = a.x; X[1] = a.y; X[2] = a.z; X[3] = a.w; X[4] = b.x; X[5] = b.y; X[6] = b.z; X[7] = b.w;
+        const float4 c = __ldg(Y4 + 2 * item), d = __ldg(Y4 + 2 * item + 1);
+        Y[0] = c.x; Y[1] = c.y; Y[2] = c.z; Y[3] = c.w; Y[4] = d.x; Y[5] = d.y; Y[6] = d.z; Y[7] = d.w;
+        const float4 e = __ldg(Z4 + 2 * item), g = __ldg(Z4 + 2 * item + 1);
+        Z[0] = e.x; Z[1] = e.y; Z[2] = e.z; Z[3] = e.w; Z[4] = g.x; Z[5] = g.y; Z[6] = g.z; Z[7] = g.w;
+    };
+    // full rounds: every thread owns one 8-point item and applies all candidates of the tile to it
+    const int nfull = (nitems / kProjThreads) * kProjThreads;
+    for (int item = threadIdx.x; item < nfull; item += kProjThreads) {
         float X[kProjPX], Y[kProjPX], Z[kProjPX];
-        {
-            const float4 a = __ldg(X4 + 2 * item), b = __ldg(X4 + 2 * item + 1);
-            X[0] = a.x; X[1] = a.y; X[2] = a.z; X[3] = a.w; X[4] = b.x; X[5] = b.y; X[6] = b.z; X[7] = b.w;
-            const float4 c = __ldg(Y4 + 2 * item), d = __ldg(Y4 + 2 * item + 1);
-            Y[0] = c.x; Y[1] = c.y; Y[2] = c.z; Y[3] = c.w; Y[4] = d.x; Y[5] = d.y; Y[6] = d.z; Y[7] = d.w;
-            const float4 e = __ldg(Z4 + 2 * item), g = __ldg(Z4 + 2 * item + 1);
-            Z[0] = e.x; Z[1] = e.y; Z[2] = e.z; Z[3] = e.w; Z[4] = g.x; Z[5] = g.y; Z[6] = g.z; Z[7] = g.w;
-        }
+        load_item(item, X, Y, Z);
+        for (int c = 0; c < nc; ++c)
+            splat_points<kMode, true>(X, Y, Z, kProjPX, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
+                                      wmax, hmax, cam.pitch, masks + (size_t)c * words);
+    }
+    // last, partial round: its (item, candidate) pairs are dealt out one by one so that all
+    // threads finish together (with ~1.5 items per thread the plain loop left half the warps
+    // idle for a whole round: 20 % of stall samples sat at the following barrier)
+    const int tail = nitems - nfull;
+    for (int u = threadIdx.x; u < tail * nc; u += kProjThreads) {
+        const int c = u / tail, item = nfull + (u - c * tail);
+        float X[kProjPX], Y[kProjPX], Z[kProjPX];
+        load_item(item, X, Y, Z);
         const int nvalid = npts - item * kProjPX;
-        if (nvalid >= kProjPX) {
-            for (int c = 0; c < nc; ++c)
-                splat_points<kMode, true>(X, Y, Z, kProjPX, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
-                                          wmax, hmax, cam.pitch, masks + (size_t)c * words);
-        } else {
-            for (int c = 0; c < nc; ++c)
-                splat_points<kMode, false>(X, Y, Z, nvalid, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
-                                           wmax, hmax, cam.pitch, masks + (size_t)c * words);
-        }
+        if (nvalid >= kProjPX)
+            splat_points<kMode, true>(X, Y, Z, kProjPX, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
+                                      wmax, hmax, cam.pitch, masks + (size_t)c * words);
+        else
+            splat_points<kMode, false>(X, Y, Z, nvalid, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
+                                       wmax, hmax, cam.pitch, masks + (size_t)c * words);
     }
 }
 

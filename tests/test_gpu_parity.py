@@ -333,3 +333,71 @@ def test_optimize_videos_equals_per_video_calls():
             assert np.array_equal(x.scores, y.scores)
             assert torch.equal(x.pred_rot_axis, y.pred_rot_axis)
             assert torch.equal(x.pred_tran_axis, y.pred_tran_axis)
+
+
+def _table_properties(res, batch, pool):
+    """Size-independent invariants of one pass (used where the oracle is too slow)."""
+    popc = pool.popc.cpu().numpy()
+    tab = res.inter_tab.cpu().numpy()
+    cand, inter, union, iou = (res.best_cand.cpu().numpy(), res.best_inter.cpu().numpy(),
+                               res.best_union.cpu().numpy(), res.best_iou.cpu().numpy())
+    ppop = res.proj_popc.cpu().numpy()
+    for j in range(batch.n_jobs):
+        jb = batch.jobs[j]
+        T, A = int(jb["n_tgt"]), int(jb["n_cand"])
+        t = tab[int(jb["tab_begin"]): int(jb["tab_begin"]) + T * A].reshape(T, A).astype(np.int64)
+        pt = popc[batch.tgt_index[int(jb["tgt_begin"]): int(jb["tgt_begin"]) + T]].astype(np.int64)
+        pp = ppop[int(jb["cand_begin"]): int(jb["cand_begin"]) + A].astype(np.int64)
+        assert (t >= 0).all() and (t <= np.minimum(pt[:, None], pp[None, :])).all()
+        u = pt[:, None] + pp[None, :] - t
+        want_iou = (torch.from_numpy(t) / torch.from_numpy(u))
+        best = want_iou.argmax(1).numpy()
+        sl = slice(int(jb["tgt_begin"]), int(jb["tgt_begin"]) + T)
+        assert np.array_equal(cand[sl], best)
+        assert np.array_equal(inter[sl], t[np.arange(T), best]) and np.array_equal(union[sl], u[np.arange(T), best])
+        assert np.array_equal(iou[sl], want_iou.numpy()[np.arange(T), best], equal_nan=True)
+        # the splat can only lose pixels (collisions), never create them
+        assert (pp <= int(pool.source_points[int(jb["src_mask"])])).all()
+
+
+@pytest.mark.parametrize("wl_name", ["c3_mini", "c4_probe"])
+def test_full_size_properties_and_kernel_agreement(wl_name, monkeypatch):
+    """BASELINE-sized grids (180 candidates x 120 frames; 720 candidates at 1024x768): invariants of
+    the result tables, identical tables from both scoring kernels and any candidate tiling, and the
+    C oracle on a sampled job."""
+    from articulation3d_b200 import workloads
+    from oracle import c_oracle
+    wl = workloads.WORKLOADS.get(wl_name) or workloads.Workload("c4_probe", "2 videos x 2 tracks x 24 frames, 720 candidates, 1024x768",
+                                                                2, 2, 24, 720, 1024, 768)
+    if wl_name == "c3_mini":
+        wl = workloads.Workload("c3_probe", "2 videos x 8 tracks x 120 frames, 180 candidates", 2, 8, 120, 180)
+    inp = workloads.build_pass(wl, 77, DEV)
+    runs = {}
+    for kernel, tile in (("ldg", None), ("tma", 1), ("ldg", 2)):
+        monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
+        res = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, want_table=True, tile_cand=tile)
+        torch.cuda.synchronize()
+        runs[(kernel, tile)] = (res.inter_tab.cpu().numpy().copy(), res.best_cand.cpu().numpy().copy(),
+                                res.proj_popc.cpu().numpy().copy())
+        if kernel == "ldg" and tile is None:
+            _table_properties(res, inp.batch, inp.pool)
+            # C oracle on the last job
+            j = inp.batch.n_jobs - 1
+            jb = inp.batch.jobs[j]
+            cfg = inp.cfg
+            A, T = int(jb["n_cand"]), int(jb["n_tgt"])
+            bits = inp.pool.bits.cpu().numpy().view(np.uint32)
+            xf = inp.batch.xform[int(jb["cand_begin"]): int(jb["cand_begin"]) + A]
+            proj = c_oracle.project(cfg.K_inv(), cfg.focal_length, cfg.cx, cfg.cy, cfg.height, cfg.width,
+                                    bits[int(jb["src_mask"])], jb["normal"], float(jb["offset"]), jb["pivot"],
+                                    int(jb["mode"]), xf)
+            got = res.proj_bits[int(jb["cand_begin"]): int(jb["cand_begin"]) + A].cpu().numpy().view(np.uint32)
+            assert np.array_equal(got, proj)
+            tg = inp.batch.tgt_index[int(jb["tgt_begin"]): int(jb["tgt_begin"]) + T]
+            inter, uni, best, iou = c_oracle.score(cfg.height, cfg.width, bits[tg], proj)
+            tab = res.inter_tab[int(jb["tab_begin"]): int(jb["tab_begin"]) + T * A].cpu().numpy().reshape(T, A)
+            assert np.array_equal(tab, inter)
+            assert np.array_equal(res.best_cand[int(jb["tgt_begin"]): int(jb["tgt_begin"]) + T].cpu().numpy(), best)
+    ref = runs[("ldg", None)]
+    for k, v in runs.items():
+        assert np.array_equal(v[0], ref[0]) and np.array_equal(v[1], ref[1]) and np.array_equal(v[2], ref[2]), k
