@@ -186,12 +186,13 @@ class PassResult:
     proj_popc: torch.Tensor       # (n_cand_total,) int32
     proj_bbox: torch.Tensor       # (n_cand_total, 4) int32
     inter_tab: torch.Tensor | None
+    block: torch.Tensor | None = None     # (4, n_tgt_total) int32: the four best_* rows, contiguous
 
 
 class DeviceBatch:
     """A JobBatch uploaded to the device (inputs resident in HBM)."""
 
-    def __init__(self, batch: JobBatch, device):
+    def __init__(self, batch: JobBatch, device, staging: "Staging | None" = None):
         self.host = batch
         self.n_jobs = batch.n_jobs
         self.n_cand_total = int(batch.xform.shape[0])
@@ -200,9 +201,44 @@ class DeviceBatch:
         self.max_tgt = int(batch.jobs["n_tgt"].max()) if self.n_jobs else 0
         self.tab_total = int((batch.jobs["n_cand"].astype(np.int64) * batch.jobs["n_tgt"]).sum())
         self.pcd_total = int(batch.jobs["pcd_cap"].astype(np.int64).sum())
-        self.jobs = torch.from_numpy(batch.jobs.view(np.uint8).reshape(-1)).to(device, non_blocking=True)
-        self.xform = torch.from_numpy(batch.xform).to(device, non_blocking=True)
-        self.tgt_index = torch.from_numpy(batch.tgt_index).to(device, non_blocking=True)
+        # one H2D for the three arrays: pinned staging block [jobs | xform | tgt_index], 16-byte aligned parts
+        nj, nx, nt = batch.jobs.nbytes, batch.xform.nbytes, batch.tgt_index.nbytes
+        oj, ox = 0, (nj + 15) & ~15
+        ot = (ox + nx + 15) & ~15
+        total = max(ot + nt, 16)
+        host = staging.host(total) if staging is not None else torch.empty(total, dtype=torch.uint8).pin_memory()
+        hv = host.numpy()
+        hv[oj:oj + nj] = batch.jobs.view(np.uint8).reshape(-1)
+        hv[ox:ox + nx] = batch.xform.view(np.uint8).reshape(-1)
+        hv[ot:ot + nt] = batch.tgt_index.view(np.uint8).reshape(-1)
+        dev = staging.device_block(total) if staging is not None else torch.empty(total, dtype=torch.uint8, device=device)
+        dev[:total].copy_(host[:total], non_blocking=True)
+        self.jobs = dev[oj:oj + nj]
+        self.xform = dev[ox:ox + nx].view(torch.float32).view(-1, 12)
+        self.tgt_index = dev[ot:ot + nt].view(torch.int32)
+
+
+class Staging:
+    """Reusable pinned-host / device byte blocks for the per-pass descriptors and results."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._host = self._dev = self._res_host = None
+
+    def host(self, n):
+        if self._host is None or self._host.numel() < n:
+            self._host = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
+        return self._host
+
+    def device_block(self, n):
+        if self._dev is None or self._dev.numel() < n:
+            self._dev = torch.empty(max(n, 1 << 16), dtype=torch.uint8, device=self.device)
+        return self._dev
+
+    def results_host(self, n_int32):
+        if self._res_host is None or self._res_host.numel() < n_int32:
+            self._res_host = torch.empty(max(n_int32, 1 << 12), dtype=torch.int32).pin_memory()
+        return self._res_host[:n_int32]
 
 
 class Workspace:
@@ -221,12 +257,28 @@ class Workspace:
         return buf[:n].view(*shape)
 
 
+_cam_cache: dict = {}
+_tile_cache: dict = {}
+
+
+def _camera_cached(cfg: OptConfig) -> _lib.Camera:
+    key = (cfg.focal_length, cfg.width, cfg.height)
+    cam = _cam_cache.get(key)
+    if cam is None:
+        cam = _cam_cache[key] = camera_struct(cfg)
+    return cam
+
+
 def choose_tile(cfg: OptConfig, n_cand_total: int, n_jobs: int = 1, sm_count: int = 148) -> int:
     """Candidates per projection CTA.  Large batches take as many as shared memory holds (the
     point cloud is read once per CTA); small batches pick the tile that minimises
     waves x (per-CTA overhead + tile) so no SM runs two CTAs while others idle."""
-    lib = _lib.load()
-    max_tile = _lib.check(lib.a3d_project_max_tile(cfg.height, cfg.width), "a3d_project_max_tile")
+    key = (cfg.height, cfg.width)
+    max_tile = _tile_cache.get(key)
+    if max_tile is None:
+        lib = _lib.load()
+        max_tile = _tile_cache[key] = _lib.check(lib.a3d_project_max_tile(cfg.height, cfg.width),
+                                                 "a3d_project_max_tile")
     per_job = -(-n_cand_total // max(n_jobs, 1))
     best, best_cost = max_tile, None
     for tile in range(max_tile, 0, -1):
@@ -255,14 +307,13 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
         pcd_ws = ws.get("pcd_ws", (max(3 * dbatch.pcd_total, 32),), torch.float32)
         pcd_count = ws.get("pcd_count", (dbatch.n_jobs,), torch.int32)
         key_ws = ws.get("key_ws", (nt,), torch.int64)
-        best_cand = ws.get("best_cand", (nt,), torch.int32)
-        best_inter = ws.get("best_inter", (nt,), torch.int32)
-        best_union = ws.get("best_union", (nt,), torch.int32)
-        best_iou = ws.get("best_iou", (nt,), torch.float32)
+        results = ws.get("results", (4, nt), torch.int32)          # one block -> one D2H
+        best_cand, best_inter, best_union = results[0], results[1], results[2]
+        best_iou = results[3].view(torch.float32)
         inter_tab = ws.get("inter_tab", (dbatch.tab_total,), torch.int32) if want_table else None
         if dbatch.n_jobs == 0:
             return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab)
-        cam = camera_struct(cfg)
+        cam = _camera_cached(cfg)
         stream = _stream_ptr()
         tile = tile_cand if tile_cand is not None else choose_tile(cfg, nc, dbatch.n_jobs)
         _lib.check(lib.a3d_project(C.byref(cam), dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_cand, tile,
@@ -277,7 +328,8 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
                                  inter_tab.data_ptr() if inter_tab is not None else None,
                                  best_cand.data_ptr(), best_inter.data_ptr(), best_union.data_ptr(),
                                  best_iou.data_ptr(), stream), "a3d_score")
-    return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab)
+    return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab,
+                      results)
 
 
 def emit_masks(bits: torch.Tensor, index: torch.Tensor | None, H: int, W: int,

@@ -355,6 +355,7 @@ class _Session:
         self.cfg = cfg
         self.device = torch.device(device)
         self.ws = engine.Workspace(self.device)
+        self.staging = engine.Staging(self.device)
         self.pool_of = []                   # per video: {(frame, box_id): pool index}
         chunks, rles, n = [], [], 0
         for preds, plane_lists in videos:
@@ -406,10 +407,12 @@ class _Session:
                                    [s.normal for s in specs], [s.offset for s in specs],
                                    [s.pivot for s in specs], [s.xform for s in specs],
                                    [s.targets for s in specs], self.pool.source_points)
-        dbatch = engine.DeviceBatch(batch, self.device)
+        dbatch = engine.DeviceBatch(batch, self.device, self.staging)
         res = engine.run_pass(self.cfg, self.pool, dbatch, self.ws)
-        packed = torch.stack([res.best_cand, res.best_inter, res.best_union,
-                              res.best_iou.view(torch.int32)]).cpu().numpy()     # one D2H, syncs
+        host = self.staging.results_host(res.block.numel())
+        host.view(4, -1).copy_(res.block, non_blocking=True)                 # one D2H into pinned memory
+        torch.cuda.current_stream().synchronize()
+        packed = host.numpy().reshape(4, -1)
         if stats is not None:
             stats.h2d_bytes += batch.jobs.nbytes + batch.xform.nbytes + batch.tgt_index.nbytes
             stats.d2h_bytes += packed.nbytes

@@ -1,0 +1,34 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel once, both
+scoring kernels, odd resolution, RLE ingest, override_depth.
+    compute-sanitizer --tool racecheck python tools/sanitize.py"""
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from articulation3d_b200 import OptConfig, adapter, engine, opt_utils, rle, synth  # noqa: E402
+
+cfg = OptConfig.scaled(200, 150)
+preds, _ = synth.make_video(5, 2, 12, cfg, kinds=[0, 1])
+for kernel in ("ldg", "tma"):
+    os.environ["A3D_SCORE_KERNEL"] = kernel
+    p = synth.clone_preds(preds)
+    random.seed(1)
+    planes = opt_utils.track_planes(p, cfg)
+    out = opt_utils.optimize_planes(p, planes, '3dc', cfg=cfg, device="cuda:0")
+    for cat in planes:
+        for pl in planes[cat]:
+            if pl.get('has_rot'):
+                _ = pl['reg_masks'][next(iter(pl['reg_masks']))]
+    print(kernel, [pl.get('has_rot') for cat in planes for pl in planes[cat]])
+H, W = 150, 200
+rles = [rle.encode(m.numpy() > 0.5) for m in preds[3].pred_masks]
+pool = engine.rle_to_pool(rles, H, W, "cuda:0")
+inst = [{"instances": [{"segmentation": r} for r in rles], "pred_plane": preds[3].pred_planes.clone()}]
+adapter.override_depth_batch(inst, depths=torch.rand(1, H, W, device="cuda:0") + 1,
+                             rays=torch.FloatTensor(adapter.get_K_inv_dot_xy_1(H, W)).cuda())
+torch.cuda.synchronize()
+print("sanitize run complete", pool.popc.tolist())
