@@ -102,23 +102,32 @@ __global__ void __launch_bounds__(256) k_pack_vec(const T* __restrict__ src, int
     const int segs = (W + 127) >> 7;                         // 128-pixel segments per row
     const int64_t total = n_rows * segs;
     const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t it = warp0 * kUnroll; it < total; it += nwarps * kUnroll) {
+    const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5) * kUnroll;
+    // (row, seg) of the warp's current item are advanced incrementally: no 64-bit division in the loop
+    int64_t it = warp0 * kUnroll;
+    int64_t row = it / segs;
+    int seg = (int)(it - row * segs);
+    const int64_t drow = stride / segs;
+    const int dseg = (int)(stride - drow * segs);
+    for (; it < total; it += stride) {
         float v[kUnroll][4];
+        int64_t r[kUnroll];
+        int sg[kUnroll];
+        {
+            int64_t rr = row;
+            int ss = seg;
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const int64_t s = it + u;
-            const int64_t row = s / segs;
-            const int px = (int)(s - row * segs) * 128 + lane * 4;
-            if (s < total && px < W) load4(src + row * (int64_t)W + px, v[u]);
-            else { v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f; }
+            for (int u = 0; u < kUnroll; ++u) {
+                r[u] = rr; sg[u] = ss;
+                const int px = ss * 128 + lane * 4;
+                if (it + u < total && px < W) load4(src + rr * (int64_t)W + px, v[u]);
+                else { v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f; }
+                if (++ss == segs) { ss = 0; ++rr; }
+            }
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            const int64_t s = it + u;
-            if (s >= total) break;
-            const int64_t row = s / segs;
-            const int seg = (int)(s - row * segs);
+            if (it + u >= total) break;
             uint32_t g = 0, z = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -132,12 +141,14 @@ __global__ void __launch_bounds__(256) k_pack_vec(const T* __restrict__ src, int
                 g |= __shfl_xor_sync(0xffffffffu, g, d);
                 z |= __shfl_xor_sync(0xffffffffu, z, d);
             }
-            const int word = seg * 4 + (lane >> 3);
+            const int word = sg[u] * 4 + (lane >> 3);
             if ((lane & 7) == 0 && word < pitch) {
-                gt[row * pitch + word] = g;
-                if (nz) nz[row * pitch + word] = z;
+                gt[r[u] * pitch + word] = g;
+                if (nz) nz[r[u] * pitch + word] = z;
             }
         }
+        row += drow; seg += dseg;
+        if (seg >= segs) { seg -= segs; ++row; }
     }
 }
 

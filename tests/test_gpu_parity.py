@@ -401,3 +401,36 @@ def test_full_size_properties_and_kernel_agreement(wl_name, monkeypatch):
     ref = runs[("ldg", None)]
     for k, v in runs.items():
         assert np.array_equal(v[0], ref[0]) and np.array_equal(v[1], ref[1]) and np.array_equal(v[2], ref[2]), k
+
+
+def test_c2_shape_with_90_angle_grid_matches_oracle():
+    """BASELINE config 2 shape (60 frames, 90-candidate cluster grid / 60-candidate final grid) through
+    the drop-in API with a lifted config, against the CPU oracle with the same config."""
+    from articulation3d_b200 import workloads
+    wl = workloads.WORKLOADS["c2"]
+    preds, cfg = workloads.make_clip(wl, 2021, tracks=2, kinds=[synth.KIND_ROT, synth.KIND_TRANS])
+    assert len(cfg.rot_cluster_grid) == 90 and len(preds) == 60
+    ocfg = restated.OracleConfig(rot_cluster_grid=cfg.rot_cluster_grid, rot_final_grid=cfg.rot_final_grid,
+                                 trans_grid=cfg.trans_grid)
+    a, b = synth.clone_preds(preds), synth.clone_preds(preds)
+    random.seed(9)
+    planes = opt_utils.track_planes(a, cfg)
+    stats = opt_utils.Stats()
+    out = opt_utils.optimize_planes(a, planes, '3dc', cfg=cfg, device=DEV, stats=stats)
+    random.seed(9)
+    planes_o = restated.track_planes(b)
+    trace = []
+    out_o = restated.optimize_planes(b, planes_o, '3dc', cfg=ocfg, trace=trace)
+    units = sum(len(v['iou']) for t in trace for v in t['visits'])
+    assert stats.units_visited == units                                  # same accounting as the reference loops
+    finals = {(t['kind'], t['track']): t for t in trace if t['phase'] == 'final'}
+    for cat in ("trans", "rot"):
+        for i, (p, q) in enumerate(zip(planes[cat], planes_o[cat])):
+            assert p['has_rot'] == q['has_rot']
+            if p['has_rot']:
+                fin = finals[(cat, i)]
+                assert [v['angle_id'] for v in fin['visits']] == p['fit']['angle_id'].tolist()
+                assert [int(v['inter'][v['angle_id']]) for v in fin['visits']] == p['fit']['inter'].tolist()
+    for x, y in zip(out, out_o):
+        assert np.array_equal(x.scores, y.scores)
+        np.testing.assert_allclose(x.pred_rot_axis.numpy(), y.pred_rot_axis.numpy(), rtol=1e-4, atol=1e-7)
