@@ -32,6 +32,8 @@ CASES = {
     "clip_a": (2020, 4, 24, [0, 0, 1, 2], 0.0),
     "clip_b": (12, 3, 20, [3, 3, 1], 0.05),
     "clip_c": (5, 2, 16, [2, 0], 0.0),
+    "clip_d": (7, 5, 40, None, 0.05),
+    "clip_e": (21, 3, 30, [1, 1, 0], 0.0),
 }
 
 
