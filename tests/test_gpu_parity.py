@@ -434,3 +434,68 @@ def test_c2_shape_with_90_angle_grid_matches_oracle():
     for x, y in zip(out, out_o):
         assert np.array_equal(x.scores, y.scores)
         np.testing.assert_allclose(x.pred_rot_axis.numpy(), y.pred_rot_axis.numpy(), rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_randomised_shapes_against_c_oracle(seed):
+    """Random image sizes (W not a multiple of 32, tiny and wide), random blob masks, random planes,
+    pivots and rigid transforms in all three modes, ragged target lists: the CUDA pass must equal the
+    C restatement bit for bit (projected masks, inter/union tables, arg-max)."""
+    from oracle import c_oracle
+    rng = np.random.RandomState(1000 + seed)
+    H = int(rng.choice([7, 33, 64, 120, 200]))
+    W = int(rng.choice([5, 31, 32, 33, 100, 257, 640]))
+    cfg = OptConfig.scaled(W, H) if rng.rand() < 0.5 else OptConfig(height=H, width=W)
+    n = 6
+    masks = np.zeros((n, H, W), np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for i in range(n):
+        for _ in range(rng.randint(1, 4)):
+            cy, cx = rng.rand() * H, rng.rand() * W
+            ry, rx = 1 + rng.rand() * H / 2, 1 + rng.rand() * W / 2
+            masks[i] += (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1)
+    masks = (masks > 0).astype(np.float32)
+    masks[n - 1] = 0                                             # an empty mask (source P = 0 / empty target)
+    pool = engine.pack_masks(torch.from_numpy(masks).to(DEV))
+    bits_ref = c_oracle.pack(masks)
+    assert np.array_equal(pool.bits.cpu().numpy().view(np.uint32), bits_ref)
+
+    def rand_rot(k):
+        ax = rng.randn(k, 3)
+        ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+        ang = rng.uniform(-np.pi, np.pi, k)
+        return geometry._axis_angle_to_matrix(torch.from_numpy(ax * ang[:, None])).to(torch.float32).numpy()
+
+    specs = []
+    for j in range(5):
+        mode = int(rng.randint(3))
+        A = int(rng.randint(1, 23))
+        xf = np.zeros((A, 12), np.float32)
+        xf[:, :9] = rand_rot(A).reshape(A, 9)
+        xf[:, 9:] = rng.randn(A, 3).astype(np.float32) * 0.3
+        normal = rng.randn(3)
+        normal[2] += 2.0 * (1 if rng.rand() < 0.8 else -1)       # mostly facing the camera, sometimes behind
+        normal = (normal / np.linalg.norm(normal)).astype(np.float32)
+        offset = np.float32(rng.uniform(0.5, 3.0))
+        pivot = rng.randn(3).astype(np.float32)
+        src = int(rng.randint(n)) if j else n - 1                # job 0: empty source
+        tg = [int(t) for t in rng.choice(n, size=rng.randint(1, n + 1), replace=True)]
+        specs.append((src, mode, normal, float(offset), pivot, xf, tg))
+    batch = engine.build_batch(*zip(*specs), pool.source_points)
+    res = engine.run_pass(cfg, pool, engine.DeviceBatch(batch, DEV), want_table=True)
+    torch.cuda.synchronize()
+    got_bits = res.proj_bits.cpu().numpy().view(np.uint32)
+    tab = res.inter_tab.cpu().numpy()
+    for j, (src, mode, normal, offset, pivot, xf, tg) in enumerate(specs):
+        jb = batch.jobs[j]
+        A, T = len(xf), len(tg)
+        want = c_oracle.project(cfg.K_inv(), cfg.focal_length, cfg.cx, cfg.cy, H, W, bits_ref[src], normal, offset,
+                                pivot, mode, xf)
+        c0 = int(jb["cand_begin"])
+        assert np.array_equal(got_bits[c0:c0 + A], want), (seed, j, mode)
+        inter, uni, best, iou = c_oracle.score(H, W, bits_ref[tg], want)
+        t0, b0 = int(jb["tgt_begin"]), int(jb["tab_begin"])
+        assert np.array_equal(tab[b0:b0 + T * A].reshape(T, A), inter)
+        assert np.array_equal(res.best_cand[t0:t0 + T].cpu().numpy(), best)
+        assert np.array_equal(res.best_union[t0:t0 + T].cpu().numpy(), uni[np.arange(T), best])
+        assert np.array_equal(res.best_iou[t0:t0 + T].cpu().numpy(), iou, equal_nan=True)
