@@ -85,9 +85,12 @@ def _axis_angle_to_matrix(axis_angle: torch.Tensor) -> torch.Tensor:
     t = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
     half = t * 0.5
     small = t.abs() < 1e-6
-    k = torch.empty_like(t)
-    k[~small] = torch.sin(half[~small]) / t[~small]
-    k[small] = 0.5 - (t[small] * t[small]) / 48
+    if bool(small.any()):
+        k = torch.empty_like(t)
+        k[~small] = torch.sin(half[~small]) / t[~small]
+        k[small] = 0.5 - (t[small] * t[small]) / 48
+    else:                                   # same elementwise values, without the masked gathers/scatters
+        k = torch.sin(half) / t
     q = torch.cat([torch.cos(half), axis_angle * k], dim=-1)
     r, i, j, kk = torch.unbind(q, -1)
     two_s = 2.0 / (q * q).sum(-1)

@@ -198,6 +198,7 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
     (reference :386-622 / :689-908 / legacy :113-340).  Mutates ``planes``."""
     cgrid, fgrid, cmode, fmode = _phase_setup(translation, legacy, cfg)
     remove_inliers = not legacy
+    finals = []
     for plane in planes:
         ids = plane['ids']
         id_list = list(ids.keys())
@@ -213,21 +214,25 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
             res = yield JobSpec(pool_of[(select_idx, box_id)], cmode, geo.normal.numpy(), float(geo.offset),
                                 geo.pivot, xf, [pool_of[(i, ids[i])] for i in order])
             row = {f: k for k, f in enumerate(order)}
-            inliers, c_angles, c_ious = [], [], []
+            # plain python lists: fp32 IoUs are exact as doubles, so `> 0.5` decides as the fp32 compare does
+            ious, cands = res.best_iou.tolist(), res.best_cand.tolist()
+            thr, n_cand = float(np.float32(cfg.inlier_iou)), len(xf)
+            inliers, c_ids, c_ious = [], [], []
             it = 0
             while it < len(id_list):            # `for idx in id_list` with in-loop removal
                 idx = id_list[it]
                 it += 1
                 k = row[idx]
-                stats.units_visited += len(xf)
-                if res.best_iou[k] > np.float32(cfg.inlier_iou):
+                stats.units_visited += n_cand
+                if ious[k] > thr:
                     inliers.append(idx)
                     if remove_inliers:
                         id_list.remove(idx)
-                    c_angles.append(angles[int(res.best_cand[k])][0])
-                    c_ious.append(float(res.best_iou[k]))
+                    c_ids.append(cands[k])
+                    c_ious.append(ious[k])
             clusters.append({'center_id': select_idx, 'inliners': inliers,
-                             'angles': torch.FloatTensor(c_angles), 'ious': c_ious})
+                             'angles': angles[c_ids, 0].clone() if c_ids else torch.FloatTensor([]),
+                             'ious': c_ious})
 
         rsqs = []
         for cluster in clusters:
@@ -242,6 +247,8 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
             continue
         plane['has_rot'] = True
 
+        # final assignment: it draws no random numbers, so the final jobs of all tracks of this list
+        # are deferred and scored together in ONE device pass after the last cluster round
         final_cluster = clusters[rsqs.argmax()]
         select_idx = final_cluster['center_id']
         box_id = ids[select_idx]
@@ -249,8 +256,14 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
         geo = geometry.source_geometry(p_instance, box_id, cfg, translation, all_boxes=legacy)
         xf, angles, R = _candidates(geo, fgrid, fmode)
         frames = list(ids.keys())
-        res = yield JobSpec(pool_of[(select_idx, box_id)], fmode, geo.normal.numpy(), float(geo.offset),
-                            geo.pivot, xf, [pool_of[(i, ids[i])] for i in frames], keep_masks=True)
+        spec = JobSpec(pool_of[(select_idx, box_id)], fmode, geo.normal.numpy(), float(geo.offset),
+                       geo.pivot, xf, [pool_of[(i, ids[i])] for i in frames], keep_masks=True)
+        finals.append((plane, spec, geo, xf, angles, R, frames, select_idx, box_id, p_instance, rsqs, clusters))
+
+    if not finals:
+        return
+    results = yield [f[1] for f in finals]
+    for (plane, spec, geo, xf, angles, R, frames, select_idx, box_id, p_instance, rsqs, clusters), res in zip(finals, results):
         stats.units_visited += len(xf) * len(frames)
         H, W = cfg.height, cfg.width
         plane['reg_masks'] = RegMasks(frames, res.masks, H, W)
@@ -439,13 +452,19 @@ def _drive(gens, session: _Session, stats: Stats):
             pass
     while pending:
         keys = list(pending.keys())
-        results, units = session.run([pending[k] for k in keys], stats)
+        specs, spans = [], []
+        for k in keys:                       # a request is one JobSpec or a list of them
+            req = pending[k]
+            group = req if isinstance(req, list) else [req]
+            spans.append((len(specs), len(group), isinstance(req, list)))
+            specs.extend(group)
+        results, units = session.run(specs, stats)
         stats.passes += 1
-        stats.jobs += len(keys)
+        stats.jobs += len(specs)
         stats.units_computed += units
-        for k, r in zip(keys, results):
+        for k, (lo, n, is_list) in zip(keys, spans):
             try:
-                pending[k] = gens[k].send(r)
+                pending[k] = gens[k].send(results[lo:lo + n] if is_list else results[lo])
             except StopIteration:
                 del pending[k]
 

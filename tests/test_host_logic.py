@@ -152,14 +152,16 @@ def test_removal_quirk_known_answer():
     gen = opt_utils._tracks_gen(preds, [plane], cfg, False, random.Random(0), pool_of, stats)
     spec = next(gen)
     visits = []
+    def answer(sp):
+        n = len(sp.targets)
+        visits.append(n)
+        return opt_utils.JobResult(np.arange(n, dtype=np.int32) % len(sp.xform),
+                                   np.full(n, 0.9, np.float32), np.ones(n, np.int32), np.ones(n, np.int32),
+                                   masks=torch.zeros(n, 1, 4, dtype=torch.int32))
+
     try:
         while True:
-            n = len(spec.targets)
-            visits.append(n)
-            res = opt_utils.JobResult(np.arange(n, dtype=np.int32) % len(spec.xform),
-                                      np.full(n, 0.9, np.float32), np.ones(n, np.int32), np.ones(n, np.int32),
-                                      masks=torch.zeros(n, 1, 4, dtype=torch.int32))
-            spec = gen.send(res)
+            spec = gen.send([answer(x) for x in spec] if isinstance(spec, list) else answer(spec))
     except StopIteration:
         pass
     assert visits[:5] == [60, 30, 15, 7, 3]          # id_list sizes handed to the device
