@@ -523,10 +523,24 @@ __device__ __forceinline__ unsigned long long make_key(float iou, int cand, int 
     return ((unsigned long long)__float_as_uint(iou) << 32) | lo;
 }
 
+// one carry-save step of the popcount accumulation: a, b are two AND-ed words, o the pending
+// weight-1 bits.  Explicit LOP3s (xor3 = 0x96, majority = 0xE8) keep it at 4 logic ops per pair;
+// left to the compiler the 5-input majority is re-derived from the un-ANDed words in 6.
+__device__ __forceinline__ void csa_step(uint32_t a, uint32_t b, uint32_t& ones, int& acc2) {
+    uint32_t s, c;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(ones), "r"(a), "r"(b));
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(c) : "r"(ones), "r"(a), "r"(b));
+    ones = s;
+    acc2 += __popc(c);
+}
+
 constexpr int kScoreTT = 8;    // targets per CTA
 constexpr int kScoreCT = 16;   // candidates per CTA
 
-// 3 CTAs/SM (<= 80 registers, a few spilled words) measured 10 % faster than 2 CTAs/SM at 96 registers.
+// kNarrow: every mask of the target pool / of the projected masks starts less than 2^32 words from its base,
+// so a load address is base + 32-bit word offset (one IMAD.WIDE) instead of a 64-bit pointer per mask —
+// without it half of the loop's instructions were address arithmetic.  3 CTAs/SM (<= 80 registers).
+template <bool kNarrow>
 __global__ void __launch_bounds__(256, 3)
 k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int ct_tiles,
         const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
@@ -548,8 +562,9 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
     const int nt = min(4, job.n_tgt - t0), ncd = min(4, job.n_cand - c0);
     const size_t words = (size_t)H * pitch;
 
-    const uint32_t* tp[4];
+    const uint32_t* tp[4];          // wide addressing: one pointer per mask
     const uint32_t* pp[4];
+    unsigned toff[4], poff[4];      // narrow addressing: 32-bit word offsets from tgt_bits / proj_bits
     int tmask[4];
     // region = (union of candidate boxes) ∩ (union of target boxes)
     int pr0 = 0x7fffffff, pr1 = -1, pc0 = 0x7fffffff, pc1 = -1;
@@ -559,11 +574,13 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
         const int ti = min(i, nt - 1);
         tmask[i] = tgt_index[job.tgt_begin + t0 + ti];
         tp[i] = tgt_bits + (size_t)tmask[i] * words;
+        toff[i] = (unsigned)tmask[i] * (unsigned)words;
         const int32_t* b = tgt_bbox + 4 * (size_t)tmask[i];
         if (b[1] >= b[0]) { qr0 = min(qr0, b[0]); qr1 = max(qr1, b[1]); qc0 = min(qc0, b[2]); qc1 = max(qc1, b[3]); }
         const int ci = min(i, ncd - 1);
         const size_t g = (size_t)job.cand_begin + c0 + ci;
         pp[i] = proj_bits + g * words;
+        poff[i] = (unsigned)g * (unsigned)words;
         const int32_t* pb = proj_bbox + 4 * g;
         if (pb[1] >= pb[0]) { pr0 = min(pr0, pb[0]); pr1 = max(pr1, pb[1]); pc0 = min(pc0, pb[2]); pc1 = max(pc1, pb[3]); }
     }
@@ -584,14 +601,19 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
         int rA = lane / ncols, cA = lane - rA * ncols;
         int rB = (lane + 32) / ncols, cB = (lane + 32) - rB * ncols;
         for (int idx = lane; idx < total; idx += 64) {
-            const int oA = (ra + rA) * pitch + ca + cA;
+            const unsigned oA = (unsigned)((ra + rA) * pitch + ca + cA);
             const bool hasB = idx + 32 < total;
-            const int oB = hasB ? (ra + rB) * pitch + ca + cB : oA;
+            const unsigned oB = hasB ? (unsigned)((ra + rB) * pitch + ca + cB) : oA;
             uint32_t tA[4], pA[4], tB[4], pB[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                tA[i] = __ldg(tp[i] + oA); pA[i] = __ldg(pp[i] + oA);
-                tB[i] = __ldg(tp[i] + oB); pB[i] = __ldg(pp[i] + oB);
+                if (kNarrow) {
+                    tA[i] = __ldg(tgt_bits + (toff[i] + oA)); pA[i] = __ldg(proj_bits + (poff[i] + oA));
+                    tB[i] = __ldg(tgt_bits + (toff[i] + oB)); pB[i] = __ldg(proj_bits + (poff[i] + oB));
+                } else {
+                    tA[i] = __ldg(tp[i] + oA); pA[i] = __ldg(pp[i] + oA);
+                    tB[i] = __ldg(tp[i] + oB); pB[i] = __ldg(pp[i] + oB);
+                }
             }
             if (!hasB) {
 #pragma unroll
@@ -600,11 +622,7 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t a = tA[i] & pA[k], b = tB[i] & pB[k], o = ones[i][k];
-                    ones[i][k] = o ^ a ^ b;                                   // sum   (LOP3)
-                    acc2[i][k] += __popc((o & a) | (o & b) | (a & b));        // carry (LOP3 + POPC)
-                }
+                for (int k = 0; k < 4; ++k) csa_step(tA[i] & pA[k], tB[i] & pB[k], ones[i][k], acc2[i][k]);
             rA += dr; cA += dc;
             if (cA >= ncols) { cA -= ncols; ++rA; }
             rB += dr; cB += dc;
@@ -829,11 +847,7 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint32_t a = tA[i] & pA[k], b = tB[i] & pB[k], o = ones[i][k];
-                            ones[i][k] = o ^ a ^ b;
-                            acc2[i][k] += __popc((o & a) | (o & b) | (a & b));
-                        }
+                        for (int k = 0; k < 4; ++k) csa_step(tA[i] & pA[k], tB[i] & pB[k], ones[i][k], acc2[i][k]);
                     rA += dr; cA += dc;
                     if (cA >= ncw) { cA -= ncw; ++rA; }
                     rB += dr; cB += dc;
@@ -1280,9 +1294,17 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
         const int tt_tiles = (max_tgt + kScoreTT - 1) / kScoreTT, ct_tiles = (max_cand + kScoreCT - 1) / kScoreCT;
         const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
         if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
-        k_score<<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc, tgt_bbox,
-                                                  tgt_index, proj_bits, proj_popc, proj_bbox,
-                                                  (unsigned long long*)key_ws, inter_tab, packed);
+        const unsigned long long words = (unsigned long long)H * pitch;
+        const bool narrow = (unsigned long long)n_pool_masks * words < (1ull << 32) &&
+                            (unsigned long long)n_cand_total * words < (1ull << 32);
+        if (narrow)
+            k_score<true><<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc,
+                                                            tgt_bbox, tgt_index, proj_bits, proj_popc, proj_bbox,
+                                                            (unsigned long long*)key_ws, inter_tab, packed);
+        else
+            k_score<false><<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc,
+                                                             tgt_bbox, tgt_index, proj_bits, proj_popc, proj_bbox,
+                                                             (unsigned long long*)key_ws, inter_tab, packed);
     }
     A3D_CUDA_TRY(cudaGetLastError());
     const int fy = packed ? (max_tgt + 255) / 256 : ((max_tgt + 7) / 8 < 64 ? (max_tgt + 7) / 8 : 64);
