@@ -535,13 +535,13 @@ __device__ __forceinline__ void csa_step(uint32_t a, uint32_t b, uint32_t& ones,
 }
 
 constexpr int kScoreTT = 8;    // targets per CTA
-constexpr int kScoreCT = 16;   // candidates per CTA
 
 // kNarrow: every mask of the target pool / of the projected masks starts less than 2^32 words from its base,
 // so a load address is base + 32-bit word offset (one IMAD.WIDE) instead of a 64-bit pointer per mask —
-// without it half of the loop's instructions were address arithmetic.  3 CTAs/SM (<= 80 registers).
-template <bool kNarrow>
-__global__ void __launch_bounds__(256, 3)
+// without it half of the loop's instructions were address arithmetic.
+// kWC: candidates per warp (warp tile = 4 targets x kWC candidates; CTA = 8 targets x 4*kWC candidates).
+template <bool kNarrow, int kWC>
+__global__ void __launch_bounds__(256, kWC == 4 ? 3 : 4)
 k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int ct_tiles,
         const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
         const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
@@ -553,18 +553,18 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
     const int rem = blockIdx.x - jid * per_job;
     const a3d_job_t job = jobs[jid];
     const int tb = (rem / ct_tiles) * kScoreTT;
-    const int cb = (rem % ct_tiles) * kScoreCT;
+    const int cb = (rem % ct_tiles) * (4 * kWC);
     if (tb >= job.n_tgt || cb >= job.n_cand) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t0 = tb + (warp >> 2) * 4;
-    const int c0 = cb + (warp & 3) * 4;
+    const int c0 = cb + (warp & 3) * kWC;
     if (t0 >= job.n_tgt || c0 >= job.n_cand) return;
-    const int nt = min(4, job.n_tgt - t0), ncd = min(4, job.n_cand - c0);
+    const int nt = min(4, job.n_tgt - t0), ncd = min(kWC, job.n_cand - c0);
     const size_t words = (size_t)H * pitch;
 
     const uint32_t* tp[4];          // wide addressing: one pointer per mask
-    const uint32_t* pp[4];
-    unsigned toff[4], poff[4];      // narrow addressing: 32-bit word offsets from tgt_bits / proj_bits
+    const uint32_t* pp[kWC];
+    unsigned toff[4], poff[kWC];    // narrow addressing: 32-bit word offsets from tgt_bits / proj_bits
     int tmask[4];
     // region = (union of candidate boxes) ∩ (union of target boxes)
     int pr0 = 0x7fffffff, pr1 = -1, pc0 = 0x7fffffff, pc1 = -1;
@@ -577,21 +577,24 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
         toff[i] = (unsigned)tmask[i] * (unsigned)words;
         const int32_t* b = tgt_bbox + 4 * (size_t)tmask[i];
         if (b[1] >= b[0]) { qr0 = min(qr0, b[0]); qr1 = max(qr1, b[1]); qc0 = min(qc0, b[2]); qc1 = max(qc1, b[3]); }
-        const int ci = min(i, ncd - 1);
+    }
+#pragma unroll
+    for (int k = 0; k < kWC; ++k) {
+        const int ci = min(k, ncd - 1);
         const size_t g = (size_t)job.cand_begin + c0 + ci;
-        pp[i] = proj_bits + g * words;
-        poff[i] = (unsigned)g * (unsigned)words;
+        pp[k] = proj_bits + g * words;
+        poff[k] = (unsigned)g * (unsigned)words;
         const int32_t* pb = proj_bbox + 4 * g;
         if (pb[1] >= pb[0]) { pr0 = min(pr0, pb[0]); pr1 = max(pr1, pb[1]); pc0 = min(pc0, pb[2]); pc1 = max(pc1, pb[3]); }
     }
     const int ra = max(pr0, qr0), rb = min(pr1, qr1), ca = max(pc0, qc0), cbw = min(pc1, qc1);
 
-    int acc2[4][4];           // number of carries (weight 2)
-    uint32_t ones[4][4];      // pending weight-1 bits
+    int acc2[4][kWC];           // number of carries (weight 2)
+    uint32_t ones[4][kWC];      // pending weight-1 bits
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { acc2[i][k] = 0; ones[i][k] = 0u; }
+        for (int k = 0; k < kWC; ++k) { acc2[i][k] = 0; ones[i][k] = 0u; }
 
     if (rb >= ra && cbw >= ca) {
         const int ncols = cbw - ca + 1;
@@ -600,54 +603,40 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
         const int dr = 64 / ncols, dc = 64 - dr * ncols;
         int rA = lane / ncols, cA = lane - rA * ncols;
         int rB = (lane + 32) / ncols, cB = (lane + 32) - rB * ncols;
-        int idx = lane;
-        struct Buf { uint32_t tA[4], pA[4], tB[4], pB[4]; };
-        auto load = [&](Buf& b) {                        // the 16 words of the current step
+        for (int idx = lane; idx < total; idx += 64) {
             const unsigned oA = (unsigned)((ra + rA) * pitch + ca + cA);
             const bool hasB = idx + 32 < total;
             const unsigned oB = hasB ? (unsigned)((ra + rB) * pitch + ca + cB) : oA;
+            uint32_t tA[4], tB[4], pA[kWC], pB[kWC];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (kNarrow) {
-                    b.tA[i] = __ldg(tgt_bits + (toff[i] + oA)); b.pA[i] = __ldg(proj_bits + (poff[i] + oA));
-                    b.tB[i] = __ldg(tgt_bits + (toff[i] + oB)); b.pB[i] = __ldg(proj_bits + (poff[i] + oB));
-                } else {
-                    b.tA[i] = __ldg(tp[i] + oA); b.pA[i] = __ldg(pp[i] + oA);
-                    b.tB[i] = __ldg(tp[i] + oB); b.pB[i] = __ldg(pp[i] + oB);
-                }
+                tA[i] = kNarrow ? __ldg(tgt_bits + (toff[i] + oA)) : __ldg(tp[i] + oA);
+                tB[i] = kNarrow ? __ldg(tgt_bits + (toff[i] + oB)) : __ldg(tp[i] + oB);
+            }
+#pragma unroll
+            for (int k = 0; k < kWC; ++k) {
+                pA[k] = kNarrow ? __ldg(proj_bits + (poff[k] + oA)) : __ldg(pp[k] + oA);
+                pB[k] = kNarrow ? __ldg(proj_bits + (poff[k] + oB)) : __ldg(pp[k] + oB);
             }
             if (!hasB) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) b.tB[i] = 0u;
+                for (int i = 0; i < 4; ++i) tB[i] = 0u;
             }
-        };
-        auto advance = [&]() {                           // next step; false when past the region
-            idx += 64;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < kWC; ++k) csa_step(tA[i] & pA[k], tB[i] & pB[k], ones[i][k], acc2[i][k]);
             rA += dr; cA += dc;
             if (cA >= ncols) { cA -= ncols; ++rA; }
             rB += dr; cB += dc;
             if (cB >= ncols) { cB -= ncols; ++rB; }
-            return idx < total;
-        };
-        auto compute = [&](const Buf& b) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) csa_step(b.tA[i] & b.pA[k], b.tB[i] & b.pB[k], ones[i][k], acc2[i][k]);
-        };
-        // (a register double-buffered variant that overlaps the next step's loads needs 127 registers,
-        //  i.e. 2 CTAs/SM, and measured 12 % slower than this loop at 3 CTAs/SM)
-        Buf b;
-        for (bool more = idx < total; more; more = advance()) {
-            load(b);
-            compute(b);
         }
     }
-    int acc[4][4];
+    int acc[4][kWC];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < kWC; ++k)
             acc[i][k] = __reduce_add_sync(0xffffffffu, 2 * acc2[i][k] + __popc(ones[i][k]));
 
     if (lane == 0) {
@@ -657,7 +646,7 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
             const int pt = tgt_popc[tmask[i]];
             unsigned long long best = 0ull;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < kWC; ++k) {
                 if (k >= ncd) break;
                 const int inter = acc[i][k];
                 const int uni = pt + proj_popc[(size_t)job.cand_begin + c0 + k] - inter;
@@ -1305,20 +1294,28 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
                                                                   tgt_bbox, tgt_index, proj_popc, proj_bbox,
                                                                   (unsigned long long*)key_ws, inter_tab, packed);
     } else {
-        const int tt_tiles = (max_tgt + kScoreTT - 1) / kScoreTT, ct_tiles = (max_cand + kScoreCT - 1) / kScoreCT;
+        // candidates per warp: 4x4 register tiles (3 CTAs/SM) are fastest on full grids (1.23 vs 1.39 ms on the
+        // C3 shard); 4x2 tiles (4 CTAs/SM, twice the CTAs) win when the 4x4 grid cannot fill the SMs
+        // (26.9 vs 30.7 us on C2).  A3D_SCORE_WC overrides for A/B runs.
+        const char* env_wc = getenv("A3D_SCORE_WC");
+        const long long blocks44 = (long long)n_jobs * ((max_tgt + kScoreTT - 1) / kScoreTT) * ((max_cand + 15) / 16);
+        int wc = blocks44 < 6 * 148 ? 2 : 4;
+        if (env_wc && (env_wc[0] == '2' || env_wc[0] == '4')) wc = env_wc[0] - '0';
+        const int tt_tiles = (max_tgt + kScoreTT - 1) / kScoreTT, ct_tiles = (max_cand + 4 * wc - 1) / (4 * wc);
         const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
         if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
         const unsigned long long words = (unsigned long long)H * pitch;
         const bool narrow = (unsigned long long)n_pool_masks * words < (1ull << 32) &&
                             (unsigned long long)n_cand_total * words < (1ull << 32);
-        if (narrow)
-            k_score<true><<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc,
-                                                            tgt_bbox, tgt_index, proj_bits, proj_popc, proj_bbox,
-                                                            (unsigned long long*)key_ws, inter_tab, packed);
-        else
-            k_score<false><<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc,
-                                                             tgt_bbox, tgt_index, proj_bits, proj_popc, proj_bbox,
-                                                             (unsigned long long*)key_ws, inter_tab, packed);
+#define A3D_LAUNCH_SCORE(N, WC)                                                                                   \
+    k_score<N, WC><<<(unsigned)nblocks, 256, 0, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, tgt_bits, tgt_popc, tgt_bbox, \
+                                                     tgt_index, proj_bits, proj_popc, proj_bbox,                   \
+                                                     (unsigned long long*)key_ws, inter_tab, packed)
+        if (narrow && wc == 4) A3D_LAUNCH_SCORE(true, 4);
+        else if (narrow) A3D_LAUNCH_SCORE(true, 2);
+        else if (wc == 4) A3D_LAUNCH_SCORE(false, 4);
+        else A3D_LAUNCH_SCORE(false, 2);
+#undef A3D_LAUNCH_SCORE
     }
     A3D_CUDA_TRY(cudaGetLastError());
     const int fy = packed ? (max_tgt + 255) / 256 : ((max_tgt + 7) / 8 < 64 ? (max_tgt + 7) / 8 : 64);
