@@ -1,0 +1,92 @@
+"""Turns the ncu captures / launch list a GPU run left in gpurun_out/ into the small text files
+tracked under profiles/ (summaries, traffic.json, launch shares).
+    python tools/refresh_profiles.py [round_tag]        # default r1_final"""
+import collections
+import csv
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import ncu_summary  # noqa: E402
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1_final"
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+
+def dram_bytes(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    d = dict(zip(rows[0], zip(rows[1], rows[2])))
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def b(k):
+        u, v = d[k]
+        return float(v.replace(",", "")) * scale[u]
+    return b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
+
+
+traffic = {}
+for f in sorted(os.listdir(G)):
+    m = re.match(r"prof_(c2|c3_mini|c3_shard)_(k_[a-z_]+)\.ncu-rep$", f)
+    if not m:
+        continue
+    wl, k = m.groups()
+    ncu_summary.main(os.path.join(G, f), os.path.join(P, f"{tag}_{wl}_{k}.txt"))
+    if k in ("k_project", "k_score"):
+        traffic.setdefault(wl, {})[k] = dram_bytes(os.path.join(G, f))
+if traffic:
+    traffic["_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none "
+                          f"(profiles/{tag}_<workload>_<kernel>.txt)")
+    with open(os.path.join(P, "traffic.json"), "w") as f:
+        json.dump(traffic, f, indent=1)
+
+lp = os.path.join(G, "launches_bench_c2.csv")
+if os.path.exists(lp):
+    rows = [r for r in csv.reader(open(lp)) if len(r) > 10]
+    h = rows[0]
+    ik, iv, ig, iid = h.index("Kernel Name"), h.index("Metric Value"), h.index("Grid Size"), h.index("ID")
+    recs = [(int(r[iid]), re.sub(r"^.*?(k_[a-z_]+).*$", r"\1", r[ik]), r[ig], float(r[iv].replace(",", ""))) for r in rows[1:]]
+    out = ["# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_* on "
+           "`python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-batched`",
+           "# per-launch device time (cold-cache, serialised under the profiler: compare SHARES, not absolutes)", ""]
+    agg = collections.OrderedDict()
+    for _, k, _, v in recs:
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    out.append("## all launches of the run (build + warm-up + 2 timed passes + e2e optimize_planes runs)")
+    for k, (n, t) in agg.items():
+        out.append(f"{k:14s} n={n:4d} total={t / 1e3:9.1f} us mean={t / n / 1e3:8.2f} us")
+    passes, i = [], 0
+    while i < len(recs) - 3:
+        if (recs[i][1] == "k_unproject" and recs[i][2].startswith("(4, 32") and recs[i + 1][1] == "k_project"
+                and recs[i + 2][1] == "k_score" and recs[i + 3][1] == "k_finalize"):
+            passes.append([recs[i + j][3] for j in range(4)])
+            i += 4
+        else:
+            i += 1
+    if passes:
+        out += ["", "## the device-resident C2 passes: per-pass kernel times and shares"]
+        m = [statistics.mean(p[j] for p in passes) / 1e3 for j in range(4)]
+        for name, v in zip(("k_unproject", "k_project", "k_score", "k_finalize"), m):
+            out.append(f"{name:12s} {v:7.2f} us  {100 * v / sum(m):5.1f} % of the pass")
+        out.append(f"{'pass total':12s} {sum(m):7.2f} us over {len(passes)} passes")
+    open(os.path.join(P, "r1_launches_bench_c2.txt"), "w").write("\n".join(out) + "\n")
+for name in ("sanitizer_racecheck.txt", "sanitizer_memcheck.txt"):
+    src = os.path.join(G, name)
+    if os.path.exists(src):
+        with open(src) as f, open(os.path.join(P, "r1_" + name), "w") as o:
+            o.writelines(l for l in f if "Host Frame" not in l)
+for name, dst in (("bench_default.txt", "r1_bench_default.json"), ("bench_reference.txt", "r1_bench_reference.json"),
+                  ("bench_n2.txt", "r1_bench_n2.json")):
+    src = os.path.join(G, name)
+    if os.path.exists(src):
+        lines = [l for l in open(src).read().splitlines() if l.startswith("{")]
+        if lines:
+            open(os.path.join(P, dst), "w").write(json.dumps(json.loads(lines[-1]), indent=1) + "\n")
+print("profiles refreshed:", sorted(os.listdir(P)))
