@@ -892,6 +892,266 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------
+// score on the tensor cores.  inter[t][c] = sum over pixels of T_t[p] * P_c[p] is a dense
+// contraction with 1-bit operands: a (targets x pixels) . (pixels x candidates) product.  Blackwell
+// has no 1-bit MMA (mma.sync .b1 is emulated with IMMA on sm_100a), so the words of the overlap
+// region are expanded to 0/1 bytes in shared memory and fed to tcgen05.mma kind::i8
+// (u8 x u8 -> s32, exact), accumulating a 128 x N tile in tensor memory:
+//   * CTA = (job, 128 targets, N <= 240 candidates); region = (union of its target boxes) ∩ (union
+//     of its candidate boxes), walked row by row in steps of <= 4 words;
+//   * 8 producer warps: lane -> (mask, word of the step); one 4-byte load, 8 shift+mask ops turn the
+//     word into 32 bytes (byte 4j+i of the K=32 slice = bit j+8i — any permutation serves as long as
+//     both operands use it), two 16-byte stores into the no-swizzle K-major core-matrix layout
+//     [K chunk of 16 B][row][16 B] (LBO = rows*16, SBO = 128; tools/mma_probe.cu pins the fields);
+//   * one thread issues one MMA (K = 32 bytes = one word position) per word of the step and commits
+//     the stage back to the producers; 4 stages of mbarrier-synchronised double buffering;
+//   * epilogue: warps 0-3 read their 32 TMEM lanes (= targets) with tcgen05.ld, and every thread
+//     scans its target's candidates: union, fp32 divide, arg-max key, one atomicMax per target.
+// ---------------------------------------------------------------------------
+constexpr int kMmaThreads = 288;              // 8 producer warps + the issuing warp
+constexpr int kMmaProducers = 256;
+constexpr int kMmaM = 128;                    // targets per CTA (TMEM lanes)
+constexpr int kMmaNMax = 240;                 // candidates per CTA (TMEM columns), multiple of 16
+constexpr int kMmaStages = 4;
+constexpr int kMmaPos = 4;                    // word positions per stage
+constexpr int kMmaItems = (kMmaM + kMmaNMax) * kMmaPos / kMmaProducers + 1;   // words per producer thread per step
+constexpr int kMmaABlock = 2 * kMmaM * 16;    // bytes of one position of A
+constexpr int kMmaPadMax = 64;
+constexpr int kMmaTmemCols = 256;
+
+// position blocks of one stage are padded so that the 16-byte stores of a quarter-warp
+// (consecutive lanes = consecutive words of one mask, then the next mask) hit distinct banks
+__host__ __device__ constexpr int mma_pad(int cw) { return cw == 2 ? 64 : (cw == 3 ? 48 : (cw == 4 ? 32 : 0)); }
+__host__ __device__ constexpr size_t mma_stage_bytes(int nb) {
+    return (size_t)kMmaPos * (kMmaABlock + kMmaPadMax) + (size_t)kMmaPos * (2 * nb * 16 + kMmaPadMax);
+}
+
+// bounded wait: a broken pipeline traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    // K-major, no swizzle: start >> 4 | LBO >> 4 (K-chunk stride) | SBO >> 4 = 8 (8-row group stride 128 B) | version 1
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)8 << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void expand_store(uint32_t w, uint32_t dst, uint32_t kc_stride) {
+    uint32_t e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = (w >> j) & 0x01010101u;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kc_stride), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]) : "memory");
+}
+
+__global__ void __launch_bounds__(kMmaThreads, 1)
+k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int ct_tiles, int ctile,
+            const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
+            const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
+            const uint32_t* __restrict__ proj_bits, const int32_t* __restrict__ proj_popc,
+            const int32_t* __restrict__ proj_bbox, unsigned long long* __restrict__ key_ws,
+            int32_t* __restrict__ inter_tab, int packed) {
+    extern __shared__ __align__(1024) uint8_t stage_mem[];
+    __shared__ const uint32_t* s_ptr[kMmaM + kMmaNMax];       // first word of every mask of the tile
+    __shared__ int s_pc[kMmaNMax];                            // pixel counts of the candidates
+    __shared__ int s_box[8];                                  // target hull, candidate hull
+    __shared__ __align__(8) uint64_t s_bar[2 * kMmaStages + 1];
+    __shared__ uint32_t s_tmem;
+
+    const int per_job = tt_tiles * ct_tiles;
+    const int jid = blockIdx.x / per_job;
+    const int rem = blockIdx.x - jid * per_job;
+    const a3d_job_t job = jobs[jid];
+    const int tb = (rem / ct_tiles) * kMmaM;
+    const int cb = (rem % ct_tiles) * ctile;
+    if (tb >= job.n_tgt || cb >= job.n_cand) return;           // whole CTA leaves together
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nt = min(kMmaM, job.n_tgt - tb), nc = min(ctile, job.n_cand - cb);
+    const int nb = (nc + 15) & ~15;                            // MMA N
+    const size_t words = (size_t)H * pitch;
+
+    if (tid < 8) s_box[tid] = (tid & 1) ? -1 : 0x7fffffff;     // {r0, r1, c0, c1} x {targets, candidates}
+    if (tid == 0) {
+        for (int i = 0; i < kMmaStages; ++i) {
+            mbar_init(smem_u32(&s_bar[i]), kMmaProducers);                 // full: every producer thread arrives
+            mbar_init(smem_u32(&s_bar[kMmaStages + i]), 1);                // empty: one tcgen05.commit
+        }
+        mbar_init(smem_u32(&s_bar[2 * kMmaStages]), 1);                    // accumulator complete
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kMmaTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    __syncthreads();
+    for (int m = tid; m < nt + nc; m += kMmaThreads) {
+        const int32_t* b;
+        if (m < nt) {
+            const int ti = tgt_index[job.tgt_begin + tb + m];
+            s_ptr[m] = tgt_bits + (size_t)ti * words;
+            b = tgt_bbox + 4 * (size_t)ti;
+        } else {
+            const size_t g = (size_t)job.cand_begin + cb + (m - nt);
+            s_ptr[m] = proj_bits + g * words;
+            s_pc[m - nt] = proj_popc[g];
+            b = proj_bbox + 4 * g;
+        }
+        if (b[1] >= b[0]) {
+            int* box = s_box + (m < nt ? 0 : 4);
+            atomicMin(box + 0, b[0]); atomicMax(box + 1, b[1]); atomicMin(box + 2, b[2]); atomicMax(box + 3, b[3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    const int ra = max(s_box[0], s_box[4]), rb = min(s_box[1], s_box[5]);
+    const int ca = max(s_box[2], s_box[6]), ce = min(s_box[3], s_box[7]);
+    int nsteps = 0, nchunks = 1, cw_base = 0, cw_rem = 0;
+    if (rb >= ra && ce >= ca) {
+        const int ncols = ce - ca + 1;
+        nchunks = (ncols + kMmaPos - 1) / kMmaPos;
+        cw_base = ncols / nchunks;
+        cw_rem = ncols - cw_base * nchunks;                      // the first cw_rem chunks are one word wider
+        nsteps = (rb - ra + 1) * nchunks;
+    }
+    const uint32_t stage0 = smem_u32(stage_mem);
+    const uint32_t stage_bytes = (uint32_t)mma_stage_bytes(nb);
+    const uint32_t b_off = (uint32_t)kMmaPos * (kMmaABlock + kMmaPadMax);
+    const uint32_t b_block = (uint32_t)(2 * nb * 16);
+    const uint32_t bar0 = smem_u32(&s_bar[0]);
+
+    if (warp < 8) {
+        // ===== producers =====
+        const int nmask = nt + nc;
+        uint32_t w[kMmaItems];
+        auto load_step = [&](int k) {
+            const int r = k / nchunks, ch = k - r * nchunks;
+            const int c0 = ca + ch * cw_base + min(ch, cw_rem), cw = cw_base + (ch < cw_rem ? 1 : 0);
+            const int n_items = nmask * cw;
+            const unsigned o = (unsigned)((ra + r) * pitch + c0);
+#pragma unroll
+            for (int u = 0; u < kMmaItems; ++u) {
+                const int i = tid + u * kMmaProducers;
+                if (i < n_items) {
+                    const int m = cw == 1 ? i : (cw == 2 ? (i >> 1) : (cw == 3 ? (int)(((unsigned)i * 43691u) >> 17) : (i >> 2)));
+                    w[u] = __ldg(s_ptr[m] + o + (unsigned)(i - m * cw));
+                }
+            }
+        };
+        if (nsteps > 0) load_step(0);
+        for (int k = 0; k < nsteps; ++k) {
+            const int st = k % kMmaStages;
+            const int r = k / nchunks, ch = k - r * nchunks;
+            const int cw = cw_base + (ch < cw_rem ? 1 : 0);
+            const int n_items = nmask * cw;
+            const uint32_t pad = (uint32_t)mma_pad(cw);
+            const uint32_t sa = stage0 + (uint32_t)st * stage_bytes, sb = sa + b_off;
+            uint32_t cur[kMmaItems];
+#pragma unroll
+            for (int u = 0; u < kMmaItems; ++u) cur[u] = w[u];
+            if (k + 1 < nsteps) load_step(k + 1);               // in flight while this step is expanded
+            mbar_wait_bounded(bar0 + 8u * (uint32_t)(kMmaStages + st), (uint32_t)(((k / kMmaStages) & 1) ^ 1));
+#pragma unroll
+            for (int u = 0; u < kMmaItems; ++u) {
+                const int i = tid + u * kMmaProducers;
+                if (i < n_items) {
+                    const int m = cw == 1 ? i : (cw == 2 ? (i >> 1) : (cw == 3 ? (int)(((unsigned)i * 43691u) >> 17) : (i >> 2)));
+                    const uint32_t q = (uint32_t)(i - m * cw);
+                    if (m < nt) expand_store(cur[u], sa + q * (kMmaABlock + pad) + (uint32_t)m * 16u, kMmaM * 16);
+                    else expand_store(cur[u], sb + q * (b_block + pad) + (uint32_t)(m - nt) * 16u, (uint32_t)nb * 16u);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async-proxy (MMA) reads
+            mbar_arrive(bar0 + 8u * (uint32_t)st);
+        }
+    } else if (lane == 0) {
+        // ===== MMA issuer (one thread) =====
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(nb >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);   // u8 x u8 -> s32, K-major
+        for (int k = 0; k < nsteps; ++k) {
+            const int st = k % kMmaStages;
+            const int r = k / nchunks, ch = k - r * nchunks;
+            const int cw = cw_base + (ch < cw_rem ? 1 : 0);
+            const uint32_t pad = (uint32_t)mma_pad(cw);
+            const uint32_t sa = stage0 + (uint32_t)st * stage_bytes, sb = sa + b_off;
+            mbar_wait_bounded(bar0 + 8u * (uint32_t)st, (uint32_t)((k / kMmaStages) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int q = 0; q < cw; ++q) {
+                const uint64_t da = umma_desc(sa + (uint32_t)q * (kMmaABlock + pad), kMmaM * 16);
+                const uint64_t db = umma_desc(sb + (uint32_t)q * (b_block + pad), (uint32_t)nb * 16u);
+                const uint32_t acc = (k > 0 || q > 0) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
+            // arrives on the stage's empty barrier once these MMAs have read shared memory
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                         ::"r"(bar0 + 8u * (uint32_t)(kMmaStages + st)) : "memory");
+        }
+        if (nsteps > 0)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                         ::"r"(bar0 + 8u * (uint32_t)(2 * kMmaStages)) : "memory");
+    }
+
+    if (warp < 4) {
+        // ===== epilogue: TMEM lane = target, column = candidate =====
+        if (nsteps > 0) {
+            mbar_wait_bounded(bar0 + 8u * (uint32_t)(2 * kMmaStages), 0u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int m = warp * 32 + lane;
+        const bool valid = m < nt;
+        const int pt = valid ? tgt_popc[tgt_index[job.tgt_begin + tb + m]] : 0;
+        unsigned long long best = 0ull;
+        for (int c0 = 0; c0 < nb; c0 += 16) {
+            uint32_t v[16];
+            if (nsteps > 0) {
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0u;
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = c0 + j;
+                    if (c < nc) {
+                        const int inter = (int)v[j];
+                        const int uni = pt + s_pc[c] - inter;
+                        const float iou = __fdiv_rn((float)inter, (float)uni);
+                        const unsigned long long key = make_key(iou, cb + c, inter, packed);
+                        best = key > best ? key : best;
+                        if (inter_tab) inter_tab[job.tab_begin + (int64_t)(tb + m) * job.n_cand + cb + c] = inter;
+                    }
+                }
+            }
+        }
+        if (valid) atomicMax(key_ws + job.tgt_begin + tb + m, best);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kMmaTmemCols));
+}
+
 // decode the winning candidate of every target.  Packed keys carry the intersection count
 // (one thread per target); otherwise one warp per target recomputes it over the candidate's box.
 __global__ void __launch_bounds__(256)
@@ -1272,7 +1532,21 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
     const char* env_kernel = getenv("A3D_SCORE_KERNEL");
     const bool use_tma = env_kernel && !strcmp(env_kernel, "tma");
     const bool tma_ok = use_tma && (n_pool_masks * H < 0x7fffffffLL) && (n_cand_total * H < 0x7fffffffLL);
-    if (tma_ok) {
+    const bool use_mma = env_kernel && !strcmp(env_kernel, "mma");
+    if (use_mma) {
+        // tensor-core scoring: CTA = (job, 128 targets, <= 240 candidates)
+        int ctile = (max_cand + 15) & ~15;
+        if (ctile > kMmaNMax) ctile = kMmaNMax;
+        const int tt_tiles = (max_tgt + kMmaM - 1) / kMmaM, ct_tiles = (max_cand + ctile - 1) / ctile;
+        const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
+        if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
+        const size_t smem = (size_t)kMmaStages * mma_stage_bytes(ctile);
+        A3D_CUDA_TRY(cudaFuncSetAttribute(k_score_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_score_mma<<<(unsigned)nblocks, kMmaThreads, smem, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, ctile, tgt_bits,
+                                                                 tgt_popc, tgt_bbox, tgt_index, proj_bits, proj_popc,
+                                                                 proj_bbox, (unsigned long long*)key_ws, inter_tab,
+                                                                 packed);
+    } else if (tma_ok) {
         // mask tiles staged by TMA: one tensor map per (array, box width)
         TmaMaps maps;
         const int widths[4] = {4, 8, 16, 32};

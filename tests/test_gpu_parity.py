@@ -110,7 +110,7 @@ def _check_pass(res, batch, proj_want, tgt_masks, W):
 
 @pytest.mark.parametrize("mode", [_lib.MODE_SEQ, _lib.MODE_COMPOSED, _lib.MODE_TRANSLATE])
 @pytest.mark.parametrize("tile", [1, 4, None])
-@pytest.mark.parametrize("kernel", ["tma", "ldg"])
+@pytest.mark.parametrize("kernel", ["tma", "ldg", "mma"])
 def test_project_and_score_match_oracle(mode, tile, kernel, monkeypatch):
     monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
     cfg, ocfg = OptConfig(), restated.OracleConfig()
@@ -127,7 +127,8 @@ def test_project_and_score_match_oracle(mode, tile, kernel, monkeypatch):
         _check_pass(res, batch, want, masks.numpy() > 0.5, cfg.width)
 
 
-@pytest.mark.parametrize("kernel,key", [("tma", "packed"), ("ldg", "packed"), ("ldg", "wide"), ("tma", "wide")])
+@pytest.mark.parametrize("kernel,key", [("tma", "packed"), ("ldg", "packed"), ("ldg", "wide"), ("tma", "wide"),
+                                        ("mma", "packed"), ("mma", "wide")])
 def test_odd_resolution_and_many_candidates(kernel, key, monkeypatch):
     """W not a multiple of 32, scaled intrinsics, a 97-candidate grid, ragged targets."""
     monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
@@ -145,7 +146,7 @@ def test_odd_resolution_and_many_candidates(kernel, key, monkeypatch):
     _check_pass(res, batch, want, (masks.numpy() > 0.5)[tg], W)
 
 
-@pytest.mark.parametrize("kernel", ["tma", "ldg"])
+@pytest.mark.parametrize("kernel", ["tma", "ldg", "mma"])
 def test_edge_cases_empty_source_degenerate_axis_behind_camera(kernel, monkeypatch):
     monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
     cfg, ocfg = OptConfig(), restated.OracleConfig()
@@ -373,7 +374,7 @@ def test_full_size_properties_and_kernel_agreement(wl_name, monkeypatch):
         wl = workloads.Workload("c3_probe", "2 videos x 8 tracks x 120 frames, 180 candidates", 2, 8, 120, 180)
     inp = workloads.build_pass(wl, 77, DEV)
     runs = {}
-    for kernel, tile in (("ldg", None), ("tma", 1), ("ldg", 2)):
+    for kernel, tile in (("ldg", None), ("tma", 1), ("ldg", 2), ("mma", None)):
         monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
         res = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, want_table=True, tile_cand=tile)
         torch.cuda.synchronize()

@@ -35,3 +35,21 @@ pr.enable()
 run()
 pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
+
+# phase split: session construction (H2D + pack) vs. the passes
+videos = [(preds, [opt_utils.track_planes(preds, cfg)["rot"]])]
+for _ in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    s = opt_utils._Session(videos, cfg, torch.device("cuda:0"))
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    print("session (H2D %.1f MB + pack) ms %.2f -> %.1f GB/s" % (s.h2d_bytes / 1e6, 1e3 * (t1 - t0), s.h2d_bytes / (t1 - t0) / 1e9))
+big = torch.cat([p.pred_masks for p in preds]).pin_memory()
+for _ in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d = big.to("cuda:0", non_blocking=True)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    print("one pinned H2D of %.1f MB: %.2f ms -> %.1f GB/s" % (big.numel() * 4 / 1e6, 1e3 * (t1 - t0), big.numel() * 4 / (t1 - t0) / 1e9))
