@@ -900,7 +900,7 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
 // (u8 x u8 -> s32, exact), accumulating a 128 x N tile in tensor memory:
 //   * CTA = (job, 128 targets, N <= 240 candidates); region = (union of its target boxes) ∩ (union
 //     of its candidate boxes), walked row by row in steps of <= 4 words;
-//   * 8 producer warps: lane -> (mask, word of the step); one 4-byte load, 8 shift+mask ops turn the
+//   * 16 producer warps: thread -> (mask, word of the step); one 4-byte load, 8 shift+mask ops turn the
 //     word into 32 bytes (byte 4j+i of the K=32 slice = bit j+8i — any permutation serves as long as
 //     both operands use it), two 16-byte stores into the no-swizzle K-major core-matrix layout
 //     [K chunk of 16 B][row][16 B] (LBO = rows*16, SBO = 128; tools/mma_probe.cu pins the fields);
@@ -909,16 +909,18 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
 //   * epilogue: warps 0-3 read their 32 TMEM lanes (= targets) with tcgen05.ld, and every thread
 //     scans its target's candidates: union, fp32 divide, arg-max key, one atomicMax per target.
 // ---------------------------------------------------------------------------
-constexpr int kMmaThreads = 288;              // 8 producer warps + the issuing warp
-constexpr int kMmaProducers = 256;
+constexpr int kMmaProducerWarps = 16;
+constexpr int kMmaProducers = 32 * kMmaProducerWarps;
+constexpr int kMmaThreads = kMmaProducers + 32;   // + the issuing warp
 constexpr int kMmaM = 128;                    // targets per CTA (TMEM lanes)
 constexpr int kMmaNMax = 240;                 // candidates per CTA (TMEM columns), multiple of 16
 constexpr int kMmaStages = 4;
 constexpr int kMmaPos = 4;                    // word positions per stage
-constexpr int kMmaItems = (kMmaM + kMmaNMax) * kMmaPos / kMmaProducers + 1;   // words per producer thread per step
+constexpr int kMmaItems = ((kMmaM + kMmaNMax) * kMmaPos + kMmaProducers - 1) / kMmaProducers;   // words per producer thread per step
 constexpr int kMmaABlock = 2 * kMmaM * 16;    // bytes of one position of A
 constexpr int kMmaPadMax = 64;
 constexpr int kMmaTmemCols = 256;
+constexpr int kMmaAhead = 8;                  // steps between a producer's loads and its stores
 
 // position blocks of one stage are padded so that the 16-byte stores of a quarter-warp
 // (consecutive lanes = consecutive words of one mask, then the next mask) hit distinct banks
@@ -990,7 +992,7 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
         mbar_init(smem_u32(&s_bar[2 * kMmaStages]), 1);                    // accumulator complete
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == kMmaProducerWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kMmaTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -1033,57 +1035,93 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
     const uint32_t b_block = (uint32_t)(2 * nb * 16);
     const uint32_t bar0 = smem_u32(&s_bar[0]);
 
-    if (warp < 8) {
+    if (warp < kMmaProducerWarps) {
         // ===== producers =====
+        // Every thread walks all steps.  A step is 1..4 words of one mask row for every mask of the tile;
+        // thread -> (mask, word) is fixed per step width (the two widths cw_base, cw_base + 1 are set up
+        // once), so a step costs one address add per word.  Loads run kMmaAhead steps ahead of the stores
+        // in a register ring (static indices through full unrolling), enough to cover a DRAM miss.
         const int nmask = nt + nc;
-        uint32_t w[kMmaItems];
-        auto load_step = [&](int k) {
-            const int r = k / nchunks, ch = k - r * nchunks;
-            const int c0 = ca + ch * cw_base + min(ch, cw_rem), cw = cw_base + (ch < cw_rem ? 1 : 0);
-            const int n_items = nmask * cw;
-            const unsigned o = (unsigned)((ra + r) * pitch + c0);
+        const uint32_t* src[2][kMmaItems];          // first word of this thread's mask + word of the step
+        uint32_t dst[2][kMmaItems];                 // byte offset of its 16-byte row slot inside a stage
+        uint32_t is_a = 0;                          // bit (2u + v): the item is a target (A) row
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int cw = cw_base + v;
+            const uint32_t pad = (uint32_t)mma_pad(cw);
 #pragma unroll
             for (int u = 0; u < kMmaItems; ++u) {
                 const int i = tid + u * kMmaProducers;
-                if (i < n_items) {
-                    const int m = cw == 1 ? i : (cw == 2 ? (i >> 1) : (cw == 3 ? (int)(((unsigned)i * 43691u) >> 17) : (i >> 2)));
-                    w[u] = __ldg(s_ptr[m] + o + (unsigned)(i - m * cw));
+                src[v][u] = nullptr;
+                dst[v][u] = 0;
+                if (nsteps > 0 && cw <= kMmaPos && i < nmask * cw) {
+                    const int m = i / cw, q = i - m * cw;
+                    src[v][u] = s_ptr[m] + q;
+                    if (m < nt) {
+                        dst[v][u] = (uint32_t)q * (kMmaABlock + pad) + (uint32_t)m * 16u;
+                        is_a |= 1u << (2 * u + v);
+                    } else {
+                        dst[v][u] = b_off + (uint32_t)q * (b_block + pad) + (uint32_t)(m - nt) * 16u;
+                    }
                 }
             }
+        }
+        const uint32_t kcs_b = (uint32_t)nb * 16u;
+        struct Cursor { int ch, c0; unsigned row; };     // chunk of the row, its first word, word offset of the row
+        auto advance = [&](Cursor& c) {
+            c.c0 += cw_base + (c.ch < cw_rem ? 1 : 0);
+            if (++c.ch == nchunks) { c.ch = 0; c.c0 = ca; c.row += (unsigned)pitch; }
         };
-        if (nsteps > 0) load_step(0);
-        for (int k = 0; k < nsteps; ++k) {
-            const int st = k % kMmaStages;
-            const int r = k / nchunks, ch = k - r * nchunks;
-            const int cw = cw_base + (ch < cw_rem ? 1 : 0);
-            const int n_items = nmask * cw;
-            const uint32_t pad = (uint32_t)mma_pad(cw);
-            const uint32_t sa = stage0 + (uint32_t)st * stage_bytes, sb = sa + b_off;
-            uint32_t cur[kMmaItems];
-#pragma unroll
-            for (int u = 0; u < kMmaItems; ++u) cur[u] = w[u];
-            if (k + 1 < nsteps) load_step(k + 1);               // in flight while this step is expanded
-            mbar_wait_bounded(bar0 + 8u * (uint32_t)(kMmaStages + st), (uint32_t)(((k / kMmaStages) & 1) ^ 1));
+        auto load_step = [&](Cursor& c, uint32_t (&w)[kMmaItems]) {
+            const bool wide = c.ch < cw_rem;
+            const unsigned o = c.row + (unsigned)c.c0;
 #pragma unroll
             for (int u = 0; u < kMmaItems; ++u) {
-                const int i = tid + u * kMmaProducers;
-                if (i < n_items) {
-                    const int m = cw == 1 ? i : (cw == 2 ? (i >> 1) : (cw == 3 ? (int)(((unsigned)i * 43691u) >> 17) : (i >> 2)));
-                    const uint32_t q = (uint32_t)(i - m * cw);
-                    if (m < nt) expand_store(cur[u], sa + q * (kMmaABlock + pad) + (uint32_t)m * 16u, kMmaM * 16);
-                    else expand_store(cur[u], sb + q * (b_block + pad) + (uint32_t)(m - nt) * 16u, (uint32_t)nb * 16u);
+                const uint32_t* p = wide ? src[1][u] : src[0][u];
+                if (p) w[u] = __ldg(p + o);
+            }
+            advance(c);
+        };
+        auto store_step = [&](Cursor& c, int st, uint32_t parity, const uint32_t (&w)[kMmaItems]) {
+            const bool wide = c.ch < cw_rem;
+            const uint32_t sa = stage0 + (uint32_t)st * stage_bytes;
+            mbar_wait_bounded(bar0 + 8u * (uint32_t)(kMmaStages + st), parity ^ 1u);
+#pragma unroll
+            for (int u = 0; u < kMmaItems; ++u) {
+                const uint32_t* p = wide ? src[1][u] : src[0][u];
+                if (p) {
+                    const bool a_row = (is_a >> (2 * u + (wide ? 1 : 0))) & 1u;
+                    expand_store(w[u], sa + (wide ? dst[1][u] : dst[0][u]), a_row ? (uint32_t)(kMmaM * 16) : kcs_b);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async-proxy (MMA) reads
             mbar_arrive(bar0 + 8u * (uint32_t)st);
+            advance(c);
+        };
+        static_assert(kMmaAhead % kMmaStages == 0, "stage and phase of a step must be static in the unrolled loop");
+        uint32_t ring[kMmaAhead][kMmaItems];
+        Cursor cl{0, ca, (unsigned)(ra * pitch)}, cs{0, ca, (unsigned)(ra * pitch)};
+#pragma unroll
+        for (int d = 0; d < kMmaAhead - 1; ++d)
+            if (d < nsteps) load_step(cl, ring[d]);
+        for (int k0 = 0; k0 < nsteps; k0 += kMmaAhead) {
+#pragma unroll
+            for (int d = 0; d < kMmaAhead; ++d) {
+                const int k = k0 + d;
+                if (k < nsteps) {
+                    if (k + kMmaAhead - 1 < nsteps) load_step(cl, ring[(d + kMmaAhead - 1) % kMmaAhead]);
+                    store_step(cs, d % kMmaStages, (uint32_t)((d / kMmaStages) & 1), ring[d]);
+                }
+            }
         }
     } else if (lane == 0) {
         // ===== MMA issuer (one thread) =====
         const uint32_t idesc = (2u << 4) | ((uint32_t)(nb >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);   // u8 x u8 -> s32, K-major
+        int ch = 0;
         for (int k = 0; k < nsteps; ++k) {
             const int st = k % kMmaStages;
-            const int r = k / nchunks, ch = k - r * nchunks;
             const int cw = cw_base + (ch < cw_rem ? 1 : 0);
+            if (++ch == nchunks) ch = 0;
             const uint32_t pad = (uint32_t)mma_pad(cw);
             const uint32_t sa = stage0 + (uint32_t)st * stage_bytes, sb = sa + b_off;
             mbar_wait_bounded(bar0 + 8u * (uint32_t)st, (uint32_t)((k / kMmaStages) & 1));
@@ -1149,7 +1187,7 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kMmaTmemCols));
+    if (warp == kMmaProducerWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kMmaTmemCols));
 }
 
 // decode the winning candidate of every target.  Packed keys carry the intersection count
