@@ -918,15 +918,14 @@ constexpr int kMmaStages = 4;
 constexpr int kMmaPos = 4;                    // word positions per stage
 constexpr int kMmaItems = ((kMmaM + kMmaNMax) * kMmaPos + kMmaProducers - 1) / kMmaProducers;   // words per producer thread per step
 constexpr int kMmaABlock = 2 * kMmaM * 16;    // bytes of one position of A
-constexpr int kMmaPadMax = 64;
 constexpr int kMmaTmemCols = 256;
 constexpr int kMmaAhead = 8;                  // steps between a producer's loads and its stores
 
-// position blocks of one stage are padded so that the 16-byte stores of a quarter-warp
-// (consecutive lanes = consecutive words of one mask, then the next mask) hit distinct banks
-__host__ __device__ constexpr int mma_pad(int cw) { return cw == 2 ? 64 : (cw == 3 ? 48 : (cw == 4 ? 32 : 0)); }
+// position blocks of one stage are padded by 32 bytes so that the 16-byte stores of a quarter-warp
+// (4 words of one mask, then of the next mask) hit distinct banks
+constexpr int kMmaPad = 32;
 __host__ __device__ constexpr size_t mma_stage_bytes(int nb) {
-    return (size_t)kMmaPos * (kMmaABlock + kMmaPadMax) + (size_t)kMmaPos * (2 * nb * 16 + kMmaPadMax);
+    return (size_t)kMmaPos * (kMmaABlock + kMmaPad) + (size_t)kMmaPos * (2 * nb * 16 + kMmaPad);
 }
 
 // bounded wait: a broken pipeline traps (launch error) instead of hanging the GPU
@@ -1019,117 +1018,99 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
+    // region = (hull of the target boxes) ∩ (hull of the candidate boxes), walked as one row-major
+    // sequence of word positions; a step = kMmaPos consecutive positions = kMmaPos MMAs
     const int ra = max(s_box[0], s_box[4]), rb = min(s_box[1], s_box[5]);
     const int ca = max(s_box[2], s_box[6]), ce = min(s_box[3], s_box[7]);
-    int nsteps = 0, nchunks = 1, cw_base = 0, cw_rem = 0;
+    int npos = 0, ncols = 1;
     if (rb >= ra && ce >= ca) {
-        const int ncols = ce - ca + 1;
-        nchunks = (ncols + kMmaPos - 1) / kMmaPos;
-        cw_base = ncols / nchunks;
-        cw_rem = ncols - cw_base * nchunks;                      // the first cw_rem chunks are one word wider
-        nsteps = (rb - ra + 1) * nchunks;
+        ncols = ce - ca + 1;
+        npos = (rb - ra + 1) * ncols;
     }
+    const int nsteps = (npos + kMmaPos - 1) / kMmaPos;
     const uint32_t stage0 = smem_u32(stage_mem);
     const uint32_t stage_bytes = (uint32_t)mma_stage_bytes(nb);
-    const uint32_t b_off = (uint32_t)kMmaPos * (kMmaABlock + kMmaPadMax);
+    const uint32_t b_off = (uint32_t)kMmaPos * (kMmaABlock + kMmaPad);
     const uint32_t b_block = (uint32_t)(2 * nb * 16);
     const uint32_t bar0 = smem_u32(&s_bar[0]);
 
     if (warp < kMmaProducerWarps) {
         // ===== producers =====
-        // Every thread walks all steps.  A step is 1..4 words of one mask row for every mask of the tile;
-        // thread -> (mask, word) is fixed per step width (the two widths cw_base, cw_base + 1 are set up
-        // once), so a step costs one address add per word.  Loads run kMmaAhead steps ahead of the stores
-        // in a register ring (static indices through full unrolling), enough to cover a DRAM miss.
+        // thread -> word (tid & 3) of the step, for the masks (tid >> 2) + 128 u: one position cursor per
+        // thread, a constant stage slot per (thread, u).  Loads run kMmaAhead steps ahead of the stores in
+        // a register ring (static indices through full unrolling).
         const int nmask = nt + nc;
-        const uint32_t* src[2][kMmaItems];          // first word of this thread's mask + word of the step
-        uint32_t dst[2][kMmaItems];                 // byte offset of its 16-byte row slot inside a stage
-        uint32_t is_a = 0;                          // bit (2u + v): the item is a target (A) row
+        const int q = tid & (kMmaPos - 1);
+        const uint32_t* src[kMmaItems];             // word (ra, ca) of this thread's masks
+        uint32_t dst[kMmaItems];                    // byte offset of the mask's 16-byte row slot inside a stage
+        uint32_t kcs[kMmaItems];                    // distance of the second K chunk
+        bool act[kMmaItems];
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int cw = cw_base + v;
-            const uint32_t pad = (uint32_t)mma_pad(cw);
-#pragma unroll
-            for (int u = 0; u < kMmaItems; ++u) {
-                const int i = tid + u * kMmaProducers;
-                src[v][u] = nullptr;
-                dst[v][u] = 0;
-                if (nsteps > 0 && cw <= kMmaPos && i < nmask * cw) {
-                    const int m = i / cw, q = i - m * cw;
-                    src[v][u] = s_ptr[m] + q;
-                    if (m < nt) {
-                        dst[v][u] = (uint32_t)q * (kMmaABlock + pad) + (uint32_t)m * 16u;
-                        is_a |= 1u << (2 * u + v);
-                    } else {
-                        dst[v][u] = b_off + (uint32_t)q * (b_block + pad) + (uint32_t)(m - nt) * 16u;
-                    }
-                }
-            }
+        for (int u = 0; u < kMmaItems; ++u) {
+            const int m = (tid >> 2) + u * (kMmaProducers / kMmaPos);
+            act[u] = m < nmask;
+            src[u] = act[u] ? s_ptr[m] + (size_t)ra * pitch + ca : nullptr;
+            const bool a_row = m < nt;
+            dst[u] = a_row ? (uint32_t)q * (kMmaABlock + kMmaPad) + (uint32_t)m * 16u
+                           : b_off + (uint32_t)q * (b_block + kMmaPad) + (uint32_t)(m - nt) * 16u;
+            kcs[u] = a_row ? (uint32_t)(kMmaM * 16) : (uint32_t)nb * 16u;
         }
-        const uint32_t kcs_b = (uint32_t)nb * 16u;
-        struct Cursor { int ch, c0; unsigned row; };     // chunk of the row, its first word, word offset of the row
-        auto advance = [&](Cursor& c) {
-            c.c0 += cw_base + (c.ch < cw_rem ? 1 : 0);
-            if (++c.ch == nchunks) { c.ch = 0; c.c0 = ca; c.row += (unsigned)pitch; }
-        };
-        auto load_step = [&](Cursor& c, uint32_t (&w)[kMmaItems]) {
-            const bool wide = c.ch < cw_rem;
-            const unsigned o = c.row + (unsigned)c.c0;
+        // position of this thread's word in the step the load cursor is at: p = 4 k + q = row * ncols + col
+        const int dr = kMmaPos / ncols, dc = kMmaPos - dr * ncols;
+        int p_ld = q, col = q % ncols;
+        unsigned rowoff = (unsigned)((q / ncols) * pitch);
+        auto load_step = [&](uint32_t (&w)[kMmaItems]) {
+            const unsigned o = rowoff + (unsigned)col;
+            const bool in = p_ld < npos;
 #pragma unroll
-            for (int u = 0; u < kMmaItems; ++u) {
-                const uint32_t* p = wide ? src[1][u] : src[0][u];
-                if (p) w[u] = __ldg(p + o);
-            }
-            advance(c);
+            for (int u = 0; u < kMmaItems; ++u)
+                if (act[u] && in) w[u] = __ldg(src[u] + o);
+            p_ld += kMmaPos;
+            col += dc;
+            rowoff += (unsigned)(dr * pitch);
+            if (col >= ncols) { col -= ncols; rowoff += (unsigned)pitch; }
         };
-        auto store_step = [&](Cursor& c, int st, uint32_t parity, const uint32_t (&w)[kMmaItems]) {
-            const bool wide = c.ch < cw_rem;
+        int p_st = q;
+        auto store_step = [&](int st, uint32_t parity, const uint32_t (&w)[kMmaItems]) {
             const uint32_t sa = stage0 + (uint32_t)st * stage_bytes;
             mbar_wait_bounded(bar0 + 8u * (uint32_t)(kMmaStages + st), parity ^ 1u);
+            if (p_st < npos) {
 #pragma unroll
-            for (int u = 0; u < kMmaItems; ++u) {
-                const uint32_t* p = wide ? src[1][u] : src[0][u];
-                if (p) {
-                    const bool a_row = (is_a >> (2 * u + (wide ? 1 : 0))) & 1u;
-                    expand_store(w[u], sa + (wide ? dst[1][u] : dst[0][u]), a_row ? (uint32_t)(kMmaM * 16) : kcs_b);
-                }
+                for (int u = 0; u < kMmaItems; ++u)
+                    if (act[u]) expand_store(w[u], sa + dst[u], kcs[u]);
             }
+            p_st += kMmaPos;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async-proxy (MMA) reads
             mbar_arrive(bar0 + 8u * (uint32_t)st);
-            advance(c);
         };
         static_assert(kMmaAhead % kMmaStages == 0, "stage and phase of a step must be static in the unrolled loop");
         uint32_t ring[kMmaAhead][kMmaItems];
-        Cursor cl{0, ca, (unsigned)(ra * pitch)}, cs{0, ca, (unsigned)(ra * pitch)};
 #pragma unroll
         for (int d = 0; d < kMmaAhead - 1; ++d)
-            if (d < nsteps) load_step(cl, ring[d]);
+            if (d < nsteps) load_step(ring[d]);
         for (int k0 = 0; k0 < nsteps; k0 += kMmaAhead) {
 #pragma unroll
             for (int d = 0; d < kMmaAhead; ++d) {
                 const int k = k0 + d;
                 if (k < nsteps) {
-                    if (k + kMmaAhead - 1 < nsteps) load_step(cl, ring[(d + kMmaAhead - 1) % kMmaAhead]);
-                    store_step(cs, d % kMmaStages, (uint32_t)((d / kMmaStages) & 1), ring[d]);
+                    if (k + kMmaAhead - 1 < nsteps) load_step(ring[(d + kMmaAhead - 1) % kMmaAhead]);
+                    store_step(d % kMmaStages, (uint32_t)((d / kMmaStages) & 1), ring[d]);
                 }
             }
         }
     } else if (lane == 0) {
         // ===== MMA issuer (one thread) =====
         const uint32_t idesc = (2u << 4) | ((uint32_t)(nb >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);   // u8 x u8 -> s32, K-major
-        int ch = 0;
         for (int k = 0; k < nsteps; ++k) {
             const int st = k % kMmaStages;
-            const int cw = cw_base + (ch < cw_rem ? 1 : 0);
-            if (++ch == nchunks) ch = 0;
-            const uint32_t pad = (uint32_t)mma_pad(cw);
+            const int cw = min(kMmaPos, npos - k * kMmaPos);
             const uint32_t sa = stage0 + (uint32_t)st * stage_bytes, sb = sa + b_off;
             mbar_wait_bounded(bar0 + 8u * (uint32_t)st, (uint32_t)((k / kMmaStages) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int q = 0; q < cw; ++q) {
-                const uint64_t da = umma_desc(sa + (uint32_t)q * (kMmaABlock + pad), kMmaM * 16);
-                const uint64_t db = umma_desc(sb + (uint32_t)q * (b_block + pad), (uint32_t)nb * 16u);
-                const uint32_t acc = (k > 0 || q > 0) ? 1u : 0u;
+            for (int j = 0; j < cw; ++j) {
+                const uint64_t da = umma_desc(sa + (uint32_t)j * (kMmaABlock + kMmaPad), kMmaM * 16);
+                const uint64_t db = umma_desc(sb + (uint32_t)j * (b_block + kMmaPad), (uint32_t)nb * 16u);
+                const uint32_t acc = (k > 0 || j > 0) ? 1u : 0u;
                 asm volatile(
                     "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
