@@ -437,12 +437,14 @@ def test_c2_shape_with_90_angle_grid_matches_oracle():
         np.testing.assert_allclose(x.pred_rot_axis.numpy(), y.pred_rot_axis.numpy(), rtol=1e-4, atol=1e-7)
 
 
+@pytest.mark.parametrize("kernel", ["ldg", "mma"])
 @pytest.mark.parametrize("seed", range(8))
-def test_randomised_shapes_against_c_oracle(seed):
+def test_randomised_shapes_against_c_oracle(seed, kernel, monkeypatch):
     """Random image sizes (W not a multiple of 32, tiny and wide), random blob masks, random planes,
     pivots and rigid transforms in all three modes, ragged target lists: the CUDA pass must equal the
     C restatement bit for bit (projected masks, inter/union tables, arg-max)."""
     from oracle import c_oracle
+    monkeypatch.setenv("A3D_SCORE_KERNEL", kernel)
     rng = np.random.RandomState(1000 + seed)
     H = int(rng.choice([7, 33, 64, 120, 200]))
     W = int(rng.choice([5, 31, 32, 33, 100, 257, 640]))
@@ -498,5 +500,54 @@ def test_randomised_shapes_against_c_oracle(seed):
         t0, b0 = int(jb["tgt_begin"]), int(jb["tab_begin"])
         assert np.array_equal(tab[b0:b0 + T * A].reshape(T, A), inter)
         assert np.array_equal(res.best_cand[t0:t0 + T].cpu().numpy(), best)
+        assert np.array_equal(res.best_union[t0:t0 + T].cpu().numpy(), uni[np.arange(T), best])
+        assert np.array_equal(res.best_iou[t0:t0 + T].cpu().numpy(), iou, equal_nan=True)
+
+
+@pytest.mark.parametrize("key", ["packed", "wide"])
+def test_mma_kernel_tiles_targets_and_candidates(key, monkeypatch):
+    """More targets than one tensor-core tile holds (128) and more candidates than one tile (240):
+    two target tiles x two candidate tiles per job meet in the per-target arg-max key; a second job
+    with an empty source shares the pass.  Checked against the C restatement."""
+    from oracle import c_oracle
+    monkeypatch.setenv("A3D_SCORE_KERNEL", "mma")
+    monkeypatch.setenv("A3D_SCORE_KEY", key)
+    rng = np.random.RandomState(42)
+    H, W = 64, 100
+    cfg = OptConfig.scaled(W, H)
+    n = 7
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks = np.zeros((n, H, W), np.float32)
+    for i in range(n - 1):
+        cy, cx = rng.rand() * H, rng.rand() * W
+        masks[i] = (((yy - cy) / (4 + rng.rand() * H / 2)) ** 2 + ((xx - cx) / (4 + rng.rand() * W / 2)) ** 2 < 1)
+    pool = engine.pack_masks(torch.from_numpy(masks).to(DEV))
+    bits_ref = c_oracle.pack(masks)
+    A = 250
+    ax = rng.randn(A, 3)
+    ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    ang = rng.uniform(-0.6, 0.6, A)
+    xf = np.zeros((A, 12), np.float32)
+    xf[:, :9] = geometry._axis_angle_to_matrix(torch.from_numpy(ax * ang[:, None])).to(torch.float32).numpy().reshape(A, 9)
+    xf[:, 9:] = rng.randn(A, 3).astype(np.float32) * 0.1
+    normal = np.array([0.1, -0.2, 1.0]) / np.linalg.norm([0.1, -0.2, 1.0])
+    specs = []
+    for src, T in ((0, 150), (n - 1, 131)):
+        tg = [int(t) for t in rng.choice(n, size=T, replace=True)]
+        specs.append((src, _lib.MODE_COMPOSED, normal.astype(np.float32), 2.0, np.zeros(3, np.float32), xf, tg))
+    batch = engine.build_batch(*zip(*specs), pool.source_points)
+    res = engine.run_pass(cfg, pool, engine.DeviceBatch(batch, DEV), want_table=True)
+    torch.cuda.synchronize()
+    tab = res.inter_tab.cpu().numpy()
+    for j, (src, mode, nrm, offset, pivot, xf_j, tg) in enumerate(specs):
+        jb = batch.jobs[j]
+        T = len(tg)
+        want = c_oracle.project(cfg.K_inv(), cfg.focal_length, cfg.cx, cfg.cy, H, W, bits_ref[src], nrm, offset,
+                                pivot, mode, xf_j)
+        inter, uni, best, iou = c_oracle.score(H, W, bits_ref[tg], want)
+        t0, b0 = int(jb["tgt_begin"]), int(jb["tab_begin"])
+        assert np.array_equal(tab[b0:b0 + T * A].reshape(T, A), inter)
+        assert np.array_equal(res.best_cand[t0:t0 + T].cpu().numpy(), best)
+        assert np.array_equal(res.best_inter[t0:t0 + T].cpu().numpy(), inter[np.arange(T), best])
         assert np.array_equal(res.best_union[t0:t0 + T].cpu().numpy(), uni[np.arange(T), best])
         assert np.array_equal(res.best_iou[t0:t0 + T].cpu().numpy(), iou, equal_nan=True)

@@ -17,7 +17,11 @@ name = sys.argv[1] if len(sys.argv) > 1 else "c3_shard"
 kernels = sys.argv[2:] or ["ldg", "mma"]
 iters = int(os.environ.get("AB_ITERS", "10"))
 dev = torch.device("cuda:0")
-wl = workloads.WORKLOADS[name]
+if "," in name:                            # custom: videos,tracks,frames,candidates
+    v, t, f, c = (int(x) for x in name.split(","))
+    wl = workloads.Workload(name, "custom", v, t, f, c)
+else:
+    wl = workloads.WORKLOADS[name]
 inp = workloads.build_pass(wl, 2020, dev)
 cfg, pool, db = inp.cfg, inp.pool, inp.dbatch
 ws = engine.Workspace(dev)
@@ -44,6 +48,9 @@ def score(table):
 
 ref = None
 for kern in kernels:
+    if ":" in kern:                       # e.g. mma:pf=0
+        kern, opt = kern.split(":")
+        os.environ["A3D_MMA_PF"] = opt.split("=")[1]
     os.environ["A3D_SCORE_KERNEL"] = kern
     res.inter_tab.zero_()
     score(True)
@@ -57,7 +64,8 @@ for kern in kernels:
         same = "identical" if all(torch.equal(a, b) for a, b in zip(ref, out)) else "DIFFERENT"
     ts = []
     for _ in range(iters):
-        flush.zero_()
+        if not os.environ.get("AB_NOFLUSH"):
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         score(False)
