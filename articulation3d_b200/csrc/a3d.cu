@@ -900,43 +900,44 @@ k_score_tma(const __grid_constant__ TmaMaps maps, const a3d_job_t* __restrict__ 
 // (u8 x u8 -> s32, exact), accumulating a 128 x N tile in tensor memory.
 //   * CTA = (job, 128 targets, N <= 240 candidates); region = (hull of its target boxes) ∩ (hull of
 //     its candidate boxes), walked as one row-major sequence of word positions, 4 per step.
-//   * 8 loader warps, one step each in turn: lane -> (mask, word of the step); 4-byte loads of every
-//     mask's word, all in flight at once, parked in a raw-word ring in shared memory.
-//   * 16 expander warps: thread -> (word of the step, up to 3 masks); 8 shift+mask ops turn a word into
-//     32 bytes (byte 4j+i of the K=32 slice = bit j+8i — any permutation serves as long as both operands
-//     use it), two 16-byte stores into the no-swizzle K-major core-matrix layout
-//     [K chunk of 16 B][row][16 B] (LBO = rows*16, SBO = 128; tools/mma_probe.cu pins the fields),
-//     fence.proxy.async, arrive.  The loads live in other warps because that fence compiles to
-//     MEMBAR.ALL.CTA, which waits for every global load the thread has in flight: with the loads
-//     prefetched by the expanding threads themselves each step cost a full memory round trip.
+//   * 24 producer warps: thread -> (word of the step, up to 2 masks).  One 4-byte load per word, issued
+//     8 steps ahead of its use (register ring, static indices through unrolling); 8 shift+mask ops turn the
+//     word into 32 bytes (byte 4j+i of the K=32 slice = bit j+8i — any permutation serves as long as both
+//     operands use it); two 16-byte stores into the no-swizzle K-major core-matrix layout
+//     [K chunk of 16 B][row][16 B] (LBO = rows*16, SBO = 128; tools/mma_probe.cu pins the fields);
+//     fence.proxy.async; arrive on the stage's full barrier.
 //   * one thread issues one MMA (K = 32 bytes = one word position) per position of the step and commits
-//     the stage back to the expanders.
+//     the stage back to the producers (4 stages).
 //   * epilogue: warps 0-3 read their 32 TMEM lanes (= targets) with tcgen05.ld, and every thread
 //     scans its target's candidates: union, fp32 divide, arg-max key, one atomicMax per target.
+// Bound: shared-memory bandwidth — every mask bit crosses shared memory as a byte twice
+// (producer store, tensor-core operand read: 2 x 10 KB per word position at N = 192).  A variant with
+// dedicated loader warps and a raw-word ring measured slower (650 vs 440 us on the C3 shard), an L2
+// prefetch of the rows ahead made no difference: the loads are not the limit.
 // ---------------------------------------------------------------------------
-constexpr int kMmaExpWarps = 16;              // expander warps (0..15; 0..3 also run the epilogue)
-constexpr int kMmaExpThreads = 32 * kMmaExpWarps;
-constexpr int kMmaLoadWarps = 8;              // loader warps (17..24), one raw slot each
-constexpr int kMmaThreads = 32 * (kMmaExpWarps + 1 + kMmaLoadWarps);
+#ifndef A3D_MMA_WARPS
+#define A3D_MMA_WARPS 24
+#endif
+#ifndef A3D_MMA_AHEAD
+#define A3D_MMA_AHEAD 8
+#endif
+constexpr int kMmaProducerWarps = A3D_MMA_WARPS;
+constexpr int kMmaProducers = 32 * kMmaProducerWarps;
+constexpr int kMmaThreads = kMmaProducers + 32;   // + the issuing warp
 constexpr int kMmaM = 128;                    // targets per CTA (TMEM lanes)
 constexpr int kMmaNMax = 240;                 // candidates per CTA (TMEM columns), multiple of 16
-constexpr int kMmaMaxStages = 4;
-constexpr int kMmaPos = 4;                    // word positions per step
-constexpr int kMmaSlots = kMmaExpThreads / kMmaPos * ((kMmaM + kMmaNMax + kMmaExpThreads / kMmaPos - 1) / (kMmaExpThreads / kMmaPos));   // mask slots: 384
-constexpr int kMmaItems = kMmaSlots / (kMmaExpThreads / kMmaPos);   // words per expander thread per step: 3
-constexpr int kMmaLoads = kMmaSlots * kMmaPos / 32;                   // words per loader lane per step: 48
-constexpr int kMmaRawBytes = kMmaSlots * kMmaPos * 4;                 // one raw slot
+constexpr int kMmaStages = 4;
+constexpr int kMmaPos = 4;                    // word positions per stage
+constexpr int kMmaItems = ((kMmaM + kMmaNMax) * kMmaPos + kMmaProducers - 1) / kMmaProducers;   // words per producer thread per step
 constexpr int kMmaABlock = 2 * kMmaM * 16;    // bytes of one position of A
 constexpr int kMmaTmemCols = 256;
+constexpr int kMmaAhead = A3D_MMA_AHEAD;                  // steps between a producer's loads and its stores
+
 // position blocks of one stage are padded by 32 bytes so that the 16-byte stores of a quarter-warp
 // (4 words of one mask, then of the next mask) hit distinct banks
 constexpr int kMmaPad = 32;
 __host__ __device__ constexpr size_t mma_stage_bytes(int nb) {
     return (size_t)kMmaPos * (kMmaABlock + kMmaPad) + (size_t)kMmaPos * (2 * nb * 16 + kMmaPad);
-}
-__host__ __device__ constexpr int mma_stages(int nb) { return nb <= 192 ? 4 : 3; }
-__host__ __device__ constexpr size_t mma_smem_bytes(int nb) {
-    return (size_t)mma_stages(nb) * mma_stage_bytes(nb) + (size_t)kMmaLoadWarps * kMmaRawBytes;
 }
 
 // bounded wait: a broken pipeline traps (launch error) instead of hanging the GPU
@@ -967,15 +968,6 @@ __device__ __forceinline__ void expand_store(uint32_t w, uint32_t dst, uint32_t 
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kc_stride), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]) : "memory");
 }
 
-#ifdef A3D_MMA_TIMING
-__device__ unsigned long long g_mma_timing[64];
-#define TMARK(var) const long long var = clock64()
-#define TADD(slot, a, b) do { if (blockIdx.x == 0 && lane == 0) t_acc[slot] += (unsigned long long)((b) - (a)); } while (0)
-#else
-#define TMARK(var)
-#define TADD(slot, a, b)
-#endif
-
 __global__ void __launch_bounds__(kMmaThreads, 1)
 k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int ct_tiles, int ctile,
             const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
@@ -983,11 +975,11 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
             const uint32_t* __restrict__ proj_bits, const int32_t* __restrict__ proj_popc,
             const int32_t* __restrict__ proj_bbox, unsigned long long* __restrict__ key_ws,
             int32_t* __restrict__ inter_tab, int packed) {
-    extern __shared__ __align__(1024) uint8_t stage_mem[];    // [stages][A | B position blocks] [raw ring]
-    __shared__ const uint32_t* s_ptr[kMmaSlots];              // word (ra, ca) of every mask of the tile
+    extern __shared__ __align__(1024) uint8_t stage_mem[];
+    __shared__ const uint32_t* s_ptr[kMmaM + kMmaNMax];       // first word of every mask of the tile
     __shared__ int s_pc[kMmaNMax];                            // pixel counts of the candidates
     __shared__ int s_box[8];                                  // target hull, candidate hull
-    __shared__ __align__(8) uint64_t s_bar[2 * kMmaMaxStages + 1 + 2 * kMmaLoadWarps];
+    __shared__ __align__(8) uint64_t s_bar[2 * kMmaStages + 1];
     __shared__ uint32_t s_tmem;
 
     const int per_job = tt_tiles * ct_tiles;
@@ -999,34 +991,28 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
     if (tb >= job.n_tgt || cb >= job.n_cand) return;           // whole CTA leaves together
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nt = min(kMmaM, job.n_tgt - tb), nc = min(ctile, job.n_cand - cb);
-    const int nmask = nt + nc;
     const int nb = (nc + 15) & ~15;                            // MMA N
-    const int stages = mma_stages((ctile + 15) & ~15);         // as the launch sized shared memory
     const size_t words = (size_t)H * pitch;
-    // barriers: full[stage], empty[stage], accumulator done, raw_full[slot], raw_empty[slot]
-    const uint32_t bar_full = smem_u32(&s_bar[0]), bar_empty = bar_full + 8u * kMmaMaxStages;
-    const uint32_t bar_done = bar_full + 16u * kMmaMaxStages;
-    const uint32_t bar_raw_full = bar_done + 8u, bar_raw_empty = bar_raw_full + 8u * kMmaLoadWarps;
 
     if (tid < 8) s_box[tid] = (tid & 1) ? -1 : 0x7fffffff;     // {r0, r1, c0, c1} x {targets, candidates}
     if (tid == 0) {
-        for (int i = 0; i < kMmaMaxStages; ++i) {
-            mbar_init(bar_full + 8u * i, kMmaExpWarps);        // one arrive per expander warp
-            mbar_init(bar_empty + 8u * i, 1);                  // one tcgen05.commit
+        for (int i = 0; i < kMmaStages; ++i) {
+#ifdef A3D_MMA_WARP_ARRIVE
+            mbar_init(smem_u32(&s_bar[i]), kMmaProducerWarps);             // full: one arrive per producer warp
+#else
+            mbar_init(smem_u32(&s_bar[i]), kMmaProducers);                 // full: every producer thread arrives
+#endif
+            mbar_init(smem_u32(&s_bar[kMmaStages + i]), 1);                // empty: one tcgen05.commit
         }
-        mbar_init(bar_done, 1);
-        for (int i = 0; i < kMmaLoadWarps; ++i) {
-            mbar_init(bar_raw_full + 8u * i, 1);               // the slot's loader warp
-            mbar_init(bar_raw_empty + 8u * i, kMmaExpWarps);
-        }
+        mbar_init(smem_u32(&s_bar[2 * kMmaStages]), 1);                    // accumulator complete
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kMmaExpWarps) {
+    if (warp == kMmaProducerWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kMmaTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     __syncthreads();
-    for (int m = tid; m < nmask; m += kMmaThreads) {
+    for (int m = tid; m < nt + nc; m += kMmaThreads) {
         const int32_t* b;
         if (m < nt) {
             const int ti = tgt_index[job.tgt_begin + tb + m];
@@ -1043,13 +1029,13 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
             atomicMin(box + 0, b[0]); atomicMax(box + 1, b[1]); atomicMin(box + 2, b[2]); atomicMax(box + 3, b[3]);
         }
     }
-    __syncthreads();
-    for (int m = nmask + tid; m < kMmaSlots; m += kMmaThreads) s_ptr[m] = s_ptr[nmask - 1];   // unused slots alias a valid mask
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
 
+    // region = (hull of the target boxes) ∩ (hull of the candidate boxes), walked as one row-major
+    // sequence of word positions; a step = kMmaPos consecutive positions = kMmaPos MMAs
     const int ra = max(s_box[0], s_box[4]), rb = min(s_box[1], s_box[5]);
     const int ca = max(s_box[2], s_box[6]), ce = min(s_box[3], s_box[7]);
     int npos = 0, ncols = 1;
@@ -1060,136 +1046,92 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
     const int nsteps = (npos + kMmaPos - 1) / kMmaPos;
     const uint32_t stage0 = smem_u32(stage_mem);
     const uint32_t stage_bytes = (uint32_t)mma_stage_bytes(nb);
-    const uint32_t raw0 = stage0 + (uint32_t)(mma_stages((ctile + 15) & ~15) * mma_stage_bytes((ctile + 15) & ~15));
     const uint32_t b_off = (uint32_t)kMmaPos * (kMmaABlock + kMmaPad);
     const uint32_t b_block = (uint32_t)(2 * nb * 16);
+    const uint32_t bar0 = smem_u32(&s_bar[0]);
 
-#ifdef A3D_MMA_TIMING
-    unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long t_begin = clock64();
-#endif
-    if (warp > kMmaExpWarps) {
-        // ===== loaders: warp j takes steps j, j + 8, ...; raw word (slot m, word q of the step) at 4 m + q =====
-        const int j = warp - kMmaExpWarps - 1;
-        const int q = lane & (kMmaPos - 1);
-        const int nld = (nmask + 7) >> 3;                      // loads per lane per step (8 masks per warp load)
-        const uint32_t raw = raw0 + (uint32_t)j * kMmaRawBytes + (uint32_t)lane * 4u;
-        const uint32_t tab = smem_u32(s_ptr) + (uint32_t)(lane >> 2) * 8u;      // &s_ptr[lane >> 2]; + 64 t for slot + 8 t
-        // this lane's position in step k: p = 4 k + q = row * ncols + col; a turn advances it by 32 positions
-        const int dr = (kMmaPos * kMmaLoadWarps) / ncols, dc = (kMmaPos * kMmaLoadWarps) - dr * ncols;
-        int p = kMmaPos * j + q;
-        int col = p % ncols;
-        unsigned rowoff = (unsigned)(ra * pitch + ca) + (unsigned)((p / ncols) * pitch);
-        uint32_t turn = 0;
-        for (int k = j; k < nsteps; k += kMmaLoadWarps, ++turn) {
-            TMARK(t0);
-            mbar_wait_bounded(bar_raw_empty + 8u * (uint32_t)j, (turn & 1u) ^ 1u);
-            TMARK(t1);
-            // positions past the end of the region (last step only) read word 0 of the region: any valid word
-            // will do, the expanders skip them
-            const unsigned o = p < npos ? rowoff + (unsigned)col : (unsigned)(ra * pitch + ca);
-            uint32_t v[kMmaLoads];
-#pragma unroll
-            for (int g = 0; g < kMmaLoads / 8; ++g) {
-                if (g * 8 < nld) {                             // uniform; slots past nmask alias the last mask
-                    uint64_t ptr[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t)
-                        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(ptr[t]) : "r"(tab + 64u * (uint32_t)(g * 8 + t)));
-#pragma unroll
-                    for (int t = 0; t < 8; ++t)
-                        v[g * 8 + t] = __ldg(reinterpret_cast<const uint32_t*>(ptr[t]) + o);
-                }
-            }
-            TMARK(t2);
-#ifdef A3D_MMA_TIMING
-            asm volatile("" ::"r"(v[0]) : "memory");             // first use of the first load
-            TMARK(t3);
-#endif
-#pragma unroll
-            for (int g = 0; g < kMmaLoads / 8; ++g) {
-                if (g * 8 < nld) {
-#pragma unroll
-                    for (int t = 0; t < 8; ++t)
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(raw + 128u * (uint32_t)(g * 8 + t)), "r"(v[g * 8 + t]) : "memory");
-                }
-            }
-            // one arrive per warp (hundreds of arrives on one barrier word serialise): the warp barrier orders the
-            // lanes' stores before lane 0's releasing arrive
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_raw_full + 8u * (uint32_t)j);
-            TMARK(t4);
-            TADD(0, t0, t1); TADD(1, t1, t2); TADD(2, t2, t3); TADD(3, t3, t4); TADD(4, t0, t0 + 1);
-            p += kMmaPos * kMmaLoadWarps;
-            col += dc;
-            rowoff += (unsigned)(dr * pitch);
-            if (col >= ncols) { col -= ncols; rowoff += (unsigned)pitch; }
-        }
-    } else if (warp < kMmaExpWarps) {
-        // ===== expanders: thread -> word (tid & 3) of the step for the mask slots (tid >> 2) + 128 u =====
+    if (warp < kMmaProducerWarps) {
+        // ===== producers =====
+        // thread -> word (tid & 3) of the step, for the masks (tid >> 2) + 128 u: one position cursor per
+        // thread, a constant stage slot per (thread, u).  Loads run kMmaAhead steps ahead of the stores in
+        // a register ring (static indices through full unrolling).
+        const int nmask = nt + nc;
         const int q = tid & (kMmaPos - 1);
+        const uint32_t* src[kMmaItems];             // word (ra, ca) of this thread's masks
         uint32_t dst[kMmaItems];                    // byte offset of the mask's 16-byte row slot inside a stage
         uint32_t kcs[kMmaItems];                    // distance of the second K chunk
         bool act[kMmaItems];
 #pragma unroll
         for (int u = 0; u < kMmaItems; ++u) {
-            const int m = (tid >> 2) + u * (kMmaExpThreads / kMmaPos);
+            const int m = (tid >> 2) + u * (kMmaProducers / kMmaPos);
             act[u] = m < nmask;
+            src[u] = act[u] ? s_ptr[m] + (size_t)ra * pitch + ca : nullptr;
             const bool a_row = m < nt;
             dst[u] = a_row ? (uint32_t)q * (kMmaABlock + kMmaPad) + (uint32_t)m * 16u
                            : b_off + (uint32_t)q * (b_block + kMmaPad) + (uint32_t)(m - nt) * 16u;
             kcs[u] = a_row ? (uint32_t)(kMmaM * 16) : (uint32_t)nb * 16u;
         }
-        int st = 0, p = q;
-        uint32_t ph = 0;
-        for (int k = 0; k < nsteps; ++k) {
-            const uint32_t rs = (uint32_t)k & (kMmaLoadWarps - 1);
-            TMARK(t0);
-            mbar_wait_bounded(bar_raw_full + 8u * rs, ((uint32_t)k / kMmaLoadWarps) & 1u);
-            TMARK(t1);
-            uint32_t w[kMmaItems];
-            const uint32_t rsrc = raw0 + rs * kMmaRawBytes + (uint32_t)tid * 4u;
+        // position of this thread's word in the step the load cursor is at: p = 4 k + q = row * ncols + col
+        const int dr = kMmaPos / ncols, dc = kMmaPos - dr * ncols;
+        int p_ld = q, col = q % ncols;
+        unsigned rowoff = (unsigned)((q / ncols) * pitch);
+        auto load_step = [&](uint32_t (&w)[kMmaItems]) {
+            const unsigned o = rowoff + (unsigned)col;
+            const bool in = p_ld < npos;
 #pragma unroll
             for (int u = 0; u < kMmaItems; ++u)
-                if (act[u]) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w[u]) : "r"(rsrc + (uint32_t)(u * kMmaExpThreads * 4)) : "memory");
-            TMARK(t2);
-            mbar_wait_bounded(bar_empty + 8u * (uint32_t)st, ph ^ 1u);
-            TMARK(t3);
-            if (p < npos) {
-                const uint32_t sa = stage0 + (uint32_t)st * stage_bytes;
+                if (act[u] && in) w[u] = __ldg(src[u] + o);
+            p_ld += kMmaPos;
+            col += dc;
+            rowoff += (unsigned)(dr * pitch);
+            if (col >= ncols) { col -= ncols; rowoff += (unsigned)pitch; }
+        };
+        int p_st = q;
+        auto store_step = [&](int st, uint32_t parity, const uint32_t (&w)[kMmaItems]) {
+            const uint32_t sa = stage0 + (uint32_t)st * stage_bytes;
+            mbar_wait_bounded(bar0 + 8u * (uint32_t)(kMmaStages + st), parity ^ 1u);
+            if (p_st < npos) {
 #pragma unroll
                 for (int u = 0; u < kMmaItems; ++u)
                     if (act[u]) expand_store(w[u], sa + dst[u], kcs[u]);
             }
-            TMARK(t4);
+            p_st += kMmaPos;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> async-proxy (MMA) reads
-            TMARK(t5);
+#ifdef A3D_MMA_WARP_ARRIVE
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar_full + 8u * (uint32_t)st);
-                mbar_arrive(bar_raw_empty + 8u * rs);          // the raw words are in registers / expanded
+            if (lane == 0) mbar_arrive(bar0 + 8u * (uint32_t)st);
+#else
+            mbar_arrive(bar0 + 8u * (uint32_t)st);
+#endif
+        };
+        static_assert(kMmaAhead % kMmaStages == 0, "stage and phase of a step must be static in the unrolled loop");
+        uint32_t ring[kMmaAhead][kMmaItems];
+#pragma unroll
+        for (int d = 0; d < kMmaAhead - 1; ++d)
+            if (d < nsteps) load_step(ring[d]);
+        for (int k0 = 0; k0 < nsteps; k0 += kMmaAhead) {
+#pragma unroll
+            for (int d = 0; d < kMmaAhead; ++d) {
+                const int k = k0 + d;
+                if (k < nsteps) {
+                    if (k + kMmaAhead - 1 < nsteps) load_step(ring[(d + kMmaAhead - 1) % kMmaAhead]);
+                    store_step(d % kMmaStages, (uint32_t)((d / kMmaStages) & 1), ring[d]);
+                }
             }
-            TMARK(t6);
-            TADD(0, t0, t1); TADD(1, t1, t2); TADD(2, t2, t3); TADD(3, t3, t4); TADD(4, t4, t5); TADD(5, t5, t6); TADD(6, t0, t0 + 1);
-            p += kMmaPos;
-            if (++st == stages) { st = 0; ph ^= 1u; }
         }
     } else if (lane == 0) {
         // ===== MMA issuer (one thread) =====
         const uint32_t idesc = (2u << 4) | ((uint32_t)(nb >> 3) << 17) | ((uint32_t)(kMmaM >> 4) << 24);   // u8 x u8 -> s32, K-major
-        int st = 0;
-        uint32_t ph = 0;
         for (int k = 0; k < nsteps; ++k) {
+            const int st = k % kMmaStages;
             const int cw = min(kMmaPos, npos - k * kMmaPos);
             const uint32_t sa = stage0 + (uint32_t)st * stage_bytes, sb = sa + b_off;
-            TMARK(t0);
-            mbar_wait_bounded(bar_full + 8u * (uint32_t)st, ph);
-            TMARK(t1);
+            mbar_wait_bounded(bar0 + 8u * (uint32_t)st, (uint32_t)((k / kMmaStages) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int i = 0; i < cw; ++i) {
-                const uint64_t da = umma_desc(sa + (uint32_t)i * (kMmaABlock + kMmaPad), kMmaM * 16);
-                const uint64_t db = umma_desc(sb + (uint32_t)i * (b_block + kMmaPad), (uint32_t)nb * 16u);
-                const uint32_t acc = (k > 0 || i > 0) ? 1u : 0u;
+            for (int j = 0; j < cw; ++j) {
+                const uint64_t da = umma_desc(sa + (uint32_t)j * (kMmaABlock + kMmaPad), kMmaM * 16);
+                const uint64_t db = umma_desc(sb + (uint32_t)j * (b_block + kMmaPad), (uint32_t)nb * 16u);
+                const uint32_t acc = (k > 0 || j > 0) ? 1u : 0u;
                 asm volatile(
                     "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                     "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
@@ -1197,20 +1139,17 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
             }
             // arrives on the stage's empty barrier once these MMAs have read shared memory
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                         ::"r"(bar_empty + 8u * (uint32_t)st) : "memory");
-            TMARK(t2);
-            TADD(0, t0, t1); TADD(1, t1, t2); TADD(2, t0, t0 + 1);
-            if (++st == stages) { st = 0; ph ^= 1u; }
+                         ::"r"(bar0 + 8u * (uint32_t)(kMmaStages + st)) : "memory");
         }
         if (nsteps > 0)
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                         ::"r"(bar_done) : "memory");
+                         ::"r"(bar0 + 8u * (uint32_t)(2 * kMmaStages)) : "memory");
     }
 
     if (warp < 4) {
         // ===== epilogue: TMEM lane = target, column = candidate =====
         if (nsteps > 0) {
-            mbar_wait_bounded(bar_done, 0u);
+            mbar_wait_bounded(bar0 + 8u * (uint32_t)(2 * kMmaStages), 0u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const int m = warp * 32 + lane;
@@ -1229,14 +1168,14 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0u;
+                for (int j = 0; j < 16; ++j) v[j] = 0u;
             }
             if (valid) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = c0 + i;
+                for (int j = 0; j < 16; ++j) {
+                    const int c = c0 + j;
                     if (c < nc) {
-                        const int inter = (int)v[i];
+                        const int inter = (int)v[j];
                         const int uni = pt + s_pc[c] - inter;
                         const float iou = __fdiv_rn((float)inter, (float)uni);
                         const unsigned long long key = make_key(iou, cb + c, inter, packed);
@@ -1248,16 +1187,9 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
         }
         if (valid) atomicMax(key_ws + job.tgt_begin + tb + m, best);
     }
-#ifdef A3D_MMA_TIMING
-    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kMmaExpWarps - 1 || warp == kMmaExpWarps || warp == kMmaExpWarps + 1)) {
-        const int row = warp == 0 ? 0 : (warp == kMmaExpWarps - 1 ? 1 : (warp == kMmaExpWarps ? 2 : 3));
-        for (int i = 0; i < 8; ++i) g_mma_timing[row * 8 + i] = t_acc[i];
-        if (warp == 0) { g_mma_timing[32] = (unsigned long long)(clock64() - t_begin); g_mma_timing[33] = (unsigned long long)nsteps; g_mma_timing[34] = (unsigned long long)nmask; }
-    }
-#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == kMmaExpWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kMmaTmemCols));
+    if (warp == kMmaProducerWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kMmaTmemCols));
 }
 
 // decode the winning candidate of every target.  Packed keys carry the intersection count
@@ -1638,9 +1570,11 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
     //  * k_score ("ldg"): AND + popcount on the integer pipes, direct loads, per-warp regions — every SM
     //    works on every job, so it is the one for few or small jobs;
     //  * k_score_mma ("mma"): tensor cores (tcgen05 kind::i8 on bit-expanded masks), one CTA per
-    //    (job, 128 targets, <= 240 candidates).  Measured on B200 (tools/score_ab.py, 120 targets x 180
-    //    candidates per job): 1.9x faster than k_score at 256 jobs, 1.2x at 96, slower below ~70 jobs or
-    //    when a job has few (target, candidate) pairs (60 x 45: 0.7x) — hence the automatic choice below;
+    //    (job, 128 targets, <= 240 candidates); its time is ~245 us per wave of CTAs almost regardless of
+    //    the candidate count.  Measured on B200 (tools/score_ab.py), 120 targets per job:
+    //    180 candidates x 256 jobs 440 us vs 1232 us; x 64 jobs 251 vs 322; x 48 jobs 249 vs 245;
+    //    720 candidates x 64 jobs 421 vs 1138; but 60 x 90 x 256 jobs 339 vs 355 and 60 x 45: 323 vs 204
+    //    — hence the automatic choice below: enough CTAs to fill the SMs and big (target, candidate) tiles;
     //  * k_score_tma ("tma"): TMA-staged variant of k_score, measured slower than direct loads.
     const char* env_kernel = getenv("A3D_SCORE_KERNEL");
     const bool use_tma = env_kernel && !strcmp(env_kernel, "tma");
@@ -1648,7 +1582,7 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
     int mma_ctile = (max_cand + 15) & ~15;
     if (mma_ctile > kMmaNMax) mma_ctile = kMmaNMax;
     const long long mma_blocks = (long long)n_jobs * ((max_tgt + kMmaM - 1) / kMmaM) * ((max_cand + mma_ctile - 1) / mma_ctile);
-    const bool mma_auto = mma_blocks >= 96 && (long long)(max_tgt < kMmaM ? max_tgt : kMmaM) * mma_ctile >= 12288;
+    const bool mma_auto = mma_blocks >= 60 && (long long)(max_tgt < kMmaM ? max_tgt : kMmaM) * mma_ctile >= 16384;
     const bool use_mma = env_kernel ? !strcmp(env_kernel, "mma") : mma_auto;
     if (use_mma) {
         // tensor-core scoring: CTA = (job, 128 targets, <= 240 candidates)
@@ -1656,7 +1590,7 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
         const int tt_tiles = (max_tgt + kMmaM - 1) / kMmaM, ct_tiles = (max_cand + ctile - 1) / ctile;
         const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;
         if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
-        const size_t smem = mma_smem_bytes(ctile);
+        const size_t smem = (size_t)kMmaStages * mma_stage_bytes(ctile);
         A3D_CUDA_TRY(cudaFuncSetAttribute(k_score_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_score_mma<<<(unsigned)nblocks, kMmaThreads, smem, s>>>(jobs, H, pitch, tt_tiles, ct_tiles, ctile, tgt_bits,
                                                                  tgt_popc, tgt_bbox, tgt_index, proj_bits, proj_popc,
@@ -1716,12 +1650,6 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
     A3D_CUDA_TRY(cudaGetLastError());
     return A3D_OK;
 }
-
-#ifdef A3D_MMA_TIMING
-extern "C" int a3d_debug_mma_timing(unsigned long long* out) {
-    return (int)cudaMemcpyFromSymbol(out, g_mma_timing, sizeof(unsigned long long) * 64);
-}
-#endif
 
 int a3d_emit_masks(const uint32_t* bits, const int32_t* index, int64_t n, int H, int W,
                    int out_dtype, void* out, void* stream) {

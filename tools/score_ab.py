@@ -11,7 +11,11 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from articulation3d_b200 import _lib, engine, workloads  # noqa: E402
+from articulation3d_b200 import _lib  # noqa: E402
+
+if os.environ.get("A3D_LIB"):              # a tuning build of csrc/a3d.cu (tools/_build/*.so)
+    _lib.LIB_PATH = os.path.abspath(os.environ["A3D_LIB"])
+from articulation3d_b200 import engine, workloads  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c3_shard"
 kernels = sys.argv[2:] or ["ldg", "mma"]
