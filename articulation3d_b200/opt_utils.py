@@ -44,6 +44,7 @@ linregress = getattr(_scipy_linregress, "__wrapped__", _scipy_linregress)
 from . import _lib, engine, geometry
 from .axis import angle_offset_to_axis, axis_to_angle_offset
 from .config import OptConfig
+from .diagnostics import check_axis, check_monotonic, fit_plane_from_normals  # noqa: F401  (reference names, row a15)
 
 __all__ = ["track_planes", "optimize_planes", "optimize_planes_3dc", "optimize_planes_3d_trans",
            "optimize_planes_3d", "optimize_planes_average", "optimize_videos", "RegMasks"]

@@ -141,6 +141,38 @@ def run_reference(preds, seed: int, method: str = "3dc") -> dict:
     return res
 
 
+def run_reference_diag(preds, seed: int) -> dict:
+    """The reference's own diagnostics (``check_axis`` / ``check_monotonic``, utils/opt_utils.py:977-1152)
+    on a clip before / after its ``optimize_planes('3dc')``."""
+    from articulation3d_b200 import synth
+    ou = ref_shim.load_reference()
+    before = synth.clone_preds(preds, ref_shim.Instances, ref_shim.Boxes)
+    work = synth.clone_preds(preds, ref_shim.Instances, ref_shim.Boxes)
+    random.seed(seed)
+    planes = ou.track_planes(work)
+    out = ou.optimize_planes(work, planes, "3dc")
+    s0, s1 = ou.check_axis(before, out, planes["rot"], "3dc")
+    c0, c1 = ou.check_monotonic(before, out, planes["rot"], "3dc")
+    return {"axis_scores": np.array([float(v) for v in s0], dtype=np.float64),
+            "axis_scores_opt": np.array([float(v) for v in s1], dtype=np.float64),
+            "fit_scores": np.array([float(v[0]) for v in c0], dtype=np.float64),
+            "fit_scores_opt": np.array([float(v[0]) for v in c1], dtype=np.float64)}
+
+
+def main_diag():
+    from articulation3d_b200 import synth
+    if not ref_shim.available():
+        raise SystemExit("reference not present; fixtures can only be generated in the build container")
+    os.makedirs(os.path.join(GOLDEN_DIR, "diag"), exist_ok=True)
+    for name in ("clip_a", "clip_b", "clip_d"):
+        seed, n_tracks, n_frames, kinds, drop = CASES[name]
+        preds, _ = synth.make_video(seed, n_tracks, n_frames, kinds=kinds, drop_prob=drop)
+        res = run_reference_diag(preds, seed)
+        path = os.path.join(GOLDEN_DIR, "diag", f"{name}.npz")
+        np.savez_compressed(path, **res)
+        print(f"wrote {path}: {len(res['axis_scores'])} axis pairs, fit {res['fit_scores']} -> {res['fit_scores_opt']}")
+
+
 def main():
     from articulation3d_b200 import synth
     if not ref_shim.available():
@@ -159,4 +191,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main_diag() if "--diag" in sys.argv else main()
