@@ -77,11 +77,21 @@ def source_geometry(p_instance, box_id: int, cfg: OptConfig, translation: bool,
     return SourceGeometry(normal, offset, pts, axis3d, d, axis3d[0].astype(np.float32))
 
 
+# quaternion -> matrix entry e = two_s * (q_a q_b + sign * q_c q_d), diagonal entries 1 - e;
+# indices into the flattened 4x4 table of products of q = (r, i, j, k)
+_QM_FIRST = torch.tensor([10, 6, 7, 6, 5, 11, 7, 11, 5])          # jj ij ik | ij ii jk | ik jk ii
+_QM_SECOND = torch.tensor([15, 12, 8, 12, 15, 4, 8, 4, 10])       # kk kr jr | kr kk ir | jr ir jj
+_QM_SIGN = torch.tensor([1., -1., 1., 1., 1., -1., -1., 1., 1.], dtype=torch.float64)
+_QM_DIAG = torch.tensor([0, 4, 8])
+
+
 def _axis_angle_to_matrix(axis_angle: torch.Tensor) -> torch.Tensor:
     """Rotation matrices of axis-angle vectors via unit quaternions, in the input
     dtype (float64 here) — the construction pytorch3d's ``axis_angle_to_matrix``
     documents: q = [cos(t/2), v sin(t/2)/t] (Taylor 1/2 - t^2/48 for |t| < 1e-6),
-    R from two_s = 2/|q|^2."""
+    R from two_s = 2/|q|^2, e.g. R00 = 1 - two_s (jj + kk), R01 = two_s (ij - kr).
+    The nine entries are evaluated together from the table of pairwise products — the same
+    multiplications, additions (x - y as x + (-1) y) and order per entry, so the same bits."""
     t = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
     half = t * 0.5
     small = t.abs() < 1e-6
@@ -92,12 +102,10 @@ def _axis_angle_to_matrix(axis_angle: torch.Tensor) -> torch.Tensor:
     else:                                   # same elementwise values, without the masked gathers/scatters
         k = torch.sin(half) / t
     q = torch.cat([torch.cos(half), axis_angle * k], dim=-1)
-    r, i, j, kk = torch.unbind(q, -1)
-    two_s = 2.0 / (q * q).sum(-1)
-    m = torch.stack((
-        1 - two_s * (j * j + kk * kk), two_s * (i * j - kk * r), two_s * (i * kk + j * r),
-        two_s * (i * j + kk * r), 1 - two_s * (i * i + kk * kk), two_s * (j * kk - i * r),
-        two_s * (i * kk - j * r), two_s * (j * kk + i * r), 1 - two_s * (i * i + j * j)), -1)
+    two_s = 2.0 / (q * q).sum(-1, keepdim=True)
+    prod = (q.unsqueeze(-1) * q.unsqueeze(-2)).flatten(-2)
+    m = two_s * (prod.index_select(-1, _QM_FIRST) + _QM_SIGN.to(q.dtype) * prod.index_select(-1, _QM_SECOND))
+    m[..., _QM_DIAG] = 1 - m[..., _QM_DIAG]
     return m.reshape(q.shape[:-1] + (3, 3))
 
 

@@ -41,9 +41,30 @@ from scipy.stats import linregress as _scipy_linregress
 # for 1-D finite inputs it forwards unchanged to this inner function (tests/test_host_logic.py).
 linregress = getattr(_scipy_linregress, "__wrapped__", _scipy_linregress)
 
+
+
+def _rvalue(y) -> np.float64:
+    """Pearson r of ``y`` against 0..n-1, exactly as ``scipy.stats.linregress(range(n), y).rvalue``
+    computes it (float64; mean-removed dot products through ``np.vecdot``; clip to [-1, 1]; NaN when both
+    the covariance and a variance vanish, 0 when only a variance does) without the array-API plumbing
+    around it, which costs several times the arithmetic.  tests/test_host_logic.py checks bit equality."""
+    y = np.asarray(y).astype(np.float64)
+    n = y.shape[0]
+    x = np.arange(n, dtype=np.float64)
+    x_ = x - np.mean(x, keepdims=True)
+    y_ = y - np.mean(y, keepdims=True)
+    ssxm = np.vecdot(x_, x_) / n
+    ssym = np.vecdot(y_, y_) / n
+    ssxym = np.vecdot(x_, y_) / n
+    if ssxm == 0.0 or ssym == 0.0:
+        return np.float64(np.nan) if ssxym == 0 else np.float64(0.0)
+    return np.clip(ssxym / np.sqrt(ssxm * ssym), -1.0, 1.0)
+
+
 from . import _lib, engine, geometry
 from .axis import angle_offset_to_axis, axis_to_angle_offset
 from .config import OptConfig
+from .structures import Instances as _OwnInstances
 from .diagnostics import check_axis, check_monotonic, fit_plane_from_normals  # noqa: F401  (reference names, row a15)
 
 __all__ = ["track_planes", "optimize_planes", "optimize_planes_3dc", "optimize_planes_3d_trans",
@@ -204,12 +225,15 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
         ids = plane['ids']
         id_list = list(ids.keys())
         clusters = []
+        geo_of = {}                       # source frame -> geometry (the final phase reuses its centre frame's)
         for _ in range(cfg.rounds):
             if len(id_list) == 0 and remove_inliers:
                 break
             select_idx = rng.choice(id_list)
             box_id = ids[select_idx]
-            geo = geometry.source_geometry(preds[select_idx], box_id, cfg, translation)
+            geo = geo_of.get(select_idx)
+            if geo is None:
+                geo = geo_of[select_idx] = geometry.source_geometry(preds[select_idx], box_id, cfg, translation)
             xf, angles, _ = _candidates(geo, cgrid, cmode)
             order = list(id_list)
             res = yield JobSpec(pool_of[(select_idx, box_id)], cmode, geo.normal.numpy(), float(geo.offset),
@@ -240,7 +264,7 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
             if len(cluster['inliners']) < cfg.min_inliers:
                 rsqs.append(0.0)
                 continue
-            rsqs.append(linregress(range(cluster['angles'].shape[0]), cluster['angles']).rvalue ** 2)
+            rsqs.append(_rvalue(cluster['angles'].numpy()) ** 2)
         rsqs = np.array(rsqs)
         if rsqs.max() < cfg.rsq_thresh:
             plane['has_rot'] = False
@@ -254,7 +278,8 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
         select_idx = final_cluster['center_id']
         box_id = ids[select_idx]
         p_instance = preds[select_idx]
-        geo = geometry.source_geometry(p_instance, box_id, cfg, translation, all_boxes=legacy)
+        geo = geo_of[select_idx] if not legacy else \
+            geometry.source_geometry(p_instance, box_id, cfg, translation, all_boxes=True)
         xf, angles, R = _candidates(geo, fgrid, fmode)
         frames = list(ids.keys())
         spec = JobSpec(pool_of[(select_idx, box_id)], fmode, geo.normal.numpy(), float(geo.offset),
@@ -293,6 +318,18 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
 # write-back (host; reference :624-682, :910-959, legacy :342-379)
 # ---------------------------------------------------------------------------
 def _rebuild(p_instance, scores):
+    if type(p_instance) is _OwnInstances:          # same fields, same order, without eight length checks
+        f = p_instance.get_fields()
+        fields = {"scores": scores, "pred_boxes": f["pred_boxes"], "pred_planes": f["pred_planes"],
+                  "pred_rot_axis": f["pred_rot_axis"], "pred_tran_axis": f["pred_tran_axis"]}
+        for name in ("pred_masks", "pred_rle"):
+            if name in f:
+                fields[name] = f[name]
+        fields["pred_classes"] = f["pred_classes"]
+        out = _OwnInstances.__new__(_OwnInstances)
+        object.__setattr__(out, "_image_size", p_instance.image_size)
+        object.__setattr__(out, "_fields", fields)
+        return out
     out = type(p_instance)(p_instance.image_size)
     out.scores = scores
     out.pred_boxes = p_instance.pred_boxes

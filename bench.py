@@ -269,10 +269,17 @@ def measure_pass(wl, steps, warmup, dev, rank, world, dist, sample_clocks=True):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(wl.name, {}).get("k_project" if proj_dom else "k_score")
+    # second bound of SURVEY 8d: the instruction pipes, as ncu saw them on the committed captures
+    pipes = None
+    ppath = os.path.join(ROOT, "profiles", "pipes.json")
+    if os.path.exists(ppath):
+        with open(ppath) as f:
+            pipes = json.load(f).get(wl.name)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": alg, "kernel_ms": t_dom,
                 "kernels_ms": {"project": t_proj, "score": t_score, "step": t_step},
+                "pipes_pct_of_peak": pipes,
                 "note": "bit-packed masks make the pass ALU-bound (fp32 splat / AND+POPC), not HBM-bound; "
                         "achieved = SURVEY 8d algorithmic bytes / dominant-kernel time"}
     del inp, ws

@@ -190,3 +190,26 @@ def test_linregress_inner_function_equals_scipy():
             a = sp(range(n), torch.from_numpy(y))
             b = opt_utils.linregress(range(n), torch.from_numpy(y))
             assert (a.rvalue == b.rvalue) or (np.isnan(a.rvalue) and np.isnan(b.rvalue))
+
+
+def test_fast_rvalue_is_bit_equal_to_scipy():
+    """opt_utils._rvalue replaces scipy.stats.linregress(range(n), y).rvalue in the model selection:
+    same float64 bits on random, near-linear, constant (NaN) and grid-valued angle lists."""
+    from scipy.stats import linregress as sp
+    rng = np.random.RandomState(1)
+    grid = np.arange(-np.pi / 2, np.pi, np.pi / 30).astype(np.float32)
+    for trial in range(400):
+        n = int(rng.randint(1, 90))
+        kind = trial % 4
+        if kind == 0:
+            y = rng.randn(n).astype(np.float32)
+        elif kind == 1:
+            y = (np.arange(n) * 0.1047 + rng.randn(n) * 0.05).astype(np.float32)
+        elif kind == 2:
+            y = np.full(n, rng.randn(), np.float32)
+        else:
+            y = rng.choice(grid, n)
+        with np.errstate(all="ignore"):
+            a = np.float64(sp(range(n), torch.from_numpy(y)).rvalue)
+            b = np.float64(opt_utils._rvalue(y))
+        assert (np.isnan(a) and np.isnan(b)) or a.tobytes() == b.tobytes(), (n, kind, a, b)

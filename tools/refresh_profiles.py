@@ -30,20 +30,50 @@ def dram_bytes(rep):
     return b("dram__bytes_read.sum") + b("dram__bytes_write.sum")
 
 
-traffic = {}
+PIPE_KEYS = {
+    "issue_active": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "alu": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "fma": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "xu": "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "lsu": "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "tensor": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "dram": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex": "l1tex__throughput.avg.pct_of_peak_sustained_active",
+}
+
+
+def pipe_pcts(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    d = dict(zip(rows[0], rows[2]))
+    out = {}
+    for k, m in PIPE_KEYS.items():
+        if m in d and d[m] not in ("", "n/a"):
+            out[k] = round(float(d[m].replace(",", "")), 2)
+    return out
+
+
+traffic, pipes = {}, {}
 for f in sorted(os.listdir(G)):
     m = re.match(r"prof_(c2|c3_mini|c3_shard)_(k_[a-z_]+)\.ncu-rep$", f)
     if not m:
         continue
     wl, k = m.groups()
     ncu_summary.main(os.path.join(G, f), os.path.join(P, f"{tag}_{wl}_{k}.txt"))
-    if k in ("k_project", "k_score"):
+    if k in ("k_project", "k_score", "k_score_mma"):
         traffic.setdefault(wl, {})[k] = dram_bytes(os.path.join(G, f))
+        pipes.setdefault(wl, {})[k] = pipe_pcts(os.path.join(G, f))
 if traffic:
     traffic["_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none "
                           f"(profiles/{tag}_<workload>_<kernel>.txt)")
     with open(os.path.join(P, "traffic.json"), "w") as f:
         json.dump(traffic, f, indent=1)
+
+if pipes:
+    pipes["_source"] = ("ncu --set full --clock-control none, per kernel: % of peak of the issue slots and of each "
+                        f"instruction pipe (profiles/{tag}_<workload>_<kernel>.txt)")
+    with open(os.path.join(P, "pipes.json"), "w") as f:
+        json.dump(pipes, f, indent=1)
 
 lp = os.path.join(G, "launches_bench_c2.csv")
 if os.path.exists(lp):

@@ -1,4 +1,4 @@
-"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel once, both
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel once, all three
 scoring kernels, odd resolution, RLE ingest, override_depth.
     compute-sanitizer --tool racecheck python tools/sanitize.py"""
 import os
@@ -13,7 +13,7 @@ from articulation3d_b200 import OptConfig, adapter, engine, opt_utils, rle, synt
 
 cfg = OptConfig.scaled(200, 150)
 preds, _ = synth.make_video(5, 2, 12, cfg, kinds=[0, 1])
-for kernel in ("ldg", "tma"):
+for kernel in ("ldg", "tma", "mma"):
     os.environ["A3D_SCORE_KERNEL"] = kernel
     p = synth.clone_preds(preds)
     random.seed(1)
