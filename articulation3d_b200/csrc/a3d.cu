@@ -360,9 +360,8 @@ __device__ __forceinline__ void splat_points(const float (&X)[kProjPX], const fl
         if (kMode == A3D_MODE_TRANSLATE) {
             sx = __fadd_rn(px, t0); sy = __fadd_rn(py, t1); sz = __fadd_rn(pz, t2);
         } else {
-            if (kMode == A3D_MODE_SEQ) {
-                px = __fsub_rn(px, ax); py = __fsub_rn(py, ay); pz = __fsub_rn(pz, az);
-            }
+            // SEQ: the caller has already moved the points into the pivot's frame (p - pivot does not
+            // depend on the candidate)
             sx = __fadd_rn(__fadd_rn(__fmul_rn(px, R00), __fmul_rn(py, R10)), __fmul_rn(pz, R20));
             sy = __fadd_rn(__fadd_rn(__fmul_rn(px, R01), __fmul_rn(py, R11)), __fmul_rn(pz, R21));
             sz = __fadd_rn(__fadd_rn(__fmul_rn(px, R02), __fmul_rn(py, R12)), __fmul_rn(pz, R22));
@@ -410,6 +409,12 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
         Y[0] = c.x; Y[1] = c.y; Y[2] = c.z; Y[3] = c.w; Y[4] = d.x; Y[5] = d.y; Y[6] = d.z; Y[7] = d.w;
         const float4 e = __ldg(Z4 + 2 * item), g = __ldg(Z4 + 2 * item + 1);
         Z[0] = e.x; Z[1] = e.y; Z[2] = e.z; Z[3] = e.w; Z[4] = g.x; Z[5] = g.y; Z[6] = g.z; Z[7] = g.w;
+        if (kMode == A3D_MODE_SEQ) {           // first step of the three-step transform, once per point
+#pragma unroll
+            for (int k = 0; k < kProjPX; ++k) {
+                X[k] = __fsub_rn(X[k], ax); Y[k] = __fsub_rn(Y[k], ay); Z[k] = __fsub_rn(Z[k], az);
+            }
+        }
     };
     // full rounds: every thread owns one 8-point item and applies all candidates of the tile to it
     const int nfull = (nitems / kProjThreads) * kProjThreads;

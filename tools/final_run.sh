@@ -1,0 +1,24 @@
+#!/bin/bash
+# Round-end validation + profile capture on one B200 (run under gpurun from the repo root):
+#   gpurun --timeout 1500 -- 'bash tools/final_run.sh'
+# then, back in the build container:  python tools/refresh_profiles.py
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.txt
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.txt
+timeout 400 python bench.py > gpurun_out/bench_default.txt 2> gpurun_out/bench_default.err; echo "bench rc=$?"
+timeout 400 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.txt 2> gpurun_out/bench_reference.err; echo "ref rc=$?"
+for wl in c2 c3_shard; do
+  for k in k_unproject k_project k_score k_finalize; do
+    A3D_SCORE_KERNEL=ldg timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f \
+      -o gpurun_out/prof_${wl}_${k} python tools/profile_pass.py --workload $wl --passes 3 > gpurun_out/ncu_${wl}_${k}.log 2>&1
+  done
+done
+A3D_SCORE_KERNEL=mma timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_score_mma -s 1 -c 1 -f \
+  -o gpurun_out/prof_c3_shard_k_score_mma python tools/profile_pass.py --workload c3_shard --passes 3 > gpurun_out/ncu_c3_shard_k_score_mma.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 600 --csv --log-file gpurun_out/launches_bench_c2.csv \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-batched > gpurun_out/launches_bench_c2.log 2>&1
+timeout 300 compute-sanitizer --tool memcheck python tools/sanitize.py > gpurun_out/sanitizer_memcheck.txt 2>&1
+timeout 400 compute-sanitizer --tool racecheck python tools/sanitize.py > gpurun_out/sanitizer_racecheck.txt 2>&1
+tail -2 gpurun_out/sanitizer_memcheck.txt gpurun_out/sanitizer_racecheck.txt
+timeout 200 python tools/score_ab.py c3_shard ldg mma tma > gpurun_out/score_ab_c3_shard.txt 2>&1; tail -3 gpurun_out/score_ab_c3_shard.txt
