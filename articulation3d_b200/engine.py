@@ -10,6 +10,7 @@ only; all arithmetic is in csrc/a3d.cu behind the C ABI of include/a3d.h.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -316,6 +317,19 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
         cam = _camera_cached(cfg)
         stream = _stream_ptr()
         tile = tile_cand if tile_cand is not None else choose_tile(cfg, nc, dbatch.n_jobs)
+        if os.environ.get("A3D_PASS_API") != "split":
+            # one call: keys cleared first, then the four kernels as programmatic dependent launches
+            _lib.check(lib.a3d_pass(C.byref(cam), dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_tgt, dbatch.max_cand,
+                                    tile, nt, len(pool), nc, pool.bits.data_ptr(), pool.popc.data_ptr(),
+                                    pool.bbox.data_ptr(), pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(),
+                                    dbatch.xform.data_ptr(), dbatch.tgt_index.data_ptr(), pcd_ws.data_ptr(),
+                                    pcd_count.data_ptr(), proj_bits.data_ptr(), proj_popc.data_ptr(),
+                                    proj_bbox.data_ptr(), key_ws.data_ptr(),
+                                    inter_tab.data_ptr() if inter_tab is not None else None,
+                                    best_cand.data_ptr(), best_inter.data_ptr(), best_union.data_ptr(),
+                                    best_iou.data_ptr(), stream), "a3d_pass")
+            return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab,
+                              results)
         _lib.check(lib.a3d_project(C.byref(cam), dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_cand, tile,
                                    pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(),
                                    dbatch.xform.data_ptr(), pcd_ws.data_ptr(), pcd_count.data_ptr(),

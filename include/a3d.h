@@ -143,6 +143,21 @@ int a3d_score(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int 
               int32_t* best_cand, int32_t* best_inter, int32_t* best_union, float* best_iou,
               void* stream);
 
+/* One whole pass = a3d_project followed by a3d_score on the same stream, as one call: the arg-max keys
+ * are cleared first, so k_project, the scoring kernel and k_finalize run as programmatic dependent
+ * launches of their predecessors (their launch latency and prologue overlap the predecessor's tail).
+ * Same results as the two calls.  pool_* = target pool; src_bits/src_bbox = source pool
+ * (NULL: the target pool is also the source pool).                                              */
+int a3d_pass(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_tgt, int max_cand,
+             int tile_cand, int64_t n_tgt_total, int64_t n_pool_masks, int64_t n_cand_total,
+             const uint32_t* pool_bits, const int32_t* pool_popc, const int32_t* pool_bbox,
+             const uint32_t* src_bits, const int32_t* src_bbox, const float* xform, const int32_t* tgt_index,
+             float* pcd_ws, int32_t* pcd_count,
+             uint32_t* proj_bits, int32_t* proj_popc, int32_t* proj_bbox,
+             uint64_t* key_ws, int32_t* inter_tab,
+             int32_t* best_cand, int32_t* best_inter, int32_t* best_union, float* best_iou,
+             void* stream);
+
 /* (a11) materialise selected packed masks as dense images: out[i] =
  * unpack(bits[index[i]]) as A3D_F32 (0.0/1.0) or A3D_U8 (0/1).  Replaces
  * `proj_masks[angle_id].cpu()` of opt_utils.py:614, 906 (index may be NULL =

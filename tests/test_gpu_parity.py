@@ -551,3 +551,25 @@ def test_mma_kernel_tiles_targets_and_candidates(key, monkeypatch):
         assert np.array_equal(res.best_inter[t0:t0 + T].cpu().numpy(), inter[np.arange(T), best])
         assert np.array_equal(res.best_union[t0:t0 + T].cpu().numpy(), uni[np.arange(T), best])
         assert np.array_equal(res.best_iou[t0:t0 + T].cpu().numpy(), iou, equal_nan=True)
+
+
+@pytest.mark.parametrize("pdl", ["0", "1"])
+def test_single_call_pass_equals_project_then_score(pdl, monkeypatch):
+    """a3d_pass (keys cleared first, optionally programmatic dependent launches) must give exactly what
+    a3d_project followed by a3d_score gives, including the full intersection table."""
+    from articulation3d_b200 import workloads
+    wl = workloads.Workload("pass_probe", "3 videos x 4 tracks x 24 frames, 45 candidates", 3, 4, 24, 45)
+    inp = workloads.build_pass(wl, 5, DEV)
+    monkeypatch.setenv("A3D_PASS_API", "split")
+    a = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, want_table=True)
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (a.best_cand, a.best_inter, a.best_union, a.best_iou.view(torch.int32), a.inter_tab,
+                                a.proj_popc, a.proj_bbox)]
+    monkeypatch.delenv("A3D_PASS_API")
+    monkeypatch.setenv("A3D_PDL", pdl)
+    for _ in range(3):                                   # back to back: dependent launches across passes
+        b = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, want_table=True)
+    torch.cuda.synchronize()
+    got = [b.best_cand, b.best_inter, b.best_union, b.best_iou.view(torch.int32), b.inter_tab, b.proj_popc, b.proj_bbox]
+    for w, g in zip(want, got):
+        assert torch.equal(w, g)
