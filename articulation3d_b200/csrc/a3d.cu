@@ -555,8 +555,8 @@ constexpr int kScoreTT = 8;    // targets per CTA
 // so a load address is base + 32-bit word offset (one IMAD.WIDE) instead of a 64-bit pointer per mask —
 // without it half of the loop's instructions were address arithmetic.
 // kWC: candidates per warp (warp tile = 4 targets x kWC candidates; CTA = 8 targets x 4*kWC candidates).
-template <bool kNarrow, int kWC>
-__global__ void __launch_bounds__(256, kWC == 4 ? 3 : 4)
+template <bool kNarrow, int kWC, bool kPipe>
+__global__ void __launch_bounds__(256, (kWC == 4 || kPipe) ? 3 : 4)
 k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int ct_tiles,
         const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
         const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
@@ -620,33 +620,57 @@ k_score(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int 
         const int dr = 64 / ncols, dc = 64 - dr * ncols;
         int rA = lane / ncols, cA = lane - rA * ncols;
         int rB = (lane + 32) / ncols, cB = (lane + 32) - rB * ncols;
-        for (int idx = lane; idx < total; idx += 64) {
+        struct Step { uint32_t tA[4], tB[4], pA[kWC], pB[kWC]; };
+        auto load = [&](int idx, Step& w) {                       // the loads of step idx, and advance the cursor
             const unsigned oA = (unsigned)((ra + rA) * pitch + ca + cA);
             const bool hasB = idx + 32 < total;
             const unsigned oB = hasB ? (unsigned)((ra + rB) * pitch + ca + cB) : oA;
-            uint32_t tA[4], tB[4], pA[kWC], pB[kWC];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                tA[i] = kNarrow ? __ldg(tgt_bits + (toff[i] + oA)) : __ldg(tp[i] + oA);
-                tB[i] = kNarrow ? __ldg(tgt_bits + (toff[i] + oB)) : __ldg(tp[i] + oB);
+                w.tA[i] = kNarrow ? __ldg(tgt_bits + (toff[i] + oA)) : __ldg(tp[i] + oA);
+                w.tB[i] = kNarrow ? __ldg(tgt_bits + (toff[i] + oB)) : __ldg(tp[i] + oB);
             }
 #pragma unroll
             for (int k = 0; k < kWC; ++k) {
-                pA[k] = kNarrow ? __ldg(proj_bits + (poff[k] + oA)) : __ldg(pp[k] + oA);
-                pB[k] = kNarrow ? __ldg(proj_bits + (poff[k] + oB)) : __ldg(pp[k] + oB);
+                w.pA[k] = kNarrow ? __ldg(proj_bits + (poff[k] + oA)) : __ldg(pp[k] + oA);
+                w.pB[k] = kNarrow ? __ldg(proj_bits + (poff[k] + oB)) : __ldg(pp[k] + oB);
             }
             if (!hasB) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) tB[i] = 0u;
+                for (int i = 0; i < 4; ++i) w.tB[i] = 0u;
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k < kWC; ++k) csa_step(tA[i] & pA[k], tB[i] & pB[k], ones[i][k], acc2[i][k]);
             rA += dr; cA += dc;
             if (cA >= ncols) { cA -= ncols; ++rA; }
             rB += dr; cB += dc;
             if (cB >= ncols) { cB -= ncols; ++rB; }
+        };
+        auto fold = [&](const Step& w) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < kWC; ++k) csa_step(w.tA[i] & w.pA[k], w.tB[i] & w.pB[k], ones[i][k], acc2[i][k]);
+        };
+        if (kPipe) {
+            // small grids are bound by the chain of load latencies of a warp's few steps (C2: ~7 steps, every
+            // first touch a DRAM miss): the next step's loads are in flight while this one is folded
+            Step a, b;
+            int idx = lane;
+            if (idx < total) load(idx, a);
+            while (idx < total) {
+                if (idx + 64 < total) load(idx + 64, b);
+                fold(a);
+                idx += 64;
+                if (idx >= total) break;
+                if (idx + 64 < total) load(idx + 64, a);
+                fold(b);
+                idx += 64;
+            }
+        } else {
+            for (int idx = lane; idx < total; idx += 64) {
+                Step w;
+                load(idx, w);
+                fold(w);
+            }
         }
     }
     int acc[4][kWC];
@@ -1743,7 +1767,7 @@ static int score_impl(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_t
         const bool narrow = (unsigned long long)n_pool_masks * words < (1ull << 32) &&
                             (unsigned long long)n_cand_total * words < (1ull << 32);
 #define A3D_LAUNCH_SCORE(N, WC)                                                                                    \
-    A3D_CUDA_TRY(launch(k_score<N, WC>, dim3((unsigned)nblocks), dim3(256), 0, s, pdl, jobs, H, pitch, tt_tiles,    \
+    A3D_CUDA_TRY(launch(k_score<N, WC, WC == 2>, dim3((unsigned)nblocks), dim3(256), 0, s, pdl, jobs, H, pitch, tt_tiles, \
                         ct_tiles, tgt_bits, tgt_popc, tgt_bbox, tgt_index, proj_bits, proj_popc, proj_bbox,         \
                         (unsigned long long*)key_ws, inter_tab, packed))
         if (narrow && wc == 4) A3D_LAUNCH_SCORE(true, 4);
