@@ -208,7 +208,7 @@ def measure_pass(wl, steps, warmup, dev, rank, world, dist, sample_clocks=True):
         if evs:
             evs[0].record()
         res = _run_split(engine, inp, ws, evs) if split else engine.run_pass(inp.cfg, inp.pool, inp.dbatch, ws)
-        if world > 1:
+        if world > 1 and not split:
             b = step_no[0] & 1
             if comm_done[b] is not None:
                 torch.cuda.current_stream().wait_event(comm_done[b])     # buffer b free again
