@@ -193,7 +193,7 @@ def measure_pass(wl, steps, warmup, dev, rank, world, dist, sample_clocks=True):
     # multi-GPU: the only exchange of the path is the gather of fixed-size per-track-frame
     # records {angle_id, inter, union}.  It runs on a side stream, double-buffered, so the
     # collective of step k overlaps the kernels of step k+1.
-    recs = [torch.zeros(inp.dbatch.n_tgt_total, 3, dtype=torch.int32, device=dev) for _ in range(2)]
+    recs = [torch.zeros(3, inp.dbatch.n_tgt_total, dtype=torch.int32, device=dev) for _ in range(2)]
     gathered = [[torch.zeros_like(recs[0]) for _ in range(world)] for _ in range(2)] if world > 1 else None
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     comm_done = [None, None]
@@ -213,7 +213,10 @@ def measure_pass(wl, steps, warmup, dev, rank, world, dist, sample_clocks=True):
             if comm_done[b] is not None:
                 torch.cuda.current_stream().wait_event(comm_done[b])     # buffer b free again
             rec = recs[b]
-            rec[:, 0], rec[:, 1], rec[:, 2] = res.best_cand, res.best_inter, res.best_union
+            if res.block is not None:
+                rec.copy_(res.block[:3])                  # one copy: the rows are contiguous in the result block
+            else:
+                rec[0], rec[1], rec[2] = res.best_cand, res.best_inter, res.best_union
             ready = torch.cuda.Event()
             ready.record()
             with torch.cuda.stream(comm_stream):
