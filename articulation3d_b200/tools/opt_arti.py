@@ -34,6 +34,8 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=2020, help="per-video RNG seed base (tools/inference.py:172)")
     ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--save-obj", action="store_true")
+    ap.add_argument("--gt-json", default=None, help="COCO-style ground truth: print the AP table before / after "
+                    "optimisation (tools/opt_arti.py:275-283)")
     ap.add_argument("--synthetic", type=int, default=0, help="first write N synthetic videos to --input")
     ap.add_argument("--tracks", type=int, default=4)
     ap.add_argument("--frames", type=int, default=60)
@@ -65,6 +67,17 @@ def main(argv=None):
         if args.save_obj:
             for k in (0, len(preds) // 3, 2 * len(preds) // 3, len(preds) - 1):
                 io.write_obj(os.path.join(args.output, f"{vid}_frame{k}.obj"), out, planes, k, cfg)
+    if args.gt_json:
+        import json
+        from articulation3d_b200 import evaluation
+        with open(args.gt_json) as f:
+            gt = evaluation.CocoGT(json.load(f))
+        before = [r for _, recs in order for r in io.opt_preds_to_records(
+            io.records_to_preds(recs, conf_threshold=args.conf_threshold, masks="rle"), recs)]
+        after = [r for (_, recs), out in zip(order, outs) for r in io.opt_preds_to_records(out, recs)]
+        for tag, records in (("before", before), ("after", after)):
+            res = evaluation.evaluate_for_arti_axis(records, gt, evaluation.Metadata(), 0.0)
+            print(f"AP {tag} optimisation: " + ", ".join(f"{k} {float(v):.4f}" for k, v in res.items()))
     n_tracks = sum(len(p["rot"]) + len(p["trans"]) for _, p in videos)
     print(f"{len(videos)} video(s), {n_tracks} track(s): {stats.units_visited} track-frame x candidate evaluations "
           f"in {dt * 1e3:.1f} ms ({stats.passes} device passes) -> {args.output}")

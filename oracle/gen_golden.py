@@ -173,6 +173,100 @@ def main_diag():
         print(f"wrote {path}: {len(res['axis_scores'])} axis pairs, fit {res['fit_scores']} -> {res['fit_scores_opt']}")
 
 
+def build_eval_case(seed: int, n_tracks: int, n_frames: int, kinds):
+    """Synthetic evaluation input: prediction records of a clip and a COCO-style ground truth with ONE
+    annotation per image (the reference's matching loop needs that), derived from the predictions by
+    seeded perturbations so that every criterion has hits and misses."""
+    from articulation3d_b200 import synth
+    from articulation3d_b200.axis import angle_offset_to_axis
+    rng = np.random.RandomState(seed)
+    preds, _ = synth.make_video(seed, n_tracks, n_frames, kinds=kinds)
+    records, anns, images = [], [], []
+    for t, p in enumerate(preds):
+        boxes = p.pred_boxes.tensor.numpy().astype(np.float64)
+        n = len(boxes)
+        scores = np.clip(0.95 - 0.1 * rng.rand(n) * (rng.rand(n) < 0.5), 0, 1)
+        inst = [{"image_id": t, "category_id": int(p.pred_classes[k]),
+                 "bbox": [boxes[k, 0], boxes[k, 1], boxes[k, 2] - boxes[k, 0], boxes[k, 3] - boxes[k, 1]],
+                 "score": float(scores[k])} for k in range(n)]
+        records.append({"image_id": t, "instances": inst, "pred_plane": p.pred_planes.clone(),
+                        "pred_rot_axis": p.pred_rot_axis.clone(), "pred_tran_axis": p.pred_tran_axis.clone()})
+        images.append({"id": t, "width": 640, "height": 480})
+        if n == 0 or rng.rand() < 0.15:
+            continue                                           # image without ground truth
+        k = int(rng.randint(n))
+        cls = int(p.pred_classes[k])
+        if rng.rand() < 0.1:
+            cls = 1 - cls                                      # wrong class
+        jit = rng.randn(4) * (3 if rng.rand() < 0.7 else 60)   # mostly IoU > 0.5, sometimes not
+        x0, y0, x1, y1 = boxes[k] + jit
+        centers = p.pred_boxes.get_centers()
+        rot_line = angle_offset_to_axis(p.pred_rot_axis[k:k + 1], centers[k:k + 1])[0].numpy().astype(np.float64)
+        tr = torch.cat((p.pred_tran_axis[k:k + 1], torch.zeros(1, 1)), 1)
+        tran_line = angle_offset_to_axis(tr, centers[k:k + 1])[0].numpy().astype(np.float64)
+        ajit = rng.randn(4) * (4 if rng.rand() < 0.6 else 150)
+        plane = p.pred_planes[k].numpy().astype(np.float64)
+        nrm = np.array([plane[0], -plane[2], plane[1]]) / max(np.linalg.norm(plane), 1e-9)   # camera frame
+        nrm = nrm + rng.randn(3) * (0.1 if rng.rand() < 0.6 else 1.0)
+        nrm /= np.linalg.norm(nrm)
+        ann = {"id": len(anns) + 1, "image_id": t, "category_id": cls + 1,
+               "bbox": [float(x0), float(y0), float(max(x1 - x0, 2.0)), float(max(y1 - y0, 2.0))],
+               "rot_axis": (rot_line + ajit).tolist() if cls == 0 and rng.rand() < 0.9 else None,
+               "tran_axis": (tran_line + ajit).tolist() if cls == 1 and rng.rand() < 0.9 else None,
+               "normal": [float(nrm[0]), float(-nrm[1]), float(nrm[2])] if rng.rand() < 0.85 else None}
+        anns.append(ann)
+    gt = {"images": images, "annotations": anns,
+          "categories": [{"id": 1, "name": "arti_rot"}, {"id": 2, "name": "arti_tran"}]}
+    return records, gt
+
+
+def main_eval():
+    """tests/golden/eval/*.json: inputs + the reference's own evaluate_for_arti_axis / _recognition outputs."""
+    import importlib
+    import json
+    import types
+    if not ref_shim.available():
+        raise SystemExit("reference not present; fixtures can only be generated in the build container")
+    ref_shim.load_reference()
+    ev = importlib.import_module("articulation3d.evaluation.arti_evaluation")
+
+    class _Boxes(ref_shim.Boxes):
+        def to(self, device):
+            return self
+
+    class _BoxMode:                                            # [3P-unverified] detectron2 BoxMode.convert, XYWH -> XYXY
+        XYWH_ABS, XYXY_ABS = 1, 0
+
+        @staticmethod
+        def convert(box, from_mode, to_mode):
+            assert (from_mode, to_mode) == (_BoxMode.XYWH_ABS, _BoxMode.XYXY_ABS)
+            arr = np.array(box, dtype=np.float64).reshape(-1, 4)
+            arr[:, 2] += arr[:, 0]
+            arr[:, 3] += arr[:, 1]
+            return arr
+
+    ev.Boxes, ev.BoxMode, ev.pairwise_iou = _Boxes, _BoxMode, ref_shim.pairwise_iou
+    ev.create_small_table = lambda d: str(d)
+    from articulation3d_b200.evaluation import CocoGT
+    meta = types.SimpleNamespace(thing_classes=["arti_rot", "arti_tran"], thing_dataset_id_to_contiguous_id={1: 0, 2: 1})
+    os.makedirs(os.path.join(GOLDEN_DIR, "eval"), exist_ok=True)
+    for name, (seed, n_tracks, n_frames, kinds) in {"case_a": (31, 3, 40, [0, 1, 0]), "case_b": (32, 2, 60, [1, 0]),
+                                                    "case_c": (33, 4, 30, [0, 0, 1, 2])}.items():
+        records, gt = build_eval_case(seed, n_tracks, n_frames, kinds)
+        want = ev.evaluate_for_arti_axis(records, CocoGT(gt), meta, 0.0)
+        rec = ev.evaluate_for_recognition(records, CocoGT(gt), meta, 0.0)
+        out = {"records": [{"image_id": r["image_id"], "instances": r["instances"],
+                            "pred_plane": r["pred_plane"].tolist(), "pred_rot_axis": r["pred_rot_axis"].tolist(),
+                            "pred_tran_axis": r["pred_tran_axis"].tolist()} for r in records],
+               "gt": gt, "filter_iou": 0.0,
+               "arti_axis": {k: float(v) for k, v in want.items()},
+               "recognition": {k: float(v) for k, v in rec.items()}}
+        path = os.path.join(GOLDEN_DIR, "eval", f"{name}.json")
+        with open(path, "w") as f:
+            json.dump(out, f)
+        print(f"wrote {path} ({os.path.getsize(path) // 1024} KB):", out["arti_axis"], out["recognition"])
+
+
 def main():
     from articulation3d_b200 import synth
     if not ref_shim.available():
@@ -191,4 +285,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main_diag() if "--diag" in sys.argv else main()
+    main_diag() if "--diag" in sys.argv else (main_eval() if "--eval" in sys.argv else main())
