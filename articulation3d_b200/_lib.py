@@ -12,10 +12,13 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liba3d.so")
+# A3D_LIB: a differently built copy of the same library (debug counters, tools/filter_stats.py)
+LIB_PATH = os.environ.get("A3D_LIB") or os.path.join(_HERE, "csrc", "liba3d.so")
 
 A3D_F32, A3D_U8 = 0, 1
 MODE_SEQ, MODE_COMPOSED, MODE_TRANSLATE = 0, 1, 2
+PCD_PLANES = 5          # A3D_PCD_PLANES: floats of point-cloud workspace per point
+HOM_FLOATS = 12         # A3D_HOM_FLOATS: floats of homography workspace per candidate
 
 
 class Camera(C.Structure):
@@ -72,13 +75,13 @@ def load():
     lib.a3d_mask_meta.restype = C.c_int
     lib.a3d_mask_meta.argtypes = [vp, i64, i32, i32, vp, vp, vp]
     lib.a3d_project.restype = C.c_int
-    lib.a3d_project.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.a3d_project.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
     lib.a3d_score.restype = C.c_int
     lib.a3d_score.argtypes = [i32, i32, vp, i32, i32, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                               vp, vp, vp, vp, vp]
     lib.a3d_pass.restype = C.c_int
     lib.a3d_pass.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp,
-                             vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+                             vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.a3d_emit_masks.restype = C.c_int
     lib.a3d_emit_masks.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp]
     lib.a3d_rle_to_bits.restype = C.c_int

@@ -230,6 +230,91 @@ __global__ void __launch_bounds__(256) k_mask_meta(const uint32_t* __restrict__ 
     if (threadIdx.x == 0) stat_store(red, popc + m, bbox + 4 * m);
 }
 
+constexpr int kHF = 12;                              // floats per candidate: H (9, recentred), E_cand, exact-only flag, pad
+
+// fp64 set-up of one candidate's homography; m = its 12 floats (R row-major, t), (x0, y0) the centre the
+// source coordinates are taken from, (xm, ym) their largest magnitudes.
+__device__ __forceinline__ void make_homography(const Cam& cam, const a3d_job_t& job, const float* __restrict__ m, int x0, int y0,
+                                float xm, float ym, float* __restrict__ out) {
+    const double U = 5.9604644775390625e-8;          // 2^-24
+    double A[9], Aa[9], b[3], ba[3];
+    const double a[3] = {(double)job.pivot[0], (double)job.pivot[1], (double)job.pivot[2]};
+    double rho = 0.0;
+    bool bad = false;
+    if (job.mode == A3D_MODE_TRANSLATE) {
+        for (int i = 0; i < 9; ++i) { A[i] = (i % 4 == 0) ? 1.0 : 0.0; Aa[i] = A[i]; }
+    } else {
+        for (int i = 0; i < 9; ++i) { A[i] = (double)m[i]; Aa[i] = fabs(A[i]); rho = fmax(rho, Aa[i]); bad |= !(Aa[i] <= 1.001); }
+    }
+    for (int j = 0; j < 3; ++j) {
+        if (job.mode == A3D_MODE_SEQ) {
+            b[j] = a[j] - (a[0] * A[j] + a[1] * A[3 + j] + a[2] * A[6 + j]);
+            ba[j] = fabs(a[j]) + fabs(a[0]) * Aa[j] + fabs(a[1]) * Aa[3 + j] + fabs(a[2]) * Aa[6 + j];
+        } else {
+            b[j] = (double)m[9 + j];
+            ba[j] = fabs(b[j]);
+        }
+    }
+    const double n[3] = {(double)job.normal[0], (double)job.normal[1], (double)job.normal[2]};
+    const double off = (double)job.offset;
+    double G[9], Ga[9];                               // G[k][j] = off A[k][j] + n[k] b[j]
+    for (int k = 0; k < 3; ++k)
+        for (int j = 0; j < 3; ++j) {
+            G[3 * k + j] = off * A[3 * k + j] + n[k] * b[j];
+            Ga[3 * k + j] = fabs(off) * Aa[3 * k + j] + fabs(n[k]) * ba[j];
+        }
+    double L[9], La[9];                               // L[mm][j] = sum_k Kinv[k][mm] G[k][j]
+    for (int mm = 0; mm < 3; ++mm)
+        for (int j = 0; j < 3; ++j) {
+            double v = 0.0, va = 0.0;
+            for (int k = 0; k < 3; ++k) { v += cam.k[3 * k + mm] * G[3 * k + j]; va += fabs(cam.k[3 * k + mm]) * Ga[3 * k + j]; }
+            L[3 * mm + j] = v; La[3 * mm + j] = va;
+        }
+    const double f = (double)cam.f, cx = (double)cam.cx, cy = (double)cam.cy;
+    double H[9], Ha[9];                               // rows u, v, w; columns x, y, 1
+    for (int mm = 0; mm < 3; ++mm) {
+        H[mm] = f * L[3 * mm] + cx * L[3 * mm + 2];          Ha[mm] = f * La[3 * mm] + fabs(cx) * La[3 * mm + 2];
+        H[3 + mm] = f * L[3 * mm + 1] + cy * L[3 * mm + 2];  Ha[3 + mm] = f * La[3 * mm + 1] + fabs(cy) * La[3 * mm + 2];
+        H[6 + mm] = L[3 * mm + 2];                           Ha[6 + mm] = La[3 * mm + 2];
+    }
+    float Hf[9];
+    double mag[3], maga[3];
+    // rows u and v are stored divided by (W-1) and (H-1): the kernel clamps u/w with a saturating FMA
+    const double scale[3] = {(double)(cam.W - 1), (double)(cam.H - 1), 1.0};
+    bad |= cam.W < 2 || cam.H < 2;
+    for (int r = 0; r < 3; ++r) {                     // recentre on (x0, y0)
+        H[3 * r + 2] += H[3 * r] * (double)x0 + H[3 * r + 1] * (double)y0;
+        Ha[3 * r + 2] += Ha[3 * r] * fabs((double)x0) + Ha[3 * r + 1] * fabs((double)y0);
+        for (int i = 0; i < 3; ++i) {
+            Hf[3 * r + i] = (float)(H[3 * r + i] / scale[r]);
+            bad |= !(fabsf(Hf[3 * r + i]) <= 3.0e38f);
+        }
+        mag[r] = scale[r] * (fabs((double)Hf[3 * r]) * xm + fabs((double)Hf[3 * r + 1]) * ym + fabs((double)Hf[3 * r + 2]));
+        maga[r] = Ha[3 * r] * xm + Ha[3 * r + 1] * ym + Ha[3 * r + 2];
+    }
+    const double Dm1 = (double)max(cam.W, cam.H) + 1.0;
+    const double ec = 1.25 * (3.0 * U * (fmax(mag[0], mag[1]) + Dm1 * mag[2]) +
+                              9.094947017729282e-13 * (fmax(maga[0], maga[1]) + Dm1 * maga[2]));      // 2^-40
+    float ecf = __double2float_ru(ec * 1.000001);
+    bad |= !(ecf <= 3.0e38f);
+    // a candidate that maps the corners of the source box onto themselves in x or in y (rotation by 0,
+    // translation along an image axis) leaves that coordinate of EVERY point on an integer boundary:
+    // the whole candidate takes the exact chain
+    bool fix_x = true, fix_y = true;
+    for (int cxs = -1; cxs <= 1; cxs += 2)
+        for (int cys = -1; cys <= 1; cys += 2) {
+            const double xx = cxs * (double)xm, yy = cys * (double)ym;
+            const double w = H[6] * xx + H[7] * yy + H[8];                // |u - x w| < 0.02 |w|: no division
+            fix_x &= fabs(H[0] * xx + H[1] * yy + H[2] - (xx + x0) * w) < 0.02 * fabs(w);
+            fix_y &= fabs(H[3] * xx + H[4] * yy + H[5] - (yy + y0) * w) < 0.02 * fabs(w);
+        }
+    bad |= fix_x | fix_y;
+    for (int i = 0; i < 9; ++i) out[i] = Hf[i];
+    out[9] = ecf;
+    out[10] = bad ? 1.f : 0.f;
+    out[11] = 0.f;
+}
+
 // ---------------------------------------------------------------------------
 // unproject: source mask -> compacted fp32 point cloud (get_pcd, vis.py:86-102).
 // One CTA per job.  Phase 1: exclusive prefix of the per-word popcounts of the
@@ -243,12 +328,15 @@ constexpr int kUnprojThreads = 256;
 template <bool kSparseK>
 __global__ void __launch_bounds__(kUnprojThreads)
 k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* __restrict__ src_bits,
-            const int32_t* __restrict__ src_bbox, float* __restrict__ pcd, int32_t* __restrict__ pcd_count) {
+            const int32_t* __restrict__ src_bbox, const float* __restrict__ xform, float* __restrict__ pcd,
+            int32_t* __restrict__ pcd_count, float* __restrict__ hom) {
     extern __shared__ uint32_t prefix[];            // one entry per word of the source box
     __shared__ uint32_t warp_sum[kUnprojThreads / 32];
     __shared__ uint32_t total_s;
+    __shared__ int tmax_s;
     pdl_launch_dependents();
     const a3d_job_t job = jobs[blockIdx.x];
+    if (threadIdx.x == 0) tmax_s = 0;
     const int pitch = cam.pitch;
     const int32_t* sb = src_bbox + 4 * (size_t)job.src_mask;
     const int r0 = sb[0], r1 = sb[1], w0 = sb[2], w1 = sb[3];
@@ -259,6 +347,19 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
     const uint32_t* src = src_bits + (size_t)job.src_mask * cam.H * pitch;
     const int ncols = w1 - w0 + 1, nwords = (r1 - r0 + 1) * ncols;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // homographies of the job's candidates for the filtered projection, one candidate per thread; source
+    // coordinates are taken from the centre of the source box (smaller terms, tighter bound)
+    if (hom) {
+        const int y0 = (r0 + r1) >> 1, x0 = 16 * (w0 + w1 + 1);
+        for (int c = blockIdx.y * kUnprojThreads + threadIdx.x; c < job.n_cand; c += kUnprojThreads * gridDim.y) {
+            const size_t g = (size_t)job.cand_begin + c;
+            float m[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) m[i] = xform[g * 12 + i];
+            make_homography(cam, job, m, x0, y0, (float)(16 * (w1 - w0 + 1)), (float)(r1 - y0), hom + g * kHF);
+        }
+    }
 
     // phase 1: block-wide exclusive scan, each thread owns a contiguous chunk of words
     const int chunk = (nwords + kUnprojThreads - 1) / kUnprojThreads;
@@ -288,12 +389,33 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
 
     // phase 2
     const int cap = job.pcd_cap;
-    float* Xp = pcd + 3 * job.pcd_begin;
+    float* Xp = pcd + (size_t)A3D_PCD_PLANES * job.pcd_begin;
     float* Yp = Xp + cap;
     float* Zp = Yp + cap;
+    uint32_t* XYp = reinterpret_cast<uint32_t*>(Zp + cap);      // (row << 16) | column of the source pixel
+    float* Cp = Zp + 2 * (size_t)cap;                           // error-bound coefficient of the point (k_project filter)
     const double n0 = (double)job.normal[0], n1 = (double)job.normal[1], n2 = (double)job.normal[2];
     const double off = (double)job.offset;
     const float NaNf = __int_as_float(0x7fffffff);
+    const float INFf = __int_as_float(0x7f800000);
+    // filter constants (see "filtered projection" above k_project): the largest |t| over the job's candidates
+    // enters the bound of the COMPOSED / TRANSLATE chains, the pivot that of the SEQ chain
+    if (job.mode != A3D_MODE_SEQ) {
+        int m = 0;
+        for (int i = threadIdx.x; i < job.n_cand * 3; i += kUnprojThreads) {
+            float v = fabsf(xform[(size_t)(job.cand_begin + i / 3) * 12 + 9 + (i % 3)]);
+            if (!(v <= 3.402823466e38f)) v = INFf;               // NaN counts as unbounded
+            m = max(m, __float_as_int(v));
+        }
+        m = __reduce_max_sync(0xffffffffu, m);
+        if (lane == 0 && m) atomicMax(&tmax_s, m);
+    }
+    __syncthreads();
+    const double tmax = (double)__int_as_float(tmax_s);
+    const double a0 = (double)job.pivot[0], a1 = (double)job.pivot[1], a2 = (double)job.pivot[2];
+    const double amax = fmax(fabs(a0), fmax(fabs(a1), fabs(a2)));
+    const double K1 = (double)cam.f + fmax(fabs((double)cam.cx), fabs((double)cam.cy));
+    const double Dm = (double)max(cam.W, cam.H);
     // the words of the box are dealt round-robin to the warps of the gridDim.y CTAs of this job
     const int wstride = (kUnprojThreads / 32) * gridDim.y;
     for (int w = blockIdx.y * (kUnprojThreads / 32) + warp; w < nwords; w += wstride) {
@@ -321,10 +443,29 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
         float z = __double2float_rn(__dmul_rn(depth, rz));
         // a point with any non-finite coordinate leaves the first homogeneous transform
         // all-NaN (every output mixes 0*coordinate terms)
-        if (!(fabsf(x) <= 3.402823466e38f && fabsf(y) <= 3.402823466e38f && fabsf(z) <= 3.402823466e38f)) {
+        const bool finite = fabsf(x) <= 3.402823466e38f && fabsf(y) <= 3.402823466e38f && fabsf(z) <= 3.402823466e38f;
+        if (!finite) {
             x = NaNf; y = NaNf; z = NaNf;
         }
         Xp[pos] = x; Yp[pos] = y; Zp[pos] = z;
+        // coefficient C of the point: |q_exact - q_true| <= C * |1/W_h| + c0 for every candidate, W_h the
+        // homogeneous w of the plane-induced homography (scaled by n.ray, hence the |dot| factor)
+        const double p1 = fabs((double)x) + fabs((double)y) + fabs((double)z);
+        double Sig, M;
+        if (job.mode == A3D_MODE_SEQ) {
+            const double pp1 = fabs((double)x - a0) + fabs((double)y - a1) + fabs((double)z - a2);
+            Sig = 1.001 * (1.01 * p1 + 5.0 * pp1) + amax;
+            M = 1.001 * pp1 + amax;
+        } else {
+            Sig = 1.001 * 5.01 * p1 + tmax;
+            M = 1.001 * p1 + tmax;
+        }
+        const double coef = 5.9604644775390625e-8 * 1.25 * fabs(dot) * (K1 * (Sig + 2.0 * M) + Dm * Sig);
+        float cf = __double2float_ru(coef * 1.000001);
+        const double dmag = fabs(n0 * rx) + fabs(n1 * ry) + fabs(n2 * rz);
+        if (!finite || !(fabs(dot) >= 1e-6 * dmag) || !(cf <= 3.402823466e38f)) cf = INFf;
+        XYp[pos] = ((uint32_t)row << 16) | (uint32_t)(wc * 32 + lane);
+        Cp[pos] = cf;
     }
     if (threadIdx.x == 0 && blockIdx.y == 0) pcd_count[blockIdx.x] = min((int)total_s, cap);
 }
@@ -349,54 +490,82 @@ __device__ __forceinline__ int clamp_index(float v, float n_minus_1) {
 constexpr int kProjThreads = 1024;
 constexpr int kProjPX = 8;
 
-// One candidate applied to up to 8 points held in registers; kMode is a compile-time
-// constant so the per-point code is straight-line.
+// The reference's fp32 chain for one point and one candidate (kMode is a compile-time constant so the
+// code is straight-line): transform, project2D, `.long()`, clamp.  For SEQ the point is already in the
+// pivot's frame (p - pivot does not depend on the candidate).
+template <int kMode>
+__device__ __forceinline__ void exact_pixel(float px, float py, float pz, const float* __restrict__ m,
+                                            float ax, float ay, float az, float f, float cx, float cy,
+                                            float wmax, float hmax, int& col, int& rw) {
+    float sx, sy, sz;
+    if (kMode == A3D_MODE_TRANSLATE) {
+        sx = __fadd_rn(px, m[9]); sy = __fadd_rn(py, m[10]); sz = __fadd_rn(pz, m[11]);
+    } else {
+        sx = __fadd_rn(__fadd_rn(__fmul_rn(px, m[0]), __fmul_rn(py, m[3])), __fmul_rn(pz, m[6]));
+        sy = __fadd_rn(__fadd_rn(__fmul_rn(px, m[1]), __fmul_rn(py, m[4])), __fmul_rn(pz, m[7]));
+        sz = __fadd_rn(__fadd_rn(__fmul_rn(px, m[2]), __fmul_rn(py, m[5])), __fmul_rn(pz, m[8]));
+        if (kMode == A3D_MODE_SEQ) {
+            sx = __fadd_rn(sx, ax); sy = __fadd_rn(sy, ay); sz = __fadd_rn(sz, az);
+        } else {
+            sx = __fadd_rn(sx, m[9]); sy = __fadd_rn(sy, m[10]); sz = __fadd_rn(sz, m[11]);
+        }
+    }
+    // project2D (vis.py:72-75): K@p, then /w.  The 0*X, 0*Y terms only matter for
+    // non-finite inputs; keeping them in w reproduces those cases exactly.
+    const float u = __fadd_rn(__fmul_rn(f, sx), __fmul_rn(cx, sz));
+    const float v = __fadd_rn(__fmul_rn(f, sy), __fmul_rn(cy, sz));
+    const float w = __fadd_rn(__fmaf_rn(0.f, sx, __fmul_rn(0.f, sy)), sz);   // (0*X + 0*Y) is exactly 0 or NaN
+    col = clamp_index(__fdiv_rn(u, w), wmax);
+    rw = clamp_index(__fdiv_rn(v, w), hmax);
+}
+
+// Hits on the same destination word are merged in registers before one shared-memory atomic.  Words
+// are tracked by their 32-bit shared-memory byte address; the flush of the pending word is one
+// predicated RED (no branch).
+__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t bits) {
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
+}
+
+struct WordMerge {
+    uint32_t addr, bits;
+    __device__ __forceinline__ void first(uint32_t a, uint32_t bm) { addr = a; bits = bm; }
+    __device__ __forceinline__ void add(uint32_t a, uint32_t bm) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.u32 p, %2, %0;\n\t"
+            "@p red.shared.or.b32 [%0], %1;\n\t"
+            "@p mov.b32 %1, 0;\n\t}"
+            : "+r"(addr), "+r"(bits) : "r"(a) : "memory");
+        addr = a;
+        bits |= bm;
+    }
+    __device__ __forceinline__ void flush() { red_or_shared(addr, bits); }
+};
+
+// shared-memory byte address of pixel (rw, col)'s word in the mask at cm; pitch4 = bytes per packed row
+__device__ __forceinline__ uint32_t word_addr(uint32_t cm, int rw, int col, int pitch4) {
+    return cm + (uint32_t)(rw * pitch4) + (((uint32_t)col >> 5) << 2);
+}
+
+// One candidate applied to up to 8 points held in registers.
 template <int kMode, bool kFull>
 __device__ __forceinline__ void splat_points(const float (&X)[kProjPX], const float (&Y)[kProjPX],
                                              const float (&Z)[kProjPX], int nvalid, const float* __restrict__ m,
                                              float ax, float ay, float az, float f, float cx, float cy,
-                                             float wmax, float hmax, int pitch, uint32_t* __restrict__ cm) {
-    const float R00 = m[0], R01 = m[1], R02 = m[2], R10 = m[3], R11 = m[4], R12 = m[5];
-    const float R20 = m[6], R21 = m[7], R22 = m[8], t0 = m[9], t1 = m[10], t2 = m[11];
-    int cur_wi = -1;
-    uint32_t cur_bits = 0;
+                                             float wmax, float hmax, int pitch4, uint32_t cm) {
+    float mm[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) mm[i] = m[i];
+    WordMerge mg;
 #pragma unroll
     for (int k = 0; k < kProjPX; ++k) {
         if (!kFull && k >= nvalid) break;
-        float px = X[k], py = Y[k], pz = Z[k];
-        float sx, sy, sz;
-        if (kMode == A3D_MODE_TRANSLATE) {
-            sx = __fadd_rn(px, t0); sy = __fadd_rn(py, t1); sz = __fadd_rn(pz, t2);
-        } else {
-            // SEQ: the caller has already moved the points into the pivot's frame (p - pivot does not
-            // depend on the candidate)
-            sx = __fadd_rn(__fadd_rn(__fmul_rn(px, R00), __fmul_rn(py, R10)), __fmul_rn(pz, R20));
-            sy = __fadd_rn(__fadd_rn(__fmul_rn(px, R01), __fmul_rn(py, R11)), __fmul_rn(pz, R21));
-            sz = __fadd_rn(__fadd_rn(__fmul_rn(px, R02), __fmul_rn(py, R12)), __fmul_rn(pz, R22));
-            if (kMode == A3D_MODE_SEQ) {
-                sx = __fadd_rn(sx, ax); sy = __fadd_rn(sy, ay); sz = __fadd_rn(sz, az);
-            } else {
-                sx = __fadd_rn(sx, t0); sy = __fadd_rn(sy, t1); sz = __fadd_rn(sz, t2);
-            }
-        }
-        // project2D (vis.py:72-75): K@p, then /w.  The 0*X, 0*Y terms only matter for
-        // non-finite inputs; keeping them in w reproduces those cases exactly.
-        const float u = __fadd_rn(__fmul_rn(f, sx), __fmul_rn(cx, sz));
-        const float v = __fadd_rn(__fmul_rn(f, sy), __fmul_rn(cy, sz));
-        const float w = __fadd_rn(__fmaf_rn(0.f, sx, __fmul_rn(0.f, sy)), sz);   // (0*X + 0*Y) is exactly 0 or NaN
-        const int col = clamp_index(__fdiv_rn(u, w), wmax);
-        const int rw = clamp_index(__fdiv_rn(v, w), hmax);
-        const int wi = rw * pitch + (col >> 5);
-        const uint32_t bm = 1u << (col & 31);
-        if (wi != cur_wi) {
-            if (cur_bits) atomicOr(cm + cur_wi, cur_bits);
-            cur_wi = wi;
-            cur_bits = bm;
-        } else {
-            cur_bits |= bm;
-        }
+        int col, rw;
+        exact_pixel<kMode>(X[k], Y[k], Z[k], mm, ax, ay, az, f, cx, cy, wmax, hmax, col, rw);
+        const uint32_t wa = word_addr(cm, rw, col, pitch4), bm = 1u << (col & 31);
+        if (k == 0) mg.first(wa, bm); else mg.add(wa, bm);
     }
-    if (cur_bits) atomicOr(cm + cur_wi, cur_bits);
+    mg.flush();
 }
 
 template <int kMode>
@@ -404,11 +573,14 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
                                           const float* __restrict__ pcd, const float* __restrict__ xf,
                                           uint32_t* __restrict__ masks, int words) {
     const int cap = job.pcd_cap;
-    const float4* X4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin);
-    const float4* Y4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin + cap);
-    const float4* Z4 = reinterpret_cast<const float4*>(pcd + 3 * job.pcd_begin + 2 * (size_t)cap);
+    const float* base = pcd + (size_t)A3D_PCD_PLANES * job.pcd_begin;
+    const float4* X4 = reinterpret_cast<const float4*>(base);
+    const float4* Y4 = reinterpret_cast<const float4*>(base + cap);
+    const float4* Z4 = reinterpret_cast<const float4*>(base + 2 * (size_t)cap);
     const float ax = job.pivot[0], ay = job.pivot[1], az = job.pivot[2];
     const float wmax = (float)(cam.W - 1), hmax = (float)(cam.H - 1);
+    const uint32_t masks_s = (uint32_t)__cvta_generic_to_shared(masks);
+    const int pitch4 = cam.pitch * 4;
     const int nitems = (npts + kProjPX - 1) / kProjPX;
     auto load_item = [&](int item, float (&X)[kProjPX], float (&Y)[kProjPX], float (&Z)[kProjPX]) {
         const float4 a = __ldg(X4 + 2 * item), b = __ldg(X4 + 2 * item + 1);
@@ -431,7 +603,7 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
         load_item(item, X, Y, Z);
         for (int c = 0; c < nc; ++c)
             splat_points<kMode, true>(X, Y, Z, kProjPX, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
-                                      wmax, hmax, cam.pitch, masks + (size_t)c * words);
+                                      wmax, hmax, pitch4, masks_s + (uint32_t)(c * words) * 4u);
     }
     // last, partial round: its (item, candidate) pairs are dealt out one by one so that all
     // threads finish together (with ~1.5 items per thread the plain loop left half the warps
@@ -444,76 +616,336 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
         const int nvalid = npts - item * kProjPX;
         if (nvalid >= kProjPX)
             splat_points<kMode, true>(X, Y, Z, kProjPX, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
-                                      wmax, hmax, cam.pitch, masks + (size_t)c * words);
+                                      wmax, hmax, pitch4, masks_s + (uint32_t)(c * words) * 4u);
         else
             splat_points<kMode, false>(X, Y, Z, nvalid, xf + 12 * c, ax, ay, az, cam.f, cam.cx, cam.cy,
-                                       wmax, hmax, cam.pitch, masks + (size_t)c * words);
+                                       wmax, hmax, pitch4, masks_s + (uint32_t)(c * words) * 4u);
     }
 }
 
+// ---------------------------------------------------------------------------
+// Filtered projection (k_project<true>).  The reference chain costs ~80 instructions per (point,
+// candidate), two thirds of them to reproduce its fp32 roundings.  But the map source pixel -> projected
+// pixel of a plane under a rigid motion is a homography: with ray = Kinv [x y 1]^T, p = off ray / (n.ray),
+// s = p A + b and [u v w] = K s,
+//     (n.ray) [u v w]^T = H [x y 1]^T,   H = K (off A + n b^T)^T Kinv      (fp64, once per candidate)
+// so q = u/w costs 6 FMA + 1 MUFU.RCP + 2 FMA.  The integer pixel trunc(q) of the cheap value is USED ONLY
+// WHEN PROVEN equal to the reference's: a running error bound
+//     |q_ref - q_cheap| <= eps = (C_point + E_cand) |1/W_h| + c0
+// (C_point: roundings of the reference chain, written by k_unproject; E_cand: roundings of the fp32
+// homography evaluation; c0: division / reciprocal terms; derivation in DESIGN.md §4a) must leave the
+// cheap value more than eps away from every integer boundary.  Otherwise — 0.3 % of the coordinates on
+// the synthetic scenes, plus whole candidates that map pixels onto themselves (angle 0) — the thread
+// evaluates the exact chain for that point.  Results are bit-identical by construction; the tests compare
+// the two kernels bit for bit.
+// ---------------------------------------------------------------------------
+#ifdef A3D_FILTER_STATS
+// debug build only (tools/filter_stats.py): [0] (point, candidate) pairs, [1] pairs sent to the exact chain,
+// [2] of those, pairs of exact-only candidates, [3] warp-iterations of the exact loop
+__device__ unsigned long long g_filter_stats[4];
+#endif
+constexpr float kMagic = 12582912.f;                 // 1.5 * 2^23: x + kMagic holds rint(x) in its low mantissa bits
+// Phase A of one (item, candidate): the cheap pixel of up to 8 points; proven ones are splatted, the
+// others come back as a bit mask (bit k = point k needs the exact chain).
+// The integer-pipe instructions (min/max, select, logic, compares; half rate) bound this loop, so the work
+// sits on the FMA pipe wherever it can: u/w is clamped to [0, W-1] by a saturating FMA on rows pre-divided
+// by W-1; x + 1.5*2^23 leaves rint(x) in the low mantissa bits and the word address is computed from those
+// bits as they are (the constant part is folded into the base); every point issues its own RED, with an
+// all-zero operand when it is unproven.
+struct FilterConst {
+    float wmax, hmax, chx, chy, c0;                   // chx = -0.5 / wmax
+    int pitch4;
+};
+
+template <bool kFull>
+__device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjPX], const float (&ys)[kProjPX],
+                                                        const float C, int nvalid, const float* __restrict__ h,
+                                                        const FilterConst& fc, uint32_t cm) {
+    if (h[10] != 0.f) return 0u;                       // exact-only candidate: handled by the straight-line chain
+    const float h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3], h4 = h[4], h5 = h[5], h6 = h[6], h7 = h[7], h8 = h[8];
+    const float ce = __fadd_ru(C, h[9]);
+    // bits of (kMagic + n) = 0x4B400000 + n: fold the constant out of  row * pitch4 + (col >> 5) * 4
+    const uint32_t cmk = cm - 0x4B400000u * (uint32_t)fc.pitch4 - ((0x4B400000u >> 5) << 2);
+    uint32_t proven = 0;
+#pragma unroll
+    for (int k = 0; k < kProjPX; ++k) {
+        if (!kFull && k >= nvalid) break;
+        const float Uq = fmaf(h0, xs[k], fmaf(h1, ys[k], h2));
+        const float Vq = fmaf(h3, xs[k], fmaf(h4, ys[k], h5));
+        const float Wq = fmaf(h6, xs[k], fmaf(h7, ys[k], h8));
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(Wq));
+        float sx, sy;                                   // clamp((u/w - 0.5) / (W-1), 0, 1); NaN -> 0
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(sx) : "f"(Uq), "f"(r), "f"(fc.chx));
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(sy) : "f"(Vq), "f"(r), "f"(fc.chy));
+        const float tx = fmaf(sx, fc.wmax, kMagic), ty = fmaf(sy, fc.hmax, kMagic);
+        const float dx = fmaf(sx, fc.wmax, -__fsub_rn(tx, kMagic)), dy = fmaf(sy, fc.hmax, -__fsub_rn(ty, kMagic));
+        const float thr = __fsub_rn(0.5f, fmaf(ce, fabsf(r), fc.c0));
+        // proven only if both fractional parts keep more than eps from the integer boundaries (a NaN or
+        // infinite eps fails the comparison)
+        const uint32_t one = (fabsf(dx) <= thr && fabsf(dy) <= thr) ? 1u : 0u;
+        const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
+        red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
+        proven += one << k;
+    }
+    return ~proven & (kFull ? 0xffu : ((1u << nvalid) - 1u));
+}
+
+// Phase B: the exact chain for the (candidate, point) pairs of one item that phase A could not prove.
+// bit 8*(c - c_begin) + k of `todo`.
+template <int kMode>
+__device__ __forceinline__ void splat_exact_list(unsigned long long todo, int c_begin, const float* __restrict__ gX,
+                                                 int cap, const float* __restrict__ xf, float ax, float ay, float az,
+                                                 float f, float cx, float cy, float wmax, float hmax, int pitch4,
+                                                 uint32_t masks_s, int words4) {
+#ifdef A3D_FILTER_STATS
+    atomicAdd(&g_filter_stats[1], (unsigned long long)__popcll(todo));
+#endif
+    while (todo) {
+#ifdef A3D_FILTER_STATS
+        if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&g_filter_stats[3], 1ull);
+#endif
+        const int b = __ffsll((long long)todo) - 1;
+        todo &= todo - 1;
+        const int c = c_begin + (b >> 3), k = b & 7;
+        float px = __ldg(gX + k), py = __ldg(gX + cap + k), pz = __ldg(gX + 2 * (size_t)cap + k);
+        if (kMode == A3D_MODE_SEQ) { px = __fsub_rn(px, ax); py = __fsub_rn(py, ay); pz = __fsub_rn(pz, az); }
+        int col, rw;
+        exact_pixel<kMode>(px, py, pz, xf + 12 * c, ax, ay, az, f, cx, cy, wmax, hmax, col, rw);
+        red_or_shared(word_addr(masks_s + (uint32_t)c * (uint32_t)words4, rw, col, pitch4), 1u << (col & 31));
+    }
+}
+
+template <int kMode>
+__device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t& job, int npts, int nc,
+                                                 const float* __restrict__ pcd, const float* __restrict__ xf,
+                                                 const float* __restrict__ hf, int x0, int y0,
+                                                 uint32_t* __restrict__ masks, int words) {
+    const int cap = job.pcd_cap;
+    const float* base = pcd + (size_t)A3D_PCD_PLANES * job.pcd_begin;
+    const uint4* XY4 = reinterpret_cast<const uint4*>(base + 3 * (size_t)cap);
+    const float4* C4 = reinterpret_cast<const float4*>(base + 4 * (size_t)cap);
+    const float ax = job.pivot[0], ay = job.pivot[1], az = job.pivot[2];
+    const float wmax = (float)(cam.W - 1), hmax = (float)(cam.H - 1);
+    const float Dm = (float)max(cam.W, cam.H);
+    const int pitch4 = cam.pitch * 4, words4 = words * 4;
+    FilterConst fc;
+    fc.wmax = wmax; fc.hmax = hmax; fc.pitch4 = pitch4;
+    fc.chx = -0.5f / wmax; fc.chy = -0.5f / hmax;
+    // (Dm + 1) (2^-22 + 6 * 2^-24) + 2^-24 Dm, rounded up: reciprocal, scaled clamp and division terms
+    fc.c0 = __fmul_ru(__fadd_ru(__fmul_ru(__fadd_ru(Dm, 1.f), 5.9604645e-7f), __fmul_ru(Dm, 5.9604645e-8f)), 1.0001f);
+    const uint32_t masks_s = (uint32_t)__cvta_generic_to_shared(masks);
+    const int nitems = (npts + kProjPX - 1) / kProjPX;
+    // C: the largest coefficient of the item's points (neighbouring pixels: nearly equal); unwritten slots of
+    // the last item are ignored
+    auto load_item = [&](int item, float (&xs)[kProjPX], float (&ys)[kProjPX], float& C, int nvalid) {
+        const uint4 a = __ldg(XY4 + 2 * item), b = __ldg(XY4 + 2 * item + 1);
+        const uint32_t xy[kProjPX] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < kProjPX; ++k) {
+            xs[k] = (float)((int)(xy[k] & 0xffffu) - x0);
+            ys[k] = (float)((int)(xy[k] >> 16) - y0);
+        }
+        const float4 c = __ldg(C4 + 2 * item), d = __ldg(C4 + 2 * item + 1);
+        const float cc[kProjPX] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+        C = 0.f;
+#pragma unroll
+        for (int k = 0; k < kProjPX; ++k)
+            if (k < nvalid) C = (cc[k] >= C) ? cc[k] : C;         // +inf propagates (a written C is never NaN)
+    };
+    // full rounds: every thread owns one 8-point item and applies the candidates of the tile to it, 8 at a
+    // time (the unproven pairs of 8 candidates x 8 points fit one 64-bit mask)
+    const int nfull = (nitems / kProjThreads) * kProjThreads;
+    for (int item = threadIdx.x; item < nfull; item += kProjThreads) {
+        float xs[kProjPX], ys[kProjPX], C;
+        load_item(item, xs, ys, C, kProjPX);
+        for (int cb = 0; cb < nc; cb += 8) {
+            unsigned long long todo = 0;
+            const int ce = min(nc, cb + 8);
+            for (int c = cb; c < ce; ++c) {
+                const uint32_t unc = splat_points_filter<true>(xs, ys, C, kProjPX, hf + kHF * c, fc,
+                                                               masks_s + (uint32_t)(c * words4));
+                todo |= (unsigned long long)unc << (8 * (c - cb));
+            }
+            splat_exact_list<kMode>(todo, cb, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy,
+                                    wmax, hmax, pitch4, masks_s, words4);
+        }
+    }
+    // last, partial round: (item, candidate) pairs dealt out one by one (see splat_job)
+    const int tail = nitems - nfull;
+    for (int u = threadIdx.x; u < tail * nc; u += kProjThreads) {
+        const int c = u / tail, item = nfull + (u - c * tail);
+        float xs[kProjPX], ys[kProjPX], C;
+        const int nvalid = min(kProjPX, npts - item * kProjPX);
+        load_item(item, xs, ys, C, nvalid);
+        const uint32_t unc = nvalid >= kProjPX
+            ? splat_points_filter<true>(xs, ys, C, kProjPX, hf + kHF * c, fc, masks_s + (uint32_t)(c * words4))
+            : splat_points_filter<false>(xs, ys, C, nvalid, hf + kHF * c, fc, masks_s + (uint32_t)(c * words4));
+        splat_exact_list<kMode>((unsigned long long)unc, c, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f,
+                                cam.cx, cam.cy, wmax, hmax, pitch4, masks_s, words4);
+    }
+}
+
+// CTA roles.  k_project<false>: CTA = (job, tile of <= tile_cand candidates), the reference chain for
+// every point.  k_project<true>: the same tiles run the filter on their candidates; candidates flagged
+// exact-only by k_unproject (rotation by 0: every pixel maps onto an integer boundary) cost 3x a filtered
+// one, so they are taken out of the tiles and given to one EXTRA CTA per job (blockIdx % (tiles + 1) ==
+// tiles), which runs the straight-line reference chain on them — unless the job has more of them than
+// one CTA holds, in which case every tile keeps its own.
+template <bool kFilter>
 __global__ void __launch_bounds__(kProjThreads, 1)
 k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int tiles_per_job,
-          const float* __restrict__ xform, const float* __restrict__ pcd,
-          const int32_t* __restrict__ pcd_count, uint32_t* __restrict__ proj_bits,
-          int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox) {
+          const float* __restrict__ xform, const int32_t* __restrict__ src_bbox, const float* __restrict__ pcd,
+          const int32_t* __restrict__ pcd_count, const float* __restrict__ hom, const int4* __restrict__ tile_map,
+          uint32_t* __restrict__ proj_bits, int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox) {
     extern __shared__ __align__(16) uint32_t smem[];
-    const int jid = blockIdx.x / tiles_per_job;
+    __shared__ int nflag_s, nlist_s;
+    int jid, c0, want;
+    bool extra;
+    if (tile_map) {                   // caller-planned tiles: {job, first candidate, count, 1 = the job's extra CTA}
+        const int4 t = tile_map[blockIdx.x];
+        jid = t.x; c0 = t.y; want = min(t.z, tile_cand); extra = t.w != 0;
+        if (extra && !kFilter) return;
+    } else {
+        const int ctas_per_job = tiles_per_job + (kFilter ? 1 : 0);
+        jid = blockIdx.x / ctas_per_job;
+        const int tile_id = blockIdx.x - jid * ctas_per_job;
+        extra = kFilter && tile_id == tiles_per_job;
+        c0 = tile_id * tile_cand; want = tile_cand;
+    }
     const a3d_job_t job = jobs[jid];
-    const int c0 = (blockIdx.x - jid * tiles_per_job) * tile_cand;
-    const int nc = min(tile_cand, job.n_cand - c0);
-    if (nc <= 0) return;
+    if (extra) c0 = 0;
+    int nc = extra ? min(tile_cand, job.n_cand) : min(want, job.n_cand - c0);   // slots in use
+    if (nc <= 0 || c0 < 0) return;
 
     const int H = cam.H, pitch = cam.pitch;
     const int words = H * pitch;
     uint32_t* masks = smem;                                        // [tile_cand][words]
     float* xf = reinterpret_cast<float*>(smem + (size_t)tile_cand * words);   // [tile_cand][12]
     int* red = reinterpret_cast<int*>(xf + tile_cand * 12);        // [tile_cand][5]
+    float* hf = reinterpret_cast<float*>(red + tile_cand * 5);     // [tile_cand][kHF]  (filter only)
+    int* gid = reinterpret_cast<int*>(hf + tile_cand * kHF);       // [tile_cand] candidate of the slot, -1 = not mine
 
     {
         uint4* m4 = reinterpret_cast<uint4*>(masks);
         const int n4 = (nc * words) >> 2;
         for (int i = threadIdx.x; i < n4; i += kProjThreads) m4[i] = make_uint4(0, 0, 0, 0);
-        const float* gx = xform + (size_t)(job.cand_begin + c0) * 12;
-        for (int i = threadIdx.x; i < nc * 12; i += kProjThreads) xf[i] = gx[i];
+        if (!extra) {
+            const float* gx = xform + (size_t)(job.cand_begin + c0) * 12;
+            for (int i = threadIdx.x; i < nc * 12; i += kProjThreads) xf[i] = gx[i];
+        }
         for (int i = threadIdx.x; i < nc; i += kProjThreads) {
             red[5 * i + 0] = 0; red[5 * i + 1] = 0x7fffffff; red[5 * i + 2] = -1;
             red[5 * i + 3] = 0x7fffffff; red[5 * i + 4] = -1;
+            gid[i] = extra ? -1 : c0 + i;
+        }
+        if (threadIdx.x == 0) { nflag_s = 0; nlist_s = 0; }
+    }
+    __syncthreads();
+    pdl_wait();                       // the point clouds of k_unproject (the shared-memory tile is already zeroed)
+    pdl_launch_dependents();
+    const int npts = pcd_count[jid];
+    int x0 = 0, y0 = 0;
+    bool moved = false;               // exact-only candidates of this job live in the extra CTA
+    if (kFilter) {
+        const int32_t* sb = src_bbox + 4 * (size_t)job.src_mask;
+        y0 = (sb[0] + sb[1]) >> 1;
+        x0 = 16 * (sb[2] + sb[3] + 1);
+        const float* gh = hom + (size_t)job.cand_begin * kHF;                 // written by k_unproject
+        int mine = 0;
+        for (int c = threadIdx.x; c < job.n_cand; c += kProjThreads) mine += (npts > 0 && gh[(size_t)c * kHF + 10] != 0.f) ? 1 : 0;
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&nflag_s, mine);
+        if (!extra)
+            for (int i = threadIdx.x; i < nc * kHF; i += kProjThreads) hf[i] = gh[(size_t)c0 * kHF + i];
+        __syncthreads();
+        const int nflag = nflag_s;
+        moved = nflag > 0 && nflag <= tile_cand;
+        if (extra) {
+            if (!moved) return;
+            for (int c = threadIdx.x; c < job.n_cand; c += kProjThreads)
+                if (gh[(size_t)c * kHF + 10] != 0.f) {
+                    const int slot = atomicAdd(&nlist_s, 1);
+                    gid[slot] = c;
+                    for (int i = 0; i < 12; ++i) xf[12 * slot + i] = xform[(size_t)(job.cand_begin + c) * 12 + i];
+                }
+            nc = nflag;
+        } else if (moved) {
+            for (int i = threadIdx.x; i < nc; i += kProjThreads)
+                if (hf[kHF * i + 10] != 0.f) gid[i] = -1;
+        }
+        __syncthreads();
+    }
+    if (npts > 0) {
+        if (kFilter && !extra) {
+            if (job.mode == A3D_MODE_SEQ) splat_job_filter<A3D_MODE_SEQ>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words);
+            else if (job.mode == A3D_MODE_COMPOSED) splat_job_filter<A3D_MODE_COMPOSED>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words);
+            else splat_job_filter<A3D_MODE_TRANSLATE>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words);
+            if (!moved && nflag_s > 0) {
+                // more exact-only candidates than the extra CTA holds: each tile runs its own
+                for (int c = 0; c < nc; ++c) {
+                    if (hf[kHF * c + 10] == 0.f) continue;
+                    if (job.mode == A3D_MODE_SEQ) splat_job<A3D_MODE_SEQ>(cam, job, npts, 1, pcd, xf + 12 * c, masks + (size_t)c * words, words);
+                    else if (job.mode == A3D_MODE_COMPOSED) splat_job<A3D_MODE_COMPOSED>(cam, job, npts, 1, pcd, xf + 12 * c, masks + (size_t)c * words, words);
+                    else splat_job<A3D_MODE_TRANSLATE>(cam, job, npts, 1, pcd, xf + 12 * c, masks + (size_t)c * words, words);
+                }
+            }
+        } else {
+            if (job.mode == A3D_MODE_SEQ) splat_job<A3D_MODE_SEQ>(cam, job, npts, nc, pcd, xf, masks, words);
+            else if (job.mode == A3D_MODE_COMPOSED) splat_job<A3D_MODE_COMPOSED>(cam, job, npts, nc, pcd, xf, masks, words);
+            else splat_job<A3D_MODE_TRANSLATE>(cam, job, npts, nc, pcd, xf, masks, words);
         }
     }
     __syncthreads();
 
-    pdl_wait();                       // the point clouds of k_unproject (the shared-memory tile is already zeroed)
-    pdl_launch_dependents();
-    const int npts = pcd_count[jid];
-    if (npts > 0) {
-        if (job.mode == A3D_MODE_SEQ) splat_job<A3D_MODE_SEQ>(cam, job, npts, nc, pcd, xf, masks, words);
-        else if (job.mode == A3D_MODE_COMPOSED) splat_job<A3D_MODE_COMPOSED>(cam, job, npts, nc, pcd, xf, masks, words);
-        else splat_job<A3D_MODE_TRANSLATE>(cam, job, npts, nc, pcd, xf, masks, words);
-    }
-    __syncthreads();
-
     // ---- stream the tile out, with popcount + bounding box per candidate ----------
+    // (row, uint4 column) of a thread's elements advance by constants: no division in the loop; the
+    // occupied word columns are collected as a bit mask (pitch <= 32 words)
     const int p4 = pitch >> 2, n4 = H * p4;
+    const int row0 = threadIdx.x / p4, col0 = threadIdx.x - row0 * p4;
+    const int drow = kProjThreads / p4, dcol = kProjThreads - drow * p4;
     for (int c = 0; c < nc; ++c) {
+        if (gid[c] < 0) continue;
         const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
-        uint4* d4 = reinterpret_cast<uint4*>(proj_bits + (size_t)(job.cand_begin + c0 + c) * words);
+        uint4* d4 = reinterpret_cast<uint4*>(proj_bits + (size_t)(job.cand_begin + gid[c]) * words);
         MaskStat s = stat_identity();
-        for (int i = threadIdx.x; i < n4; i += kProjThreads) {
-            const uint4 v = s4[i];
-            d4[i] = v;
-            if (v.x | v.y | v.z | v.w) {
-                const int row = i / p4, cc = (i - row * p4) << 2;
-                stat_add_word(s, v.x, row, cc);
-                stat_add_word(s, v.y, row, cc + 1);
-                stat_add_word(s, v.z, row, cc + 2);
-                stat_add_word(s, v.w, row, cc + 3);
+        if (pitch <= 32) {
+            uint32_t colmask = 0;
+            int row = row0, col = col0;
+            for (int i = threadIdx.x; i < n4; i += kProjThreads) {
+                const uint4 v = s4[i];
+                d4[i] = v;
+                if (v.x | v.y | v.z | v.w) {
+                    s.popc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+                    s.rmin = min(s.rmin, row);
+                    s.rmax = max(s.rmax, row);
+                    const uint32_t nz = (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
+                    colmask |= nz << (4 * col);
+                }
+                row += drow; col += dcol;
+                if (col >= p4) { col -= p4; ++row; }
+            }
+            colmask = __reduce_or_sync(0xffffffffu, colmask);
+            if (colmask) { s.cmin = __ffs(colmask) - 1; s.cmax = 31 - __clz(colmask); }
+        } else {
+            for (int i = threadIdx.x; i < n4; i += kProjThreads) {
+                const uint4 v = s4[i];
+                d4[i] = v;
+                if (v.x | v.y | v.z | v.w) {
+                    const int row = i / p4, cc = (i - row * p4) << 2;
+                    stat_add_word(s, v.x, row, cc);
+                    stat_add_word(s, v.y, row, cc + 1);
+                    stat_add_word(s, v.z, row, cc + 2);
+                    stat_add_word(s, v.w, row, cc + 3);
+                }
             }
         }
         stat_block_accumulate(red + 5 * c, s);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < nc; c += kProjThreads) {
-        const size_t g = (size_t)job.cand_begin + c0 + c;
+        if (gid[c] < 0) continue;
+        const size_t g = (size_t)job.cand_begin + gid[c];
         stat_store(red + 5 * c, proj_popc + g, proj_bbox + 4 * g);
     }
 }
@@ -1461,7 +1893,8 @@ int device_smem_optin() {
 }
 
 size_t project_smem_bytes(int H, int pitch, int tile) {
-    return (size_t)tile * H * pitch * 4 + (size_t)tile * 12 * 4 + (size_t)tile * 5 * 4;
+    return (size_t)tile * H * pitch * 4 + (size_t)tile * 12 * 4 + (size_t)tile * 5 * 4 + (size_t)tile * kHF * 4 +
+           (size_t)tile * 4;
 }
 
 }  // namespace
@@ -1488,7 +1921,8 @@ static cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 
 static int project_impl(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
                         int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,
-                        const float* xform, float* pcd_ws, int32_t* pcd_count,
+                        const float* xform, float* pcd_ws, int32_t* pcd_count, float* hom_ws,
+                        const int32_t* tile_map, int n_tiles,
                         uint32_t* proj_bits, int32_t* proj_popc, int32_t* proj_bbox, void* stream, bool pdl);
 static int score_impl(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_tgt, int max_cand,
                       int64_t n_tgt_total, int64_t n_pool_masks, int64_t n_cand_total,
@@ -1502,6 +1936,14 @@ static int score_impl(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_t
 extern "C" {
 
 int a3d_version(void) { return A3D_VERSION; }
+
+#ifdef A3D_FILTER_STATS
+int a3d_debug_filter_stats(unsigned long long* out4, int reset) {
+    if (out4) cudaMemcpyFromSymbol(out4, g_filter_stats, sizeof(unsigned long long) * 4);
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_filter_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 const char* a3d_last_error_string(void) { return g_err; }
 
@@ -1569,17 +2011,18 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W, int32_t* popc, 
 
 int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
                 int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,
-                const float* xform, float* pcd_ws, int32_t* pcd_count,
+                const float* xform, float* pcd_ws, int32_t* pcd_count, float* hom_ws,
+                const int32_t* tile_map, int n_tiles,
                 uint32_t* proj_bits, int32_t* proj_popc, int32_t* proj_bbox, void* stream) {
-    return project_impl(cam, jobs, n_jobs, max_cand, tile_cand, src_bits, src_bbox, xform, pcd_ws, pcd_count,
-                        proj_bits, proj_popc, proj_bbox, stream, false);
+    return project_impl(cam, jobs, n_jobs, max_cand, tile_cand, src_bits, src_bbox, xform, pcd_ws, pcd_count, hom_ws,
+                        tile_map, n_tiles, proj_bits, proj_popc, proj_bbox, stream, false);
 }
 
 int a3d_pass(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_tgt, int max_cand,
              int tile_cand, int64_t n_tgt_total, int64_t n_pool_masks, int64_t n_cand_total,
              const uint32_t* pool_bits, const int32_t* pool_popc, const int32_t* pool_bbox,
              const uint32_t* src_bits, const int32_t* src_bbox, const float* xform, const int32_t* tgt_index,
-             float* pcd_ws, int32_t* pcd_count,
+             float* pcd_ws, int32_t* pcd_count, float* hom_ws, const int32_t* tile_map, int n_tiles,
              uint32_t* proj_bits, int32_t* proj_popc, int32_t* proj_bbox,
              uint64_t* key_ws, int32_t* inter_tab,
              int32_t* best_cand, int32_t* best_inter, int32_t* best_union, float* best_iou,
@@ -1598,8 +2041,8 @@ int a3d_pass(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max
     const char* env_pdl = getenv("A3D_PDL");
     const bool pdl = env_pdl ? env_pdl[0] == '1' : (long long)n_jobs * (max_cand > 0 ? max_cand : 1) <= 6 * 296;
     int rc = project_impl(cam, jobs, n_jobs, max_cand, tile_cand, src_bits ? src_bits : pool_bits,
-                          src_bits ? src_bbox : pool_bbox, xform, pcd_ws, pcd_count, proj_bits, proj_popc, proj_bbox,
-                          stream, pdl);
+                          src_bits ? src_bbox : pool_bbox, xform, pcd_ws, pcd_count, hom_ws, tile_map, n_tiles,
+                          proj_bits, proj_popc, proj_bbox, stream, pdl);
     if (rc != A3D_OK || !score) return rc;
     return score_impl(cam->H, cam->W, jobs, n_jobs, max_tgt, max_cand, n_tgt_total, n_pool_masks, n_cand_total,
                       pool_bits, pool_popc, pool_bbox, tgt_index, proj_bits, proj_popc, proj_bbox, key_ws, inter_tab,
@@ -1610,13 +2053,20 @@ int a3d_pass(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max
 
 static int project_impl(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
                         int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,
-                        const float* xform, float* pcd_ws, int32_t* pcd_count,
+                        const float* xform, float* pcd_ws, int32_t* pcd_count, float* hom_ws,
+                        const int32_t* tile_map, int n_tiles,
                         uint32_t* proj_bits, int32_t* proj_popc, int32_t* proj_bbox, void* stream, bool pdl) {
     if (!cam || n_jobs < 0 || max_cand < 0) return fail(A3D_EINVAL, "a3d_project: bad argument");
     if (n_jobs == 0 || max_cand == 0) return A3D_OK;
     if (!jobs || !src_bits || !src_bbox || !xform || !pcd_ws || !pcd_count || !proj_bits || !proj_popc ||
         !proj_bbox)
         return fail(A3D_EINVAL, "a3d_project: null pointer");
+    // A3D_PROJECT_KERNEL = exact | filter (default filter: homography + proven truncation, exact chain on
+    // demand; identical results).  The filter packs source coordinates in 16 bits and needs hom_ws.
+    const char* env_proj = getenv("A3D_PROJECT_KERNEL");
+    const bool filter = !(env_proj && !strcmp(env_proj, "exact")) && cam->H <= 32768 && cam->W <= 32768 && hom_ws;
+    if (env_proj && !strcmp(env_proj, "filter") && !hom_ws)
+        return fail(A3D_EINVAL, "a3d_project: A3D_PROJECT_KERNEL=filter needs hom_ws");
     const int max_tile = a3d_project_max_tile(cam->H, cam->W);
     if (max_tile < 0) return max_tile;
     if (tile_cand <= 0) tile_cand = max_tile;
@@ -1642,23 +2092,40 @@ static int project_impl(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jo
     if (c.sparse) {
         A3D_CUDA_TRY(cudaFuncSetAttribute(k_unproject<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
         A3D_CUDA_TRY(launch(k_unproject<true>, ugrid, dim3(kUnprojThreads), usmem, s, false, c, jobs, src_bits, src_bbox,
-                            pcd_ws, pcd_count));
+                            xform, pcd_ws, pcd_count, filter ? hom_ws : (float*)nullptr));
     } else {
         A3D_CUDA_TRY(cudaFuncSetAttribute(k_unproject<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
         A3D_CUDA_TRY(launch(k_unproject<false>, ugrid, dim3(kUnprojThreads), usmem, s, false, c, jobs, src_bits, src_bbox,
-                            pcd_ws, pcd_count));
+                            xform, pcd_ws, pcd_count, filter ? hom_ws : (float*)nullptr));
     }
     A3D_CUDA_TRY(cudaGetLastError());
 
     // 2. candidates
     const size_t smem = project_smem_bytes(c.H, c.pitch, tile_cand);
     const int tiles_per_job = (max_cand + tile_cand - 1) / tile_cand;
-    const long long nblocks = (long long)n_jobs * tiles_per_job;
+    long long nblocks = (long long)n_jobs * tiles_per_job;
     if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_project: too many (job, tile) blocks");
-    A3D_CUDA_TRY(cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    A3D_CUDA_TRY(launch(k_project, dim3((unsigned)nblocks), dim3(kProjThreads), smem, s, pdl, c, jobs, tile_cand,
-                        tiles_per_job, xform, (const float*)pcd_ws, (const int32_t*)pcd_count, proj_bits, proj_popc,
-                        proj_bbox));
+    const int4* tmap = nullptr;
+    if (tile_map) {                   // caller-planned tiles (their extra CTAs included)
+        if (n_tiles <= 0) return fail(A3D_EINVAL, "a3d_project: tile_map with n_tiles %d", n_tiles);
+        if ((uintptr_t)tile_map % 16) return fail(A3D_EINVAL, "a3d_project: tile_map must be 16-byte aligned");
+        tmap = reinterpret_cast<const int4*>(tile_map);
+        nblocks = n_tiles;
+    } else if (filter) {
+        nblocks += n_jobs;            // one extra CTA per job for its exact-only candidates
+        if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_project: too many (job, tile) blocks");
+    }
+    if (filter) {
+        A3D_CUDA_TRY(cudaFuncSetAttribute(k_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        A3D_CUDA_TRY(launch(k_project<true>, dim3((unsigned)nblocks), dim3(kProjThreads), smem, s, pdl, c, jobs, tile_cand,
+                            tiles_per_job, xform, src_bbox, (const float*)pcd_ws, (const int32_t*)pcd_count,
+                            (const float*)hom_ws, tmap, proj_bits, proj_popc, proj_bbox));
+    } else {
+        A3D_CUDA_TRY(cudaFuncSetAttribute(k_project<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        A3D_CUDA_TRY(launch(k_project<false>, dim3((unsigned)nblocks), dim3(kProjThreads), smem, s, pdl, c, jobs, tile_cand,
+                            tiles_per_job, xform, src_bbox, (const float*)pcd_ws, (const int32_t*)pcd_count,
+                            (const float*)hom_ws, tmap, proj_bits, proj_popc, proj_bbox));
+    }
     return A3D_OK;
 }
 

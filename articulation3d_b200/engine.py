@@ -128,6 +128,57 @@ def pool_from_bits(bits: torch.Tensor, H: int, W: int) -> MaskPool:
     return MaskPool(bits.contiguous(), popc, bbox, H, W)
 
 
+def plan_tiles(jobs: np.ndarray, max_tile: int, sm_count: int = 148, fixed: float = 21500.0, per_cand: float = 3000.0):
+    """Split of a pass into projection CTAs when the grid is about one wave: jobs whose source masks
+    differ in size get tiles of different size, so that every CTA carries about the same number of
+    (point, candidate) pairs and the SMs finish together (uniform tiles leave the kernel waiting for the
+    CTAs of the largest mask: C2's four tracks have 10-38 k source pixels).
+
+    Cost model, in point units, from the ncu instruction counts of k_project<filter> on C2: a CTA costs
+    ``fixed + tile * (per_cand + points)``; the job's extra CTA (exact-only candidates, role 1)
+    ``fixed + per_cand + 2.5 * points``.  Returns ``(tile_cand, tile_map)``; ``tile_map`` is None when
+    the grid is several waves anyway (uniform tiles of ``tile_cand``, the hardware scheduler balances) and
+    else an int32 array (n_tiles, 4) of {job, first candidate, candidates, role}, most expensive first."""
+    n = len(jobs)
+    if n == 0:
+        return max_tile, None
+    ncand = jobs["n_cand"].astype(np.int64)
+    cost = jobs["pcd_cap"].astype(np.float64) + per_cand
+    min_ctas = int((-(-ncand // max_tile)).sum())
+    waves = 1 if min_ctas + n <= sm_count else 2
+    if min_ctas + n > waves * sm_count:
+        return max_tile, None
+    cap = waves * sm_count - n
+
+    def tiles_for(w):
+        return np.clip(np.floor(w / cost), 1, max_tile).astype(np.int64)
+
+    lo, hi = float(cost.min()), float(cost.max()) * max_tile
+    for _ in range(40):                                  # smallest budget whose CTAs fit the wave(s)
+        mid = 0.5 * (lo + hi)
+        if int((-(-ncand // tiles_for(mid))).sum()) <= cap:
+            hi = mid
+        else:
+            lo = mid
+    tile = tiles_for(hi)
+    rows = []
+    for j in range(n):
+        if ncand[j] == 0:
+            continue
+        k = int(-(-ncand[j] // tile[j]))
+        base, rem = divmod(int(ncand[j]), k)
+        c = 0
+        for i in range(k):
+            sz = base + (1 if i < rem else 0)
+            rows.append((fixed + sz * cost[j], j, c, sz, 0))
+            c += sz
+    for j in range(n):
+        rows.append((fixed + per_cand + 2.5 * float(jobs["pcd_cap"][j]), j, 0, 0, 1))
+    rows.sort(key=lambda r: -r[0])
+    tmap = np.array([r[1:] for r in rows], dtype=np.int32).reshape(-1, 4)
+    return int(tmap[:, 2].max()), tmap
+
+
 @dataclass
 class JobBatch:
     """Host description of one pass (numpy, ready for a single H2D each)."""
@@ -193,8 +244,17 @@ class PassResult:
 class DeviceBatch:
     """A JobBatch uploaded to the device (inputs resident in HBM)."""
 
-    def __init__(self, batch: JobBatch, device, staging: "Staging | None" = None):
+    def __init__(self, batch: JobBatch, device, staging: "Staging | None" = None, cfg: OptConfig | None = None):
         self.host = batch
+        self.device = device
+        self._plans = {}
+        plan = None
+        if cfg is not None and os.environ.get("A3D_TILE_PLAN") != "uniform":
+            plan = plan_tiles(batch.jobs, max_tile(cfg))
+            if plan[1] is None:
+                plan = (choose_tile(cfg, int(batch.xform.shape[0]), batch.n_jobs), None)
+            self._plans[(cfg.height, cfg.width)] = plan
+        tmap = plan[1] if plan is not None and plan[1] is not None else np.zeros((0, 4), np.int32)
         self.n_jobs = batch.n_jobs
         self.n_cand_total = int(batch.xform.shape[0])
         self.n_tgt_total = int(batch.tgt_index.shape[0])
@@ -203,20 +263,38 @@ class DeviceBatch:
         self.tab_total = int((batch.jobs["n_cand"].astype(np.int64) * batch.jobs["n_tgt"]).sum())
         self.pcd_total = int(batch.jobs["pcd_cap"].astype(np.int64).sum())
         # one H2D for the three arrays: pinned staging block [jobs | xform | tgt_index], 16-byte aligned parts
-        nj, nx, nt = batch.jobs.nbytes, batch.xform.nbytes, batch.tgt_index.nbytes
+        nj, nx, nt, nm = batch.jobs.nbytes, batch.xform.nbytes, batch.tgt_index.nbytes, tmap.nbytes
         oj, ox = 0, (nj + 15) & ~15
         ot = (ox + nx + 15) & ~15
-        total = max(ot + nt, 16)
+        om = (ot + nt + 15) & ~15
+        total = max(om + nm, 16)
         host = staging.host(total) if staging is not None else torch.empty(total, dtype=torch.uint8).pin_memory()
         hv = host.numpy()
         hv[oj:oj + nj] = batch.jobs.view(np.uint8).reshape(-1)
         hv[ox:ox + nx] = batch.xform.view(np.uint8).reshape(-1)
         hv[ot:ot + nt] = batch.tgt_index.view(np.uint8).reshape(-1)
+        hv[om:om + nm] = tmap.view(np.uint8).reshape(-1)
         dev = staging.device_block(total) if staging is not None else torch.empty(total, dtype=torch.uint8, device=device)
         dev[:total].copy_(host[:total], non_blocking=True)
         self.jobs = dev[oj:oj + nj]
         self.xform = dev[ox:ox + nx].view(torch.float32).view(-1, 12)
         self.tgt_index = dev[ot:ot + nt].view(torch.int32)
+        self._tmap_dev = {(cfg.height, cfg.width): dev[om:om + nm].view(torch.int32).view(-1, 4)} if nm else {}
+
+    def tile_plan(self, cfg: OptConfig):
+        """(tile_cand, device tile map or None) for this camera: planned once, uploaded once."""
+        key = (cfg.height, cfg.width)
+        if key not in self._plans:
+            if os.environ.get("A3D_TILE_PLAN") == "uniform":
+                self._plans[key] = (choose_tile(cfg, self.n_cand_total, self.n_jobs), None)
+            else:
+                tile, tmap = plan_tiles(self.host.jobs, max_tile(cfg))
+                if tmap is None:
+                    tile = choose_tile(cfg, self.n_cand_total, self.n_jobs)
+                else:
+                    self._tmap_dev[key] = torch.from_numpy(tmap).to(self.device)
+                self._plans[key] = (tile, tmap)
+        return self._plans[key][0], self._tmap_dev.get(key)
 
 
 class Staging:
@@ -270,19 +348,24 @@ def _camera_cached(cfg: OptConfig) -> _lib.Camera:
     return cam
 
 
-def choose_tile(cfg: OptConfig, n_cand_total: int, n_jobs: int = 1, sm_count: int = 148) -> int:
-    """Candidates per projection CTA.  Large batches take as many as shared memory holds (the
-    point cloud is read once per CTA); small batches pick the tile that minimises
-    waves x (per-CTA overhead + tile) so no SM runs two CTAs while others idle."""
+def max_tile(cfg: OptConfig) -> int:
+    """Most candidates one projection CTA holds in shared memory for this image size."""
     key = (cfg.height, cfg.width)
-    max_tile = _tile_cache.get(key)
-    if max_tile is None:
+    t = _tile_cache.get(key)
+    if t is None:
         lib = _lib.load()
-        max_tile = _tile_cache[key] = _lib.check(lib.a3d_project_max_tile(cfg.height, cfg.width),
-                                                 "a3d_project_max_tile")
+        t = _tile_cache[key] = _lib.check(lib.a3d_project_max_tile(cfg.height, cfg.width), "a3d_project_max_tile")
+    return t
+
+
+def choose_tile(cfg: OptConfig, n_cand_total: int, n_jobs: int = 1, sm_count: int = 148) -> int:
+    """Candidates per projection CTA for uniform tiles.  Large batches take as many as shared memory
+    holds (the point cloud is read once per CTA); small batches pick the tile that minimises
+    waves x (per-CTA overhead + tile) so no SM runs two CTAs while others idle."""
+    mt = max_tile(cfg)
     per_job = -(-n_cand_total // max(n_jobs, 1))
-    best, best_cost = max_tile, None
-    for tile in range(max_tile, 0, -1):
+    best, best_cost = mt, None
+    for tile in range(mt, 0, -1):
         ctas = n_jobs * -(-per_job // tile)
         cost = -(-ctas // sm_count) * (0.3 + tile)
         if best_cost is None or cost < best_cost - 1e-9:
@@ -305,8 +388,9 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
         proj_bits = ws.get("proj_bits", (nc, H, pitch), torch.int32)
         proj_popc = ws.get("proj_popc", (nc,), torch.int32)
         proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
-        pcd_ws = ws.get("pcd_ws", (max(3 * dbatch.pcd_total, 32),), torch.float32)
+        pcd_ws = ws.get("pcd_ws", (max(_lib.PCD_PLANES * dbatch.pcd_total, 32),), torch.float32)
         pcd_count = ws.get("pcd_count", (dbatch.n_jobs,), torch.int32)
+        hom_ws = ws.get("hom_ws", (max(nc, 1), _lib.HOM_FLOATS), torch.float32)
         key_ws = ws.get("key_ws", (nt,), torch.int64)
         results = ws.get("results", (4, nt), torch.int32)          # one block -> one D2H
         best_cand, best_inter, best_union = results[0], results[1], results[2]
@@ -316,14 +400,20 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
             return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab)
         cam = _camera_cached(cfg)
         stream = _stream_ptr()
-        tile = tile_cand if tile_cand is not None else choose_tile(cfg, nc, dbatch.n_jobs)
+        tmap = None
+        if tile_cand is not None:
+            tile = tile_cand
+        else:
+            tile, tmap = dbatch.tile_plan(cfg)
+        tmap_ptr, n_tiles = (tmap.data_ptr(), int(tmap.shape[0])) if tmap is not None else (None, 0)
         if os.environ.get("A3D_PASS_API") != "split":
             # one call: keys cleared first, then the four kernels as programmatic dependent launches
             _lib.check(lib.a3d_pass(C.byref(cam), dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_tgt, dbatch.max_cand,
                                     tile, nt, len(pool), nc, pool.bits.data_ptr(), pool.popc.data_ptr(),
                                     pool.bbox.data_ptr(), pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(),
                                     dbatch.xform.data_ptr(), dbatch.tgt_index.data_ptr(), pcd_ws.data_ptr(),
-                                    pcd_count.data_ptr(), proj_bits.data_ptr(), proj_popc.data_ptr(),
+                                    pcd_count.data_ptr(), hom_ws.data_ptr(), tmap_ptr, n_tiles,
+                                    proj_bits.data_ptr(), proj_popc.data_ptr(),
                                     proj_bbox.data_ptr(), key_ws.data_ptr(),
                                     inter_tab.data_ptr() if inter_tab is not None else None,
                                     best_cand.data_ptr(), best_inter.data_ptr(), best_union.data_ptr(),
@@ -332,7 +422,8 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
                               results)
         _lib.check(lib.a3d_project(C.byref(cam), dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_cand, tile,
                                    pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(),
-                                   dbatch.xform.data_ptr(), pcd_ws.data_ptr(), pcd_count.data_ptr(),
+                                   dbatch.xform.data_ptr(), pcd_ws.data_ptr(), pcd_count.data_ptr(), hom_ws.data_ptr(),
+                                   tmap_ptr, n_tiles,
                                    proj_bits.data_ptr(), proj_popc.data_ptr(), proj_bbox.data_ptr(), stream),
                    "a3d_project")
         _lib.check(lib.a3d_score(H, W, dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_tgt, dbatch.max_cand, nt,

@@ -458,7 +458,7 @@ class _Session:
                                    [s.normal for s in specs], [s.offset for s in specs],
                                    [s.pivot for s in specs], [s.xform for s in specs],
                                    [s.targets for s in specs], self.pool.source_points)
-        dbatch = engine.DeviceBatch(batch, self.device, self.staging)
+        dbatch = engine.DeviceBatch(batch, self.device, self.staging, self.cfg)
         res = engine.run_pass(self.cfg, self.pool, dbatch, self.ws)
         host = self.staging.results_host(res.block.numel())
         host.view(4, -1).copy_(res.block, non_blocking=True)                 # one D2H into pinned memory

@@ -74,9 +74,10 @@ class PassInputs:
 
 
 def build_pass(wl: Workload, seed0: int, device, source_frame: int | None = None,
-               progress=None) -> PassInputs:
-    """Render every track of ``wl`` on the device, pack the masks, and describe one
-    cluster-phase (three-step rotation) pass with the middle frame of each track as source."""
+               progress=None, mode: int = _lib.MODE_SEQ) -> PassInputs:
+    """Render every track of ``wl`` on the device, pack the masks, and describe one pass with the
+    middle frame of each track as source: cluster-phase three-step rotations (``MODE_SEQ``, the
+    default), final-phase composed rotations or translations along the axis direction."""
     cfg = wl.cfg()
     T = wl.frames
     s = T // 2 if source_frame is None else source_frame
@@ -105,10 +106,13 @@ def build_pass(wl: Workload, seed0: int, device, source_frame: int | None = None
             progress(v)
     pool = engine.pool_from_bits(torch.cat(bits), cfg.height, cfg.width)
     del bits
-    R = geometry.rotation_matrices(cfg.rot_cluster_grid, np.stack(dirs))             # (S,A,3,3)
-    xf = geometry.xforms_seq(R)
+    if mode == _lib.MODE_TRANSLATE:
+        xf = geometry.xforms_translate(np.linspace(-1.0, 1.0, wl.cand, endpoint=False), np.stack(dirs))
+    else:
+        R = geometry.rotation_matrices(cfg.rot_cluster_grid, np.stack(dirs))         # (S,A,3,3)
+        xf = geometry.xforms_seq(R) if mode == _lib.MODE_SEQ else geometry.xforms_composed(R, np.stack(pivots))
     S = len(srcs)
-    batch = engine.build_batch(srcs, [_lib.MODE_SEQ] * S, normals, offsets, pivots, list(xf),
+    batch = engine.build_batch(srcs, [mode] * S, normals, offsets, pivots, list(xf),
                                [np.arange(i * T, (i + 1) * T, dtype=np.int32) for i in range(S)],
                                pool.source_points)
     dbatch = engine.DeviceBatch(batch, device)

@@ -405,17 +405,19 @@ def _run_split(engine, inp, ws, evs):
     proj_bits = ws.get("proj_bits", (nc, H, pitch), torch.int32)
     proj_popc = ws.get("proj_popc", (nc,), torch.int32)
     proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
-    pcd_ws = ws.get("pcd_ws", (max(3 * db.pcd_total, 32),), torch.float32)
+    pcd_ws = ws.get("pcd_ws", (max(_lib.PCD_PLANES * db.pcd_total, 32),), torch.float32)
     pcd_count = ws.get("pcd_count", (db.n_jobs,), torch.int32)
+    hom_ws = ws.get("hom_ws", (max(nc, 1), _lib.HOM_FLOATS), torch.float32)
     key_ws = ws.get("key_ws", (nt,), torch.int64)
     outs = [ws.get(n, (nt,), dt) for n, dt in (("best_cand", torch.int32), ("best_inter", torch.int32),
                                                ("best_union", torch.int32), ("best_iou", torch.float32))]
     cam = engine.camera_struct(cfg)
     stream = torch.cuda.current_stream().cuda_stream
-    tile = engine.choose_tile(cfg, nc, db.n_jobs)
+    tile, tmap = db.tile_plan(cfg)
+    tmap_ptr, n_tiles = (tmap.data_ptr(), int(tmap.shape[0])) if tmap is not None else (None, 0)
     _lib.check(lib.a3d_project(C.byref(cam), db.jobs.data_ptr(), db.n_jobs, db.max_cand, tile,
                                pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(), db.xform.data_ptr(),
-                               pcd_ws.data_ptr(), pcd_count.data_ptr(),
+                               pcd_ws.data_ptr(), pcd_count.data_ptr(), hom_ws.data_ptr(), tmap_ptr, n_tiles,
                                proj_bits.data_ptr(), proj_popc.data_ptr(), proj_bbox.data_ptr(), stream),
                "a3d_project")
     if evs:

@@ -46,6 +46,12 @@ enum {
 /* mask element types accepted by a3d_pack_masks / produced by a3d_emit_masks */
 enum { A3D_F32 = 0, A3D_U8 = 1 };
 
+/* floats of point-cloud workspace per point: X | Y | Z planes, the packed source pixel and the
+ * error-bound coefficient of the filtered projection */
+#define A3D_PCD_PLANES 5
+/* floats of homography workspace per candidate (filtered projection) */
+#define A3D_HOM_FLOATS 12
+
 /* candidate transform modes (one per job) */
 enum {
     A3D_MODE_SEQ = 0,        /* q=p-a; r=q*R; s=r+a  — cluster phase, opt_utils.py:433-435   */
@@ -115,13 +121,25 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W,
  *   src_bits   source mask pool, src_bbox its a3d_mask_meta boxes
  *   xform      [n_cand_total][12] fp32: rows 0-2 of R (row-vector convention,
  *              p' = p*R), then t
- *   pcd_ws     workspace, 3 * sum(pcd_cap) floats (X|Y|Z planes per job slice)
+ *   pcd_ws     workspace, A3D_PCD_PLANES * sum(pcd_cap) floats (planes of pcd_cap floats per job slice)
  *   pcd_count  workspace, [n_jobs] int32 (points actually produced per job)
+ *   hom_ws     workspace, [n_cand_total][A3D_HOM_FLOATS] floats: per candidate the plane-induced
+ *              homography source pixel -> projected pixel and its error bound, from which the
+ *              filtered projection kernel takes every pixel it can PROVE equal to the reference
+ *              chain's (the others run that chain; results are identical either way).  NULL or
+ *              A3D_PROJECT_KERNEL=exact: the reference chain for every point.
+ *   tile_map   optional [n_tiles][4] int32, 16-byte aligned: the caller's split of the work into
+ *              CTAs, {job, first candidate, candidates (<= tile_cand), role}; role 1 marks the CTA
+ *              that takes the job's exact-only candidates (one per job, first/count ignored).
+ *              Every candidate of every job must be covered exactly once by role-0 entries.
+ *              NULL: uniform tiles of tile_cand candidates.  Jobs of very different size in a
+ *              grid of about one wave are the case for it (see engine.plan_tiles).
  *   proj_bits  [n_cand_total][H][pitch]; proj_popc [n_cand_total];
  *   proj_bbox  [n_cand_total][4]                                               */
 int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
                 int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,
-                const float* xform, float* pcd_ws, int32_t* pcd_count,
+                const float* xform, float* pcd_ws, int32_t* pcd_count, float* hom_ws,
+                const int32_t* tile_map, int n_tiles,
                 uint32_t* proj_bits, int32_t* proj_popc, int32_t* proj_bbox, void* stream);
 
 /* (a8) mask-IoU scoring with fused arg-max over candidates.  Replaces the
@@ -152,7 +170,7 @@ int a3d_pass(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max
              int tile_cand, int64_t n_tgt_total, int64_t n_pool_masks, int64_t n_cand_total,
              const uint32_t* pool_bits, const int32_t* pool_popc, const int32_t* pool_bbox,
              const uint32_t* src_bits, const int32_t* src_bbox, const float* xform, const int32_t* tgt_index,
-             float* pcd_ws, int32_t* pcd_count,
+             float* pcd_ws, int32_t* pcd_count, float* hom_ws, const int32_t* tile_map, int n_tiles,
              uint32_t* proj_bits, int32_t* proj_popc, int32_t* proj_bbox,
              uint64_t* key_ws, int32_t* inter_tab,
              int32_t* best_cand, int32_t* best_inter, int32_t* best_union, float* best_iou,

@@ -573,3 +573,27 @@ def test_single_call_pass_equals_project_then_score(pdl, monkeypatch):
     got = [b.best_cand, b.best_inter, b.best_union, b.best_iou.view(torch.int32), b.inter_tab, b.proj_popc, b.proj_bbox]
     for w, g in zip(want, got):
         assert torch.equal(w, g)
+
+
+@pytest.mark.parametrize("mode", [_lib.MODE_SEQ, _lib.MODE_COMPOSED, _lib.MODE_TRANSLATE])
+@pytest.mark.parametrize("shape", ["640x480", "1024x768"])
+def test_filtered_projection_equals_exact_chain(mode, shape, monkeypatch):
+    """k_project<filter> (homography + proven truncation, exact chain on demand) against k_project<exact>
+    (the reference's fp32 chain for every point): projected masks, counts, boxes and the scores bit for bit,
+    over ~10^8 (point, candidate) pairs per case, any candidate tiling."""
+    from articulation3d_b200 import workloads
+    wl = workloads.Workload("probe", "4 videos x 4 tracks x 16 frames, 96 candidates", 4, 4, 16, 96) if shape == "640x480" \
+        else workloads.Workload("probe", "2 videos x 2 tracks x 12 frames, 144 candidates, 1024x768", 2, 2, 12, 144, 1024, 768)
+    inp = workloads.build_pass(wl, 300 + mode, DEV, mode=mode)
+    out = {}
+    for kernel, tile in (("exact", None), ("filter", None), ("filter", 1), ("filter", 2)):
+        monkeypatch.setenv("A3D_PROJECT_KERNEL", kernel)
+        res = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, want_table=True, tile_cand=tile)
+        torch.cuda.synchronize()
+        out[(kernel, tile)] = [t.cpu().numpy().copy() for t in (res.proj_bits, res.proj_popc, res.proj_bbox,
+                                                                 res.inter_tab, res.best_cand)]
+    ref = out[("exact", None)]
+    assert ref[1].sum() > 0
+    for k, v in out.items():
+        for a, b in zip(v, ref):
+            assert np.array_equal(a, b), k

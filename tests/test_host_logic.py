@@ -213,3 +213,37 @@ def test_fast_rvalue_is_bit_equal_to_scipy():
             a = np.float64(sp(range(n), torch.from_numpy(y)).rvalue)
             b = np.float64(opt_utils._rvalue(y))
         assert (np.isnan(a) and np.isnan(b)) or a.tobytes() == b.tobytes(), (n, kind, a, b)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_plan_tiles_covers_every_candidate_once(seed):
+    """engine.plan_tiles: role-0 entries partition each job's candidates, no tile exceeds the shared-memory
+    limit, one role-1 entry per job, the grid fits the wave(s) it was planned for, and larger source masks
+    never get larger tiles."""
+    rng = np.random.RandomState(seed)
+    n = int(rng.randint(1, 9))
+    jobs = np.zeros(n, dtype=_lib.JOB_DTYPE)
+    jobs["n_cand"] = rng.randint(0, 120, size=n)
+    jobs["pcd_cap"] = (rng.randint(0, 60000, size=n) + 31) & ~31
+    jobs["cand_begin"] = np.cumsum(np.r_[0, jobs["n_cand"][:-1]])
+    max_tile = int(rng.randint(1, 7))
+    tile, tmap = engine.plan_tiles(jobs, max_tile)
+    if tmap is None:
+        assert tile == max_tile and int((-(-jobs["n_cand"].astype(np.int64) // max_tile)).sum()) + n > 148
+        return
+    assert tmap.dtype == np.int32 and tmap.shape[1] == 4 and len(tmap) <= 2 * 148
+    assert 1 <= tile <= max_tile and tmap[:, 2].max() == tile
+    sizes = {}
+    for j in range(n):
+        assert int(((tmap[:, 0] == j) & (tmap[:, 3] == 1)).sum()) == 1
+        r = tmap[(tmap[:, 0] == j) & (tmap[:, 3] == 0)]
+        r = r[np.argsort(r[:, 1])]
+        assert int(r[:, 2].sum()) == int(jobs["n_cand"][j])
+        assert r[:, 1].tolist() == np.cumsum(np.r_[0, r[:, 2]])[:-1].tolist()
+        if len(r):
+            assert r[:, 2].min() >= 1
+            sizes[j] = int(r[:, 2].max())
+    for a in sizes:
+        for b in sizes:
+            if jobs["pcd_cap"][a] > jobs["pcd_cap"][b] and jobs["n_cand"][a] >= tile and jobs["n_cand"][b] >= tile:
+                assert sizes[a] <= sizes[b] + 1
