@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -487,7 +488,11 @@ __device__ __forceinline__ int clamp_index(float v, float n_minus_1) {
     return __float2int_rz(c);
 }
 
-constexpr int kProjThreads = 1024;
+#ifndef A3D_PROJ_THREADS
+#define A3D_PROJ_THREADS 1024
+#endif
+constexpr int kProjThreads = A3D_PROJ_THREADS;      // 1024: one CTA per SM; 512: two, each with half the candidate slots
+constexpr int kProjCtasPerSm = 1024 / kProjThreads;
 constexpr int kProjPX = 8;
 
 // The reference's fp32 chain for one point and one candidate (kMode is a compile-time constant so the
@@ -653,7 +658,7 @@ constexpr float kMagic = 12582912.f;                 // 1.5 * 2^23: x + kMagic h
 // bits as they are (the constant part is folded into the base); every point issues its own RED, with an
 // all-zero operand when it is unproven.
 struct FilterConst {
-    float wmax, hmax, chx, chy, c0;                   // chx = -0.5 / wmax
+    float wmax, hmax, chx, chy, c0h;                  // chx = -0.5 / wmax; c0h = c0 - 0.5 (rounded up)
     int pitch4;
 };
 
@@ -661,6 +666,13 @@ template <bool kFull>
 __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjPX], const float (&ys)[kProjPX],
                                                         const float C, int nvalid, const float* __restrict__ h,
                                                         const FilterConst& fc, uint32_t cm) {
+#ifdef A3D_FILTER_STATS
+    atomicAdd(&g_filter_stats[0], (unsigned long long)(kFull ? 8 : nvalid));
+    if (h[10] != 0.f) {
+        atomicAdd(&g_filter_stats[1], (unsigned long long)(kFull ? 8 : nvalid));
+        atomicAdd(&g_filter_stats[2], (unsigned long long)(kFull ? 8 : nvalid));
+    }
+#endif
     if (h[10] != 0.f) return 0u;                       // exact-only candidate: handled by the straight-line chain
     const float h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3], h4 = h[4], h5 = h[5], h6 = h[6], h7 = h[7], h8 = h[8];
     const float ce = __fadd_ru(C, h[9]);
@@ -680,10 +692,10 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
         asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(sy) : "f"(Vq), "f"(r), "f"(fc.chy));
         const float tx = fmaf(sx, fc.wmax, kMagic), ty = fmaf(sy, fc.hmax, kMagic);
         const float dx = fmaf(sx, fc.wmax, -__fsub_rn(tx, kMagic)), dy = fmaf(sy, fc.hmax, -__fsub_rn(ty, kMagic));
-        const float thr = __fsub_rn(0.5f, fmaf(ce, fabsf(r), fc.c0));
+        const float neg_thr = fmaf(ce, fabsf(r), fc.c0h);         // eps - 0.5
         // proven only if both fractional parts keep more than eps from the integer boundaries (a NaN or
         // infinite eps fails the comparison)
-        const uint32_t one = (fabsf(dx) <= thr && fabsf(dy) <= thr) ? 1u : 0u;
+        const uint32_t one = (fabsf(dx) <= -neg_thr && fabsf(dy) <= -neg_thr) ? 1u : 0u;
         const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
         red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
         proven += one << k;
@@ -733,7 +745,7 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
     fc.wmax = wmax; fc.hmax = hmax; fc.pitch4 = pitch4;
     fc.chx = -0.5f / wmax; fc.chy = -0.5f / hmax;
     // (Dm + 1) (2^-22 + 6 * 2^-24) + 2^-24 Dm, rounded up: reciprocal, scaled clamp and division terms
-    fc.c0 = __fmul_ru(__fadd_ru(__fmul_ru(__fadd_ru(Dm, 1.f), 5.9604645e-7f), __fmul_ru(Dm, 5.9604645e-8f)), 1.0001f);
+    fc.c0h = __fadd_ru(__fmul_ru(__fadd_ru(__fmul_ru(__fadd_ru(Dm, 1.f), 5.9604645e-7f), __fmul_ru(Dm, 5.9604645e-8f)), 1.0001f), -0.5f);
     const uint32_t masks_s = (uint32_t)__cvta_generic_to_shared(masks);
     const int nitems = (npts + kProjPX - 1) / kProjPX;
     // C: the largest coefficient of the item's points (neighbouring pixels: nearly equal); unwritten slots of
@@ -771,18 +783,32 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
                                     wmax, hmax, pitch4, masks_s, words4);
         }
     }
-    // last, partial round: (item, candidate) pairs dealt out one by one (see splat_job)
+    // last, partial round: its items are dealt out in (item, group of g candidates) units so that all threads
+    // finish together; g is the largest group size that does not lengthen the round (a group shares one
+    // load of the item and one exact list)
     const int tail = nitems - nfull;
-    for (int u = threadIdx.x; u < tail * nc; u += kProjThreads) {
-        const int c = u / tail, item = nfull + (u - c * tail);
-        float xs[kProjPX], ys[kProjPX], C;
-        const int nvalid = min(kProjPX, npts - item * kProjPX);
-        load_item(item, xs, ys, C, nvalid);
-        const uint32_t unc = nvalid >= kProjPX
-            ? splat_points_filter<true>(xs, ys, C, kProjPX, hf + kHF * c, fc, masks_s + (uint32_t)(c * words4))
-            : splat_points_filter<false>(xs, ys, C, nvalid, hf + kHF * c, fc, masks_s + (uint32_t)(c * words4));
-        splat_exact_list<kMode>((unsigned long long)unc, c, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f,
-                                cam.cx, cam.cy, wmax, hmax, pitch4, masks_s, words4);
+    if (tail > 0) {
+        int g = 1, best = 0x7fffffff;
+        for (int t = 1; t <= min(nc, 8); ++t) {
+            const int rounds = (tail * ((nc + t - 1) / t) + kProjThreads - 1) / kProjThreads;
+            if (rounds * t <= best) { best = rounds * t; g = t; }
+        }
+        const int ngroups = (nc + g - 1) / g;
+        for (int u = threadIdx.x; u < tail * ngroups; u += kProjThreads) {
+            const int grp = u / tail, item = nfull + (u - grp * tail);
+            const int cb = grp * g, ce = min(nc, cb + g);
+            float xs[kProjPX], ys[kProjPX], C;
+            const int nvalid = min(kProjPX, npts - item * kProjPX);
+            load_item(item, xs, ys, C, nvalid);
+            unsigned long long todo = 0;
+            for (int c = cb; c < ce; ++c) {
+                const uint32_t unc = splat_points_filter<false>(xs, ys, C, nvalid, hf + kHF * c, fc,
+                                                                masks_s + (uint32_t)(c * words4));
+                todo |= (unsigned long long)unc << (8 * (c - cb));
+            }
+            splat_exact_list<kMode>(todo, cb, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy,
+                                    wmax, hmax, pitch4, masks_s, words4);
+        }
     }
 }
 
@@ -793,7 +819,7 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
 // tiles), which runs the straight-line reference chain on them — unless the job has more of them than
 // one CTA holds, in which case every tile keeps its own.
 template <bool kFilter>
-__global__ void __launch_bounds__(kProjThreads, 1)
+__global__ void __launch_bounds__(kProjThreads, kProjCtasPerSm)
 k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int tiles_per_job,
           const float* __restrict__ xform, const int32_t* __restrict__ src_bbox, const float* __restrict__ pcd,
           const int32_t* __restrict__ pcd_count, const float* __restrict__ hom, const int4* __restrict__ tile_map,
@@ -829,7 +855,9 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
     {
         uint4* m4 = reinterpret_cast<uint4*>(masks);
         const int n4 = (nc * words) >> 2;
+#ifndef A3D_X_NOZERO
         for (int i = threadIdx.x; i < n4; i += kProjThreads) m4[i] = make_uint4(0, 0, 0, 0);
+#endif
         if (!extra) {
             const float* gx = xform + (size_t)(job.cand_begin + c0) * 12;
             for (int i = threadIdx.x; i < nc * 12; i += kProjThreads) xf[i] = gx[i];
@@ -870,11 +898,12 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
                     for (int i = 0; i < 12; ++i) xf[12 * slot + i] = xform[(size_t)(job.cand_begin + c) * 12 + i];
                 }
             nc = nflag;
+            __syncthreads();          // the slots' transforms and candidate ids
         } else if (moved) {
+            // (read again only after the barrier that ends the splat)
             for (int i = threadIdx.x; i < nc; i += kProjThreads)
                 if (hf[kHF * i + 10] != 0.f) gid[i] = -1;
         }
-        __syncthreads();
     }
     if (npts > 0) {
         if (kFilter && !extra) {
@@ -914,8 +943,14 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
             int row = row0, col = col0;
             for (int i = threadIdx.x; i < n4; i += kProjThreads) {
                 const uint4 v = s4[i];
+#ifndef A3D_X_NOSTORE
                 d4[i] = v;
+#endif
+#ifndef A3D_X_NOSTAT
                 if (v.x | v.y | v.z | v.w) {
+#else
+                if (v.x == 0x12345678u) {
+#endif
                     s.popc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
                     s.rmin = min(s.rmin, row);
                     s.rmax = max(s.rmax, row);
@@ -1892,6 +1927,13 @@ int device_smem_optin() {
     return v;
 }
 
+int device_sm_count() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return v;
+}
+
 size_t project_smem_bytes(int H, int pitch, int tile) {
     return (size_t)tile * H * pitch * 4 + (size_t)tile * 12 * 4 + (size_t)tile * 5 * 4 + (size_t)tile * kHF * 4 +
            (size_t)tile * 4;
@@ -1948,6 +1990,73 @@ int a3d_debug_filter_stats(unsigned long long* out4, int reset) {
 const char* a3d_last_error_string(void) { return g_err; }
 
 int a3d_pitch_words(int W) { return W > 0 ? pitch_words(W) : 0; }
+
+// Host-side planner of projection CTAs for grids of about one wave (see include/a3d.h).  Cost model in
+// point units, from the ncu instruction counts of k_project<filter>: a CTA costs
+// kPlanFixed + tile * (kPlanPerCand + points); the job's extra CTA kPlanFixed + kPlanPerCand + 2.5 points.
+int a3d_plan_tiles(const a3d_job_t* jobs_host, int n_jobs, int tile_max, int sm_count, int32_t* tile_map_out,
+                   int cap_tiles, int* tile_cand_out) {
+    const double kPlanFixed = 21500.0, kPlanPerCand = 3000.0;
+    if (n_jobs < 0 || tile_max < 1 || sm_count < 1 || !tile_cand_out || (n_jobs > 0 && !jobs_host))
+        return fail(A3D_EINVAL, "a3d_plan_tiles: bad argument");
+    *tile_cand_out = tile_max;
+    if (n_jobs == 0) return 0;
+    long long min_ctas = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        if (jobs_host[j].n_cand < 0) return fail(A3D_EINVAL, "a3d_plan_tiles: job %d has n_cand < 0", j);
+        min_ctas += (jobs_host[j].n_cand + tile_max - 1) / tile_max;
+    }
+    const int waves = (min_ctas + n_jobs <= sm_count) ? 1 : 2;
+    if (min_ctas + n_jobs > (long long)waves * sm_count) return 0;           // several waves anyway: uniform tiles
+    const long long cap = (long long)waves * sm_count - n_jobs;
+    if (!tile_map_out || cap_tiles < waves * sm_count) return fail(A3D_EINVAL, "a3d_plan_tiles: tile_map_out too small");
+    auto cost = [&](int j) { return (double)jobs_host[j].pcd_cap + kPlanPerCand; };
+    auto tile_of = [&](int j, double w) {
+        const double t = floor(w / cost(j));
+        return t < 1.0 ? 1 : (t > tile_max ? tile_max : (int)t);
+    };
+    double lo = cost(0), hi = cost(0);
+    for (int j = 1; j < n_jobs; ++j) { lo = cost(j) < lo ? cost(j) : lo; hi = cost(j) > hi ? cost(j) : hi; }
+    hi *= tile_max;
+    for (int it = 0; it < 40; ++it) {                  // smallest per-CTA budget whose CTAs fit the wave(s)
+        const double mid = 0.5 * (lo + hi);
+        long long ctas = 0;
+        for (int j = 0; j < n_jobs; ++j) {
+            const int t = tile_of(j, mid);
+            ctas += (jobs_host[j].n_cand + t - 1) / t;
+        }
+        if (ctas <= cap) hi = mid; else lo = mid;
+    }
+    struct Row { double c; int32_t v[4]; };
+    Row* rows = (Row*)malloc(sizeof(Row) * (size_t)(cap + n_jobs));
+    if (!rows) return fail(A3D_EINVAL, "a3d_plan_tiles: out of memory");
+    int n = 0, tile_used = 1;
+    for (int j = 0; j < n_jobs; ++j) {
+        const int nc = jobs_host[j].n_cand;
+        if (nc == 0) continue;
+        const int t = tile_of(j, hi), k = (nc + t - 1) / t, base = nc / k, rem = nc % k;
+        int c = 0;
+        for (int i = 0; i < k; ++i) {
+            const int sz = base + (i < rem ? 1 : 0);
+            rows[n++] = {kPlanFixed + sz * cost(j), {j, c, sz, 0}};
+            c += sz;
+            tile_used = sz > tile_used ? sz : tile_used;
+        }
+    }
+    for (int j = 0; j < n_jobs; ++j)
+        rows[n++] = {kPlanFixed + kPlanPerCand + 2.5 * (double)jobs_host[j].pcd_cap, {j, 0, 0, 1}};
+    // most expensive first (stable: ties keep job / candidate order)
+    for (int i = 1; i < n; ++i) {
+        const Row r = rows[i];
+        int k = i - 1;
+        while (k >= 0 && rows[k].c < r.c) { rows[k + 1] = rows[k]; --k; }
+        rows[k + 1] = r;
+    }
+    for (int i = 0; i < n; ++i) memcpy(tile_map_out + 4 * (size_t)i, rows[i].v, sizeof(int32_t) * 4);
+    free(rows);
+    *tile_cand_out = tile_used;
+    return n;
+}
 
 int a3d_project_max_tile(int H, int W) {
     if (H <= 0 || W <= 0) return fail(A3D_EINVAL, "a3d_project_max_tile: bad shape %dx%d", H, W);
@@ -2063,10 +2172,18 @@ static int project_impl(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jo
         return fail(A3D_EINVAL, "a3d_project: null pointer");
     // A3D_PROJECT_KERNEL = exact | filter (default filter: homography + proven truncation, exact chain on
     // demand; identical results).  The filter packs source coordinates in 16 bits and needs hom_ws.
+    // Default: the filter kernel when the grid is more than two waves of CTAs; on smaller grids the per-CTA
+    // fixed work and the extra CTAs outweigh the cheaper pixels (C2, 124-148 CTAs: 46 us against 42 us).
     const char* env_proj = getenv("A3D_PROJECT_KERNEL");
-    const bool filter = !(env_proj && !strcmp(env_proj, "exact")) && cam->H <= 32768 && cam->W <= 32768 && hom_ws;
-    if (env_proj && !strcmp(env_proj, "filter") && !hom_ws)
-        return fail(A3D_EINVAL, "a3d_project: A3D_PROJECT_KERNEL=filter needs hom_ws");
+    const bool force_filter = env_proj && !strcmp(env_proj, "filter"), force_exact = env_proj && !strcmp(env_proj, "exact");
+    if (force_filter && !hom_ws) return fail(A3D_EINVAL, "a3d_project: A3D_PROJECT_KERNEL=filter needs hom_ws");
+    bool filter = !force_exact && cam->H <= 32768 && cam->W <= 32768 && hom_ws;
+    if (filter && !force_filter) {
+        const int mt = a3d_project_max_tile(cam->H, cam->W);
+        const int t = tile_cand > 0 ? tile_cand : (mt > 0 ? mt : 1);
+        const long long grid = tile_map ? n_tiles : (long long)n_jobs * ((max_cand + t - 1) / t);
+        filter = grid > 2LL * device_sm_count();
+    }
     const int max_tile = a3d_project_max_tile(cam->H, cam->W);
     if (max_tile < 0) return max_tile;
     if (tile_cand <= 0) tile_cand = max_tile;

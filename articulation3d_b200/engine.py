@@ -179,6 +179,22 @@ def plan_tiles(jobs: np.ndarray, max_tile: int, sm_count: int = 148, fixed: floa
     return int(tmap[:, 2].max()), tmap
 
 
+_plan_buf = {}
+
+
+def plan_tiles_native(jobs: np.ndarray, max_tile: int, sm_count: int = 148):
+    """``plan_tiles`` through the library's host planner (a3d_plan_tiles): same result, microseconds."""
+    lib = _lib.load()
+    buf = _plan_buf.get(sm_count)
+    if buf is None:
+        buf = _plan_buf[sm_count] = np.empty((2 * sm_count, 4), dtype=np.int32)
+    jobs = np.ascontiguousarray(jobs)
+    tile = C.c_int(0)
+    n = _lib.check(lib.a3d_plan_tiles(jobs.ctypes.data, len(jobs), max_tile, sm_count, buf.ctypes.data, len(buf),
+                                      C.byref(tile)), "a3d_plan_tiles")
+    return (tile.value, buf[:n].copy()) if n > 0 else (tile.value, None)
+
+
 @dataclass
 class JobBatch:
     """Host description of one pass (numpy, ready for a single H2D each)."""
@@ -250,7 +266,7 @@ class DeviceBatch:
         self._plans = {}
         plan = None
         if cfg is not None and os.environ.get("A3D_TILE_PLAN") != "uniform":
-            plan = plan_tiles(batch.jobs, max_tile(cfg))
+            plan = plan_tiles_native(batch.jobs, max_tile(cfg))
             if plan[1] is None:
                 plan = (choose_tile(cfg, int(batch.xform.shape[0]), batch.n_jobs), None)
             self._plans[(cfg.height, cfg.width)] = plan
@@ -288,7 +304,7 @@ class DeviceBatch:
             if os.environ.get("A3D_TILE_PLAN") == "uniform":
                 self._plans[key] = (choose_tile(cfg, self.n_cand_total, self.n_jobs), None)
             else:
-                tile, tmap = plan_tiles(self.host.jobs, max_tile(cfg))
+                tile, tmap = plan_tiles_native(self.host.jobs, max_tile(cfg))
                 if tmap is None:
                     tile = choose_tile(cfg, self.n_cand_total, self.n_jobs)
                 else:

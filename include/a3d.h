@@ -95,6 +95,18 @@ int a3d_pitch_words(int W);
  * an HxW mask on the current device (>=1), or A3D_ELIMIT. */
 int a3d_project_max_tile(int H, int W);
 
+/* HOST helper: split of a pass into projection CTAs ("tile map" of a3d_project / a3d_pass) when the
+ * grid is about one wave, so that jobs whose source masks differ in size get tiles of different size
+ * and every CTA carries about the same number of (point, candidate) pairs.
+ *   jobs_host     [n_jobs] HOST copy of the jobs (n_cand and pcd_cap are read)
+ *   tile_max      a3d_project_max_tile(H, W);  sm_count  SMs of the device
+ *   tile_map_out  HOST [cap_tiles][4] int32, cap_tiles >= 2 * sm_count
+ *   tile_cand_out candidates per CTA to pass as tile_cand (the largest tile of the map)
+ * Returns the number of tiles written, 0 when the grid is several waves anyway (use uniform tiles of
+ * *tile_cand_out = tile_max and no map), or a negative A3D_E* code.                              */
+int a3d_plan_tiles(const a3d_job_t* jobs_host, int n_jobs, int tile_max, int sm_count,
+                   int32_t* tile_map_out, int cap_tiles, int* tile_cand_out);
+
 /* (a7/a8 input stage) threshold + bit-pack.  Replaces the per-visit
  * `(pred_mask > 0.5)` of opt_utils.py:471-473 and `pred_mask.nonzero()` of :409.
  *   src      [n][H][W] of dtype (A3D_F32 | A3D_U8), contiguous

@@ -17,6 +17,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["exact", "filter"])
+def projection_kernel(request, monkeypatch):
+    """Every test of this module runs with both projection kernels (the library's default picks one from
+    the grid size): the reference chain for every point, and the homography filter with proven truncation."""
+    monkeypatch.setenv("A3D_PROJECT_KERNEL", request.param)
+    return request.param
+
+
 def _unpack(bits: torch.Tensor, W: int) -> np.ndarray:
     """(n,H,pitch) int32 device -> (n,H,W) bool numpy"""
     b = bits.cpu().numpy().view(np.uint32)

@@ -228,6 +228,11 @@ def test_plan_tiles_covers_every_candidate_once(seed):
     jobs["cand_begin"] = np.cumsum(np.r_[0, jobs["n_cand"][:-1]])
     max_tile = int(rng.randint(1, 7))
     tile, tmap = engine.plan_tiles(jobs, max_tile)
+    # the library's host planner (a3d_plan_tiles) is the same statement in C
+    tile_c, tmap_c = engine.plan_tiles_native(jobs, max_tile)
+    assert tile_c == tile and (tmap is None) == (tmap_c is None)
+    if tmap is not None:
+        assert np.array_equal(tmap, tmap_c)
     if tmap is None:
         assert tile == max_tile and int((-(-jobs["n_cand"].astype(np.int64) // max_tile)).sum()) + n > 148
         return

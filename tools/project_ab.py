@@ -27,6 +27,8 @@ pcd_count = torch.empty((db.n_jobs,), dtype=torch.int32, device=dev)
 hom_ws = torch.empty((nc, _lib.HOM_FLOATS), dtype=torch.float32, device=dev)
 cam = engine.camera_struct(cfg)
 tile, tmap = db.tile_plan(cfg)                      # A3D_TILE_PLAN=uniform: tiles of equal size
+if os.environ.get("AB_TILE"):
+    tile, tmap = int(os.environ["AB_TILE"]), None
 tmap_ptr, n_tiles = (tmap.data_ptr(), int(tmap.shape[0])) if tmap is not None else (None, 0)
 print("tile", tile, "planned tiles", n_tiles, "points per job", inp.batch.jobs["pcd_cap"][:8].tolist())
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -60,7 +60,7 @@ for f in sorted(os.listdir(G)):
         continue
     wl, k = m.groups()
     ncu_summary.main(os.path.join(G, f), os.path.join(P, f"{tag}_{wl}_{k}.txt"))
-    if k in ("k_project", "k_score", "k_score_mma"):
+    if k in ("k_project", "k_project_exact", "k_score", "k_score_mma"):
         traffic.setdefault(wl, {})[k] = dram_bytes(os.path.join(G, f))
         pipes.setdefault(wl, {})[k] = pipe_pcts(os.path.join(G, f))
 if traffic:
