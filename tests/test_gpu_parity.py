@@ -605,3 +605,55 @@ def test_filtered_projection_equals_exact_chain(mode, shape, monkeypatch):
     for k, v in out.items():
         for a, b in zip(v, ref):
             assert np.array_equal(a, b), k
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_filter_kernel_adversarial_geometry(seed, monkeypatch):
+    """Filter against exact chain where the error bound is under stress: grazing planes, planes a few
+    centimetres from the camera, pivots far off the surface so that points swing through w = 0 and behind
+    the camera, full-circle rotations, translations of metres, huge and tiny focal lengths, big masks.
+    Bit-identical projected masks, counts and boxes are required for every candidate."""
+    rng = np.random.RandomState(7000 + seed)
+    H, W = [(480, 640), (768, 1024), (120, 200)][seed % 3]
+    cfg = OptConfig.scaled(W, H) if seed % 2 == 0 else OptConfig(height=H, width=W,
+                                                                  focal_length=float(rng.choice([40.0, 517.97, 6000.0])))
+    n = 5
+    yy, xx = np.mgrid[0:H, 0:W]
+    masks = np.zeros((n, H, W), np.float32)
+    for i in range(n):
+        cy, cx = rng.uniform(0.2, 0.8) * H, rng.uniform(0.2, 0.8) * W
+        ry, rx = rng.uniform(0.1, 0.6) * H, rng.uniform(0.1, 0.6) * W
+        masks[i] = (np.abs(yy - cy) < ry) & (np.abs(xx - cx) < rx)
+    masks[1, ::2] = 0                                             # ragged rows
+    masks[2] *= (rng.rand(H, W) < 0.5)                            # salt and pepper
+    pool = engine.pack_masks(torch.from_numpy(masks).to(DEV))
+    specs = []
+    for j in range(10):
+        mode = j % 3
+        A = 24
+        ax = rng.randn(A, 3)
+        ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+        ang = rng.uniform(-np.pi, np.pi, A) * (1e-3 if j == 3 else 1.0)     # job 3: rotations of a milliradian
+        xf = np.zeros((A, 12), np.float32)
+        xf[:, :9] = geometry._axis_angle_to_matrix(torch.from_numpy(ax * ang[:, None])).to(torch.float32).numpy().reshape(A, 9)
+        xf[:, 9:] = (rng.randn(A, 3) * rng.choice([1e-3, 0.3, 5.0])).astype(np.float32)
+        kind = j % 5
+        normal = rng.randn(3)
+        if kind == 0:
+            normal[2] = 1e-3 * rng.randn()                         # grazing: the plane contains the viewing direction
+        elif kind == 1:
+            normal = np.array([0.0, 0.0, 1.0]) + 1e-4 * rng.randn(3)   # fronto-parallel
+        normal = (normal / np.linalg.norm(normal)).astype(np.float32)
+        offset = np.float32(rng.choice([0.02, 0.5, 2.0, 50.0]))
+        pivot = (rng.randn(3) * rng.choice([0.1, 3.0, 100.0])).astype(np.float32)
+        specs.append((int(rng.randint(n)), mode, normal, float(offset), pivot, xf, [0]))
+    batch = engine.build_batch(*zip(*specs), pool.source_points)
+    out = {}
+    for kernel in ("exact", "filter"):
+        monkeypatch.setenv("A3D_PROJECT_KERNEL", kernel)
+        res = engine.run_pass(cfg, pool, engine.DeviceBatch(batch, DEV))
+        torch.cuda.synchronize()
+        out[kernel] = [t.cpu().numpy().copy() for t in (res.proj_bits, res.proj_popc, res.proj_bbox, res.best_inter)]
+    for a, b in zip(out["exact"], out["filter"]):
+        assert np.array_equal(a, b)
+    assert out["exact"][1].max() > 0
