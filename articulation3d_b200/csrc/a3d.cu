@@ -338,6 +338,7 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
     pdl_launch_dependents();
     const a3d_job_t job = jobs[blockIdx.x];
     if (threadIdx.x == 0) tmax_s = 0;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) pcd_count[gridDim.x] = 0;   // work counter of k_project_p
     const int pitch = cam.pitch;
     const int32_t* sb = src_bbox + 4 * (size_t)job.src_mask;
     const int r0 = sb[0], r1 = sb[1], w0 = sb[2], w1 = sb[3];
@@ -493,6 +494,9 @@ __device__ __forceinline__ int clamp_index(float v, float n_minus_1) {
 #endif
 constexpr int kProjThreads = A3D_PROJ_THREADS;      // 1024: one CTA per SM; 512: two, each with half the candidate slots
 constexpr int kProjCtasPerSm = 1024 / kProjThreads;
+#ifndef A3D_PROJECT_PERSISTENT_DEFAULT
+#define A3D_PROJECT_PERSISTENT_DEFAULT false
+#endif
 constexpr int kProjPX = 8;
 
 // The reference's fp32 chain for one point and one candidate (kMode is a compile-time constant so the
@@ -573,10 +577,10 @@ __device__ __forceinline__ void splat_points(const float (&X)[kProjPX], const fl
     mg.flush();
 }
 
-template <int kMode>
+template <int kMode, int kStride>
 __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, int npts, int nc,
                                           const float* __restrict__ pcd, const float* __restrict__ xf,
-                                          uint32_t* __restrict__ masks, int words) {
+                                          uint32_t* __restrict__ masks, int words, int tid) {
     const int cap = job.pcd_cap;
     const float* base = pcd + (size_t)A3D_PCD_PLANES * job.pcd_begin;
     const float4* X4 = reinterpret_cast<const float4*>(base);
@@ -602,8 +606,8 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
         }
     };
     // full rounds: every thread owns one 8-point item and applies all candidates of the tile to it
-    const int nfull = (nitems / kProjThreads) * kProjThreads;
-    for (int item = threadIdx.x; item < nfull; item += kProjThreads) {
+    const int nfull = (nitems / kStride) * kStride;
+    for (int item = tid; item < nfull; item += kStride) {
         float X[kProjPX], Y[kProjPX], Z[kProjPX];
         load_item(item, X, Y, Z);
         for (int c = 0; c < nc; ++c)
@@ -614,7 +618,7 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
     // threads finish together (with ~1.5 items per thread the plain loop left half the warps
     // idle for a whole round: 20 % of stall samples sat at the following barrier)
     const int tail = nitems - nfull;
-    for (int u = threadIdx.x; u < tail * nc; u += kProjThreads) {
+    for (int u = tid; u < tail * nc; u += kStride) {
         const int c = u / tail, item = nfull + (u - c * tail);
         float X[kProjPX], Y[kProjPX], Z[kProjPX];
         load_item(item, X, Y, Z);
@@ -728,11 +732,11 @@ __device__ __forceinline__ void splat_exact_list(unsigned long long todo, int c_
     }
 }
 
-template <int kMode>
+template <int kMode, int kStride>
 __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t& job, int npts, int nc,
                                                  const float* __restrict__ pcd, const float* __restrict__ xf,
                                                  const float* __restrict__ hf, int x0, int y0,
-                                                 uint32_t* __restrict__ masks, int words) {
+                                                 uint32_t* __restrict__ masks, int words, int tid) {
     const int cap = job.pcd_cap;
     const float* base = pcd + (size_t)A3D_PCD_PLANES * job.pcd_begin;
     const uint4* XY4 = reinterpret_cast<const uint4*>(base + 3 * (size_t)cap);
@@ -767,8 +771,8 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
     };
     // full rounds: every thread owns one 8-point item and applies the candidates of the tile to it, 8 at a
     // time (the unproven pairs of 8 candidates x 8 points fit one 64-bit mask)
-    const int nfull = (nitems / kProjThreads) * kProjThreads;
-    for (int item = threadIdx.x; item < nfull; item += kProjThreads) {
+    const int nfull = (nitems / kStride) * kStride;
+    for (int item = tid; item < nfull; item += kStride) {
         float xs[kProjPX], ys[kProjPX], C;
         load_item(item, xs, ys, C, kProjPX);
         for (int cb = 0; cb < nc; cb += 8) {
@@ -790,11 +794,11 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
     if (tail > 0) {
         int g = 1, best = 0x7fffffff;
         for (int t = 1; t <= min(nc, 8); ++t) {
-            const int rounds = (tail * ((nc + t - 1) / t) + kProjThreads - 1) / kProjThreads;
+            const int rounds = (tail * ((nc + t - 1) / t) + kStride - 1) / kStride;
             if (rounds * t <= best) { best = rounds * t; g = t; }
         }
         const int ngroups = (nc + g - 1) / g;
-        for (int u = threadIdx.x; u < tail * ngroups; u += kProjThreads) {
+        for (int u = tid; u < tail * ngroups; u += kStride) {
             const int grp = u / tail, item = nfull + (u - grp * tail);
             const int cb = grp * g, ce = min(nc, cb + g);
             float xs[kProjPX], ys[kProjPX], C;
@@ -812,127 +816,137 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
     }
 }
 
-// CTA roles.  k_project<false>: CTA = (job, tile of <= tile_cand candidates), the reference chain for
+// CTA roles.  k_project<false>: a worker = (job, tile of <= tile_cand candidates), the reference chain for
 // every point.  k_project<true>: the same tiles run the filter on their candidates; candidates flagged
 // exact-only by k_unproject (rotation by 0: every pixel maps onto an integer boundary) cost 3x a filtered
-// one, so they are taken out of the tiles and given to one EXTRA CTA per job (blockIdx % (tiles + 1) ==
-// tiles), which runs the straight-line reference chain on them — unless the job has more of them than
-// one CTA holds, in which case every tile keeps its own.
-template <bool kFilter>
-__global__ void __launch_bounds__(kProjThreads, kProjCtasPerSm)
-k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int tiles_per_job,
-          const float* __restrict__ xform, const int32_t* __restrict__ src_bbox, const float* __restrict__ pcd,
-          const int32_t* __restrict__ pcd_count, const float* __restrict__ hom, const int4* __restrict__ tile_map,
-          uint32_t* __restrict__ proj_bits, int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int nflag_s, nlist_s;
-    int jid, c0, want;
-    bool extra;
-    if (tile_map) {                   // caller-planned tiles: {job, first candidate, count, 1 = the job's extra CTA}
-        const int4 t = tile_map[blockIdx.x];
-        jid = t.x; c0 = t.y; want = min(t.z, tile_cand); extra = t.w != 0;
-        if (extra && !kFilter) return;
-    } else {
-        const int ctas_per_job = tiles_per_job + (kFilter ? 1 : 0);
-        jid = blockIdx.x / ctas_per_job;
-        const int tile_id = blockIdx.x - jid * ctas_per_job;
-        extra = kFilter && tile_id == tiles_per_job;
-        c0 = tile_id * tile_cand; want = tile_cand;
-    }
-    const a3d_job_t job = jobs[jid];
-    if (extra) c0 = 0;
-    int nc = extra ? min(tile_cand, job.n_cand) : min(want, job.n_cand - c0);   // slots in use
-    if (nc <= 0 || c0 < 0) return;
+// one, so they are taken out of the tiles and given to one EXTRA worker per job, which runs the
+// straight-line reference chain on them — unless the job has more of them than one worker holds, in which
+// case every tile keeps its own.
+//
+// A worker is kStride threads with their own candidate slots in shared memory and their own barrier:
+// the whole CTA (k_project: 1024 threads, one tile per CTA) or half of it (k_project_p: two groups of 512
+// threads that fetch tiles from a global counter until none is left — while one group sits in the load
+// latencies of its prologue, the barrier at the end of its splat or its write-out, the other one computes).
+struct ProjSmem {
+    uint32_t* masks;   // [slots][words]
+    float* xf;         // [slots][12]
+    int* red;          // [slots][5]
+    float* hf;         // [slots][kHF]   (filter only)
+    int* gid;          // [slots] candidate of the slot, -1 = not mine
+    int* ctl;          // [2] nflag, nlist
+};
 
+template <int kStride>
+__device__ __forceinline__ void worker_sync(int barrier_id) {
+    if (kStride == kProjThreads) __syncthreads();
+    else if (barrier_id == 1) asm volatile("bar.sync 1, %0;" ::"n"(kStride) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(kStride) : "memory");
+}
+
+template <bool kFilter, int kStride>
+__device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& job, int jid, int c0, int want, bool extra,
+                                             int slots, const float* __restrict__ xform,
+                                             const int32_t* __restrict__ src_bbox, const float* __restrict__ pcd,
+                                             const int32_t* __restrict__ pcd_count, const float* __restrict__ hom,
+                                             uint32_t* __restrict__ proj_bits, int32_t* __restrict__ proj_popc,
+                                             int32_t* __restrict__ proj_bbox, const ProjSmem& sm, int tid, int bar,
+                                             bool first) {
+    if (extra) c0 = 0;
+    int nc = extra ? min(slots, job.n_cand) : min(want, job.n_cand - c0);   // slots in use
+    if (nc <= 0 || c0 < 0) {
+        if (first) { pdl_wait(); pdl_launch_dependents(); }
+        return;
+    }
     const int H = cam.H, pitch = cam.pitch;
     const int words = H * pitch;
-    uint32_t* masks = smem;                                        // [tile_cand][words]
-    float* xf = reinterpret_cast<float*>(smem + (size_t)tile_cand * words);   // [tile_cand][12]
-    int* red = reinterpret_cast<int*>(xf + tile_cand * 12);        // [tile_cand][5]
-    float* hf = reinterpret_cast<float*>(red + tile_cand * 5);     // [tile_cand][kHF]  (filter only)
-    int* gid = reinterpret_cast<int*>(hf + tile_cand * kHF);       // [tile_cand] candidate of the slot, -1 = not mine
-
+    uint32_t* masks = sm.masks;
+    float* xf = sm.xf;
+    int* red = sm.red;
+    float* hf = sm.hf;
+    int* gid = sm.gid;
     {
         uint4* m4 = reinterpret_cast<uint4*>(masks);
         const int n4 = (nc * words) >> 2;
-#ifndef A3D_X_NOZERO
-        for (int i = threadIdx.x; i < n4; i += kProjThreads) m4[i] = make_uint4(0, 0, 0, 0);
-#endif
+        for (int i = tid; i < n4; i += kStride) m4[i] = make_uint4(0, 0, 0, 0);
         if (!extra) {
             const float* gx = xform + (size_t)(job.cand_begin + c0) * 12;
-            for (int i = threadIdx.x; i < nc * 12; i += kProjThreads) xf[i] = gx[i];
+            for (int i = tid; i < nc * 12; i += kStride) xf[i] = gx[i];
         }
-        for (int i = threadIdx.x; i < nc; i += kProjThreads) {
+        for (int i = tid; i < nc; i += kStride) {
             red[5 * i + 0] = 0; red[5 * i + 1] = 0x7fffffff; red[5 * i + 2] = -1;
             red[5 * i + 3] = 0x7fffffff; red[5 * i + 4] = -1;
             gid[i] = extra ? -1 : c0 + i;
         }
-        if (threadIdx.x == 0) { nflag_s = 0; nlist_s = 0; }
+        if (tid == 0) { sm.ctl[0] = 0; sm.ctl[1] = 0; }
     }
-    __syncthreads();
-    pdl_wait();                       // the point clouds of k_unproject (the shared-memory tile is already zeroed)
-    pdl_launch_dependents();
+    worker_sync<kStride>(bar);
+    if (first) {
+        pdl_wait();                   // the point clouds of k_unproject (the shared-memory tile is already zeroed)
+        pdl_launch_dependents();
+    }
     const int npts = pcd_count[jid];
     int x0 = 0, y0 = 0;
-    bool moved = false;               // exact-only candidates of this job live in the extra CTA
+    bool moved = false;               // exact-only candidates of this job live in the extra worker
     if (kFilter) {
         const int32_t* sb = src_bbox + 4 * (size_t)job.src_mask;
         y0 = (sb[0] + sb[1]) >> 1;
         x0 = 16 * (sb[2] + sb[3] + 1);
         const float* gh = hom + (size_t)job.cand_begin * kHF;                 // written by k_unproject
         int mine = 0;
-        for (int c = threadIdx.x; c < job.n_cand; c += kProjThreads) mine += (npts > 0 && gh[(size_t)c * kHF + 10] != 0.f) ? 1 : 0;
+        for (int c = tid; c < job.n_cand; c += kStride) mine += (npts > 0 && gh[(size_t)c * kHF + 10] != 0.f) ? 1 : 0;
         mine = __reduce_add_sync(0xffffffffu, mine);
-        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&nflag_s, mine);
+        if ((tid & 31) == 0 && mine) atomicAdd(&sm.ctl[0], mine);
         if (!extra)
-            for (int i = threadIdx.x; i < nc * kHF; i += kProjThreads) hf[i] = gh[(size_t)c0 * kHF + i];
-        __syncthreads();
-        const int nflag = nflag_s;
-        moved = nflag > 0 && nflag <= tile_cand;
+            for (int i = tid; i < nc * kHF; i += kStride) hf[i] = gh[(size_t)c0 * kHF + i];
+        worker_sync<kStride>(bar);
+        const int nflag = sm.ctl[0];
+        moved = nflag > 0 && nflag <= slots;
         if (extra) {
             if (!moved) return;
-            for (int c = threadIdx.x; c < job.n_cand; c += kProjThreads)
+            for (int c = tid; c < job.n_cand; c += kStride)
                 if (gh[(size_t)c * kHF + 10] != 0.f) {
-                    const int slot = atomicAdd(&nlist_s, 1);
+                    const int slot = atomicAdd(&sm.ctl[1], 1);
                     gid[slot] = c;
                     for (int i = 0; i < 12; ++i) xf[12 * slot + i] = xform[(size_t)(job.cand_begin + c) * 12 + i];
                 }
             nc = nflag;
-            __syncthreads();          // the slots' transforms and candidate ids
+            worker_sync<kStride>(bar);          // the slots' transforms and candidate ids
         } else if (moved) {
             // (read again only after the barrier that ends the splat)
-            for (int i = threadIdx.x; i < nc; i += kProjThreads)
+            for (int i = tid; i < nc; i += kStride)
                 if (hf[kHF * i + 10] != 0.f) gid[i] = -1;
         }
+    } else if (extra) {
+        return;
     }
     if (npts > 0) {
         if (kFilter && !extra) {
-            if (job.mode == A3D_MODE_SEQ) splat_job_filter<A3D_MODE_SEQ>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words);
-            else if (job.mode == A3D_MODE_COMPOSED) splat_job_filter<A3D_MODE_COMPOSED>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words);
-            else splat_job_filter<A3D_MODE_TRANSLATE>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words);
-            if (!moved && nflag_s > 0) {
-                // more exact-only candidates than the extra CTA holds: each tile runs its own
+            if (job.mode == A3D_MODE_SEQ) splat_job_filter<A3D_MODE_SEQ, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid);
+            else if (job.mode == A3D_MODE_COMPOSED) splat_job_filter<A3D_MODE_COMPOSED, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid);
+            else splat_job_filter<A3D_MODE_TRANSLATE, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid);
+            if (!moved && sm.ctl[0] > 0) {
+                // more exact-only candidates than the extra worker holds: each tile runs its own
                 for (int c = 0; c < nc; ++c) {
                     if (hf[kHF * c + 10] == 0.f) continue;
-                    if (job.mode == A3D_MODE_SEQ) splat_job<A3D_MODE_SEQ>(cam, job, npts, 1, pcd, xf + 12 * c, masks + (size_t)c * words, words);
-                    else if (job.mode == A3D_MODE_COMPOSED) splat_job<A3D_MODE_COMPOSED>(cam, job, npts, 1, pcd, xf + 12 * c, masks + (size_t)c * words, words);
-                    else splat_job<A3D_MODE_TRANSLATE>(cam, job, npts, 1, pcd, xf + 12 * c, masks + (size_t)c * words, words);
+                    if (job.mode == A3D_MODE_SEQ) splat_job<A3D_MODE_SEQ, kStride>(cam, job, npts, 1, pcd, xf + 12 * c, masks + (size_t)c * words, words, tid);
+                    else if (job.mode == A3D_MODE_COMPOSED) splat_job<A3D_MODE_COMPOSED, kStride>(cam, job, npts, 1, pcd, xf + 12 * c, masks + (size_t)c * words, words, tid);
+                    else splat_job<A3D_MODE_TRANSLATE, kStride>(cam, job, npts, 1, pcd, xf + 12 * c, masks + (size_t)c * words, words, tid);
                 }
             }
         } else {
-            if (job.mode == A3D_MODE_SEQ) splat_job<A3D_MODE_SEQ>(cam, job, npts, nc, pcd, xf, masks, words);
-            else if (job.mode == A3D_MODE_COMPOSED) splat_job<A3D_MODE_COMPOSED>(cam, job, npts, nc, pcd, xf, masks, words);
-            else splat_job<A3D_MODE_TRANSLATE>(cam, job, npts, nc, pcd, xf, masks, words);
+            if (job.mode == A3D_MODE_SEQ) splat_job<A3D_MODE_SEQ, kStride>(cam, job, npts, nc, pcd, xf, masks, words, tid);
+            else if (job.mode == A3D_MODE_COMPOSED) splat_job<A3D_MODE_COMPOSED, kStride>(cam, job, npts, nc, pcd, xf, masks, words, tid);
+            else splat_job<A3D_MODE_TRANSLATE, kStride>(cam, job, npts, nc, pcd, xf, masks, words, tid);
         }
     }
-    __syncthreads();
+    worker_sync<kStride>(bar);
 
     // ---- stream the tile out, with popcount + bounding box per candidate ----------
     // (row, uint4 column) of a thread's elements advance by constants: no division in the loop; the
     // occupied word columns are collected as a bit mask (pitch <= 32 words)
     const int p4 = pitch >> 2, n4 = H * p4;
-    const int row0 = threadIdx.x / p4, col0 = threadIdx.x - row0 * p4;
-    const int drow = kProjThreads / p4, dcol = kProjThreads - drow * p4;
+    const int row0 = tid / p4, col0 = tid - row0 * p4;
+    const int drow = kStride / p4, dcol = kStride - drow * p4;
     for (int c = 0; c < nc; ++c) {
         if (gid[c] < 0) continue;
         const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
@@ -941,16 +955,10 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
         if (pitch <= 32) {
             uint32_t colmask = 0;
             int row = row0, col = col0;
-            for (int i = threadIdx.x; i < n4; i += kProjThreads) {
+            for (int i = tid; i < n4; i += kStride) {
                 const uint4 v = s4[i];
-#ifndef A3D_X_NOSTORE
                 d4[i] = v;
-#endif
-#ifndef A3D_X_NOSTAT
                 if (v.x | v.y | v.z | v.w) {
-#else
-                if (v.x == 0x12345678u) {
-#endif
                     s.popc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
                     s.rmin = min(s.rmin, row);
                     s.rmax = max(s.rmax, row);
@@ -963,7 +971,7 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
             colmask = __reduce_or_sync(0xffffffffu, colmask);
             if (colmask) { s.cmin = __ffs(colmask) - 1; s.cmax = 31 - __clz(colmask); }
         } else {
-            for (int i = threadIdx.x; i < n4; i += kProjThreads) {
+            for (int i = tid; i < n4; i += kStride) {
                 const uint4 v = s4[i];
                 d4[i] = v;
                 if (v.x | v.y | v.z | v.w) {
@@ -977,11 +985,95 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
         }
         stat_block_accumulate(red + 5 * c, s);
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < nc; c += kProjThreads) {
+    worker_sync<kStride>(bar);
+    for (int c = tid; c < nc; c += kStride) {
         if (gid[c] < 0) continue;
         const size_t g = (size_t)job.cand_begin + gid[c];
         stat_store(red + 5 * c, proj_popc + g, proj_bbox + 4 * g);
+    }
+}
+
+// worker id -> (job, first candidate, candidates, extra): from the caller's tile map, else uniform tiles
+template <bool kFilter>
+__device__ __forceinline__ void decode_work(int w, const int4* __restrict__ tile_map, int tile_cand, int tiles_per_job,
+                                            int& jid, int& c0, int& want, bool& extra) {
+    if (tile_map) {                   // caller-planned tiles: {job, first candidate, count, 1 = the job's extra worker}
+        const int4 t = tile_map[w];
+        jid = t.x; c0 = t.y; want = min(t.z, tile_cand); extra = t.w != 0;
+    } else {
+        const int per_job = tiles_per_job + (kFilter ? 1 : 0);
+        jid = w / per_job;
+        const int tile_id = w - jid * per_job;
+        extra = kFilter && tile_id == tiles_per_job;
+        c0 = tile_id * tile_cand; want = tile_cand;
+    }
+}
+
+template <bool kFilter>
+__global__ void __launch_bounds__(kProjThreads, kProjCtasPerSm)
+k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int tiles_per_job,
+          const float* __restrict__ xform, const int32_t* __restrict__ src_bbox, const float* __restrict__ pcd,
+          const int32_t* __restrict__ pcd_count, const float* __restrict__ hom, const int4* __restrict__ tile_map,
+          uint32_t* __restrict__ proj_bits, int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int ctl[2];
+    int jid, c0, want;
+    bool extra;
+    decode_work<kFilter>(blockIdx.x, tile_map, tile_cand, tiles_per_job, jid, c0, want, extra);
+    const a3d_job_t job = jobs[jid];
+    const int words = cam.H * cam.pitch;
+    ProjSmem sm;
+    sm.masks = smem;
+    sm.xf = reinterpret_cast<float*>(smem + (size_t)tile_cand * words);
+    sm.red = reinterpret_cast<int*>(sm.xf + tile_cand * 12);
+    sm.hf = reinterpret_cast<float*>(sm.red + tile_cand * 5);
+    sm.gid = reinterpret_cast<int*>(sm.hf + tile_cand * kHF);
+    sm.ctl = ctl;
+    project_tile<kFilter, kProjThreads>(cam, job, jid, c0, want, extra, tile_cand, xform, src_bbox, pcd, pcd_count, hom,
+                                        proj_bits, proj_popc, proj_bbox, sm, threadIdx.x, 0, true);
+}
+
+// Persistent variant: gridDim.x <= SM count CTAs of two 512-thread groups; each group owns tile_cand
+// candidate slots and takes the next tile from *work_counter (zeroed by k_unproject) until n_work are done.
+constexpr int kGroupThreads = kProjThreads / 2;
+
+template <bool kFilter>
+__global__ void __launch_bounds__(kProjThreads, 1)
+k_project_p(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int tiles_per_job, int n_work,
+            int* __restrict__ work_counter, const float* __restrict__ xform, const int32_t* __restrict__ src_bbox,
+            const float* __restrict__ pcd, const int32_t* __restrict__ pcd_count, const float* __restrict__ hom,
+            const int4* __restrict__ tile_map, uint32_t* __restrict__ proj_bits, int32_t* __restrict__ proj_popc,
+            int32_t* __restrict__ proj_bbox) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int ctl[2][2];
+    __shared__ int next_work[2];
+    const int g = threadIdx.x / kGroupThreads, tid = threadIdx.x - g * kGroupThreads;
+    const int words = cam.H * cam.pitch;
+    // per group: masks | xf | red | hf | gid, laid out as in k_project with tile_cand slots
+    const size_t group_words = ((size_t)tile_cand * (words + 12 + 5 + kHF + 1) + 3) & ~(size_t)3;
+    uint32_t* base = smem + (size_t)g * group_words;
+    ProjSmem sm;
+    sm.masks = base;
+    sm.xf = reinterpret_cast<float*>(base + (size_t)tile_cand * words);
+    sm.red = reinterpret_cast<int*>(sm.xf + tile_cand * 12);
+    sm.hf = reinterpret_cast<float*>(sm.red + tile_cand * 5);
+    sm.gid = reinterpret_cast<int*>(sm.hf + tile_cand * kHF);
+    sm.ctl = ctl[g];
+    const int bar = 1 + g;
+    pdl_wait();                       // the work counter and the point clouds of k_unproject
+    pdl_launch_dependents();
+    for (;;) {
+        if (tid == 0) next_work[g] = atomicAdd(work_counter, 1);
+        worker_sync<kGroupThreads>(bar);
+        const int w = next_work[g];
+        if (w >= n_work) break;
+        int jid, c0, want;
+        bool extra;
+        decode_work<kFilter>(w, tile_map, tile_cand, tiles_per_job, jid, c0, want, extra);
+        const a3d_job_t job = jobs[jid];
+        project_tile<kFilter, kGroupThreads>(cam, job, jid, c0, want, extra, tile_cand, xform, src_bbox, pcd, pcd_count,
+                                             hom, proj_bits, proj_popc, proj_bbox, sm, tid, bar, false);
+        worker_sync<kGroupThreads>(bar);        // the slots and next_work are free again
     }
 }
 
@@ -1934,9 +2026,16 @@ int device_sm_count() {
     return v;
 }
 
+// A3D_PROJECT_SCHED = cta | persistent: one tile per 1024-thread CTA, or persistent CTAs of two 512-thread
+// groups that fetch tiles from a counter (each group holds `tile` candidate slots)
+bool project_persistent() {
+    const char* e = getenv("A3D_PROJECT_SCHED");
+    return e ? !strcmp(e, "persistent") : A3D_PROJECT_PERSISTENT_DEFAULT;
+}
+
 size_t project_smem_bytes(int H, int pitch, int tile) {
-    return (size_t)tile * H * pitch * 4 + (size_t)tile * 12 * 4 + (size_t)tile * 5 * 4 + (size_t)tile * kHF * 4 +
-           (size_t)tile * 4;
+    const size_t group_words = ((size_t)tile * ((size_t)H * pitch + 12 + 5 + kHF + 1) + 3) & ~(size_t)3;
+    return group_words * 4 * (project_persistent() ? 2 : 1);
 }
 
 }  // namespace
@@ -2231,6 +2330,24 @@ static int project_impl(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jo
     } else if (filter) {
         nblocks += n_jobs;            // one extra CTA per job for its exact-only candidates
         if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_project: too many (job, tile) blocks");
+    }
+    if (project_persistent()) {
+        int* counter = pcd_count + n_jobs;           // zeroed by k_unproject
+        const int sms = device_sm_count();
+        const long long want_ctas = (nblocks + 1) / 2;
+        const unsigned grid = (unsigned)(want_ctas < sms ? want_ctas : sms);
+        if (filter) {
+            A3D_CUDA_TRY(cudaFuncSetAttribute(k_project_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            A3D_CUDA_TRY(launch(k_project_p<true>, dim3(grid), dim3(kProjThreads), smem, s, pdl, c, jobs, tile_cand,
+                                tiles_per_job, (int)nblocks, counter, xform, src_bbox, (const float*)pcd_ws,
+                                (const int32_t*)pcd_count, (const float*)hom_ws, tmap, proj_bits, proj_popc, proj_bbox));
+        } else {
+            A3D_CUDA_TRY(cudaFuncSetAttribute(k_project_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            A3D_CUDA_TRY(launch(k_project_p<false>, dim3(grid), dim3(kProjThreads), smem, s, pdl, c, jobs, tile_cand,
+                                tiles_per_job, (int)nblocks, counter, xform, src_bbox, (const float*)pcd_ws,
+                                (const int32_t*)pcd_count, (const float*)hom_ws, tmap, proj_bits, proj_popc, proj_bbox));
+        }
+        return A3D_OK;
     }
     if (filter) {
         A3D_CUDA_TRY(cudaFuncSetAttribute(k_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -405,7 +405,7 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
         proj_popc = ws.get("proj_popc", (nc,), torch.int32)
         proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
         pcd_ws = ws.get("pcd_ws", (max(_lib.PCD_PLANES * dbatch.pcd_total, 32),), torch.float32)
-        pcd_count = ws.get("pcd_count", (dbatch.n_jobs,), torch.int32)
+        pcd_count = ws.get("pcd_count", (dbatch.n_jobs + 1,), torch.int32)
         hom_ws = ws.get("hom_ws", (max(nc, 1), _lib.HOM_FLOATS), torch.float32)
         key_ws = ws.get("key_ws", (nt,), torch.int64)
         results = ws.get("results", (4, nt), torch.int32)          # one block -> one D2H

@@ -406,7 +406,7 @@ def _run_split(engine, inp, ws, evs):
     proj_popc = ws.get("proj_popc", (nc,), torch.int32)
     proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
     pcd_ws = ws.get("pcd_ws", (max(_lib.PCD_PLANES * db.pcd_total, 32),), torch.float32)
-    pcd_count = ws.get("pcd_count", (db.n_jobs,), torch.int32)
+    pcd_count = ws.get("pcd_count", (db.n_jobs + 1,), torch.int32)
     hom_ws = ws.get("hom_ws", (max(nc, 1), _lib.HOM_FLOATS), torch.float32)
     key_ws = ws.get("key_ws", (nt,), torch.int64)
     outs = [ws.get(n, (nt,), dt) for n, dt in (("best_cand", torch.int32), ("best_inter", torch.int32),

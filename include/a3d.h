@@ -134,7 +134,8 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W,
  *   xform      [n_cand_total][12] fp32: rows 0-2 of R (row-vector convention,
  *              p' = p*R), then t
  *   pcd_ws     workspace, A3D_PCD_PLANES * sum(pcd_cap) floats (planes of pcd_cap floats per job slice)
- *   pcd_count  workspace, [n_jobs] int32 (points actually produced per job)
+ *   pcd_count  workspace, [n_jobs + 1] int32 (points actually produced per job; the last entry is the
+ *              work counter of the persistent projection kernel)
  *   hom_ws     workspace, [n_cand_total][A3D_HOM_FLOATS] floats: per candidate the plane-induced
  *              homography source pixel -> projected pixel and its error bound, from which the
  *              filtered projection kernel takes every pixel it can PROVE equal to the reference

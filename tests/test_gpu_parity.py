@@ -594,8 +594,11 @@ def test_filtered_projection_equals_exact_chain(mode, shape, monkeypatch):
         else workloads.Workload("probe", "2 videos x 2 tracks x 12 frames, 144 candidates, 1024x768", 2, 2, 12, 144, 1024, 768)
     inp = workloads.build_pass(wl, 300 + mode, DEV, mode=mode)
     out = {}
-    for kernel, tile in (("exact", None), ("filter", None), ("filter", 1), ("filter", 2)):
-        monkeypatch.setenv("A3D_PROJECT_KERNEL", kernel)
+    for kernel, tile in (("exact", None), ("filter", None), ("filter", 1), ("filter", 2), ("filter/persistent", 1),
+                         ("exact/persistent", 1)):
+        # ".../persistent": CTAs of two 512-thread groups that fetch tiles from a counter (A3D_PROJECT_SCHED)
+        monkeypatch.setenv("A3D_PROJECT_KERNEL", kernel.split("/")[0])
+        monkeypatch.setenv("A3D_PROJECT_SCHED", "persistent" if "/" in kernel else "cta")
         res = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, want_table=True, tile_cand=tile)
         torch.cuda.synchronize()
         out[(kernel, tile)] = [t.cpu().numpy().copy() for t in (res.proj_bits, res.proj_popc, res.proj_bbox,

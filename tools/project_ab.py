@@ -23,7 +23,7 @@ proj_bits = torch.empty((nc, H, pitch), dtype=torch.int32, device=dev)
 proj_popc = torch.empty((nc,), dtype=torch.int32, device=dev)
 proj_bbox = torch.empty((nc, 4), dtype=torch.int32, device=dev)
 pcd_ws = torch.empty((max(_lib.PCD_PLANES * db.pcd_total, 32),), dtype=torch.float32, device=dev)
-pcd_count = torch.empty((db.n_jobs,), dtype=torch.int32, device=dev)
+pcd_count = torch.empty((db.n_jobs + 1,), dtype=torch.int32, device=dev)
 hom_ws = torch.empty((nc, _lib.HOM_FLOATS), dtype=torch.float32, device=dev)
 cam = engine.camera_struct(cfg)
 tile, tmap = db.tile_plan(cfg)                      # A3D_TILE_PLAN=uniform: tiles of equal size
@@ -62,4 +62,4 @@ for kernel in ("exact", "filter", "exact", "filter"):
     torch.cuda.synchronize()
     t = sorted(a.elapsed_time(b) for a, b in ev)
     print(f"{name} mode {mode} {kernel:6s}: median {t[len(t) // 2] * 1e3:8.1f} us  min {t[0] * 1e3:8.1f} us  "
-          f"results {'same' if same else 'DIFFERENT'} (points {int(pcd_count.sum())}, candidates {nc})", flush=True)
+          f"results {'same' if same else 'DIFFERENT'} (points {int(pcd_count[:-1].sum())}, candidates {nc})", flush=True)

@@ -1,5 +1,5 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel once, all three
-scoring kernels, odd resolution, RLE ingest, override_depth.
+scoring kernels, both projection kernels, odd resolution, RLE ingest, override_depth.
     compute-sanitizer --tool racecheck python tools/sanitize.py"""
 import os
 import random
@@ -13,8 +13,11 @@ from articulation3d_b200 import OptConfig, adapter, engine, opt_utils, rle, synt
 
 cfg = OptConfig.scaled(200, 150)
 preds, _ = synth.make_video(5, 2, 12, cfg, kinds=[0, 1])
-for kernel in ("ldg", "tma", "mma"):
+for kernel, proj, sched in (("ldg", "exact", "cta"), ("tma", "filter", "cta"), ("mma", "filter", "persistent")):
     os.environ["A3D_SCORE_KERNEL"] = kernel
+    os.environ["A3D_PROJECT_KERNEL"] = proj          # both projection kernels, both CTA schedulers
+    os.environ["A3D_PROJECT_SCHED"] = sched
+    engine._tile_cache.clear()                       # the largest tile depends on the scheduler
     p = synth.clone_preds(preds)
     random.seed(1)
     planes = opt_utils.track_planes(p, cfg)
