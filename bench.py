@@ -186,7 +186,10 @@ def measure_pass(wl, steps, warmup, dev, rank, world, dist, sample_clocks=True):
     from articulation3d_b200 import engine, workloads
 
     inp = workloads.build_pass(wl, seed0=2020 + 1000 * rank, device=dev)
-    ws = engine.Workspace(dev)
+    # two sets of pass buffers when ranks exchange results: the gather of step k reads the result block of
+    # step k in place while step k+1 writes the other set (no staging copy in the step)
+    wss = [engine.Workspace(dev) for _ in range(2 if world > 1 else 1)]
+    ws = wss[0]
     packed_bytes = inp.pool.bits.numel() * 4
     l2_bytes = 126 * 2 ** 20
     flush = None if packed_bytes > 2 * l2_bytes else torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
@@ -207,15 +210,15 @@ def measure_pass(wl, steps, warmup, dev, rank, world, dist, sample_clocks=True):
             flush.zero_()
         if evs:
             evs[0].record()
-        res = _run_split(engine, inp, ws, evs) if split else engine.run_pass(inp.cfg, inp.pool, inp.dbatch, ws)
+        b = step_no[0] & 1 if (world > 1 and not split) else 0
+        if world > 1 and not split and comm_done[b] is not None:
+            torch.cuda.current_stream().wait_event(comm_done[b])         # buffer set b free again
+        res = _run_split(engine, inp, ws, evs) if split else engine.run_pass(inp.cfg, inp.pool, inp.dbatch, wss[b])
         if world > 1 and not split:
-            b = step_no[0] & 1
-            if comm_done[b] is not None:
-                torch.cuda.current_stream().wait_event(comm_done[b])     # buffer b free again
-            rec = recs[b]
             if res.block is not None:
-                rec.copy_(res.block[:3])                  # one copy: the rows are contiguous in the result block
+                rec = res.block[:3]                       # the rows are contiguous in the result block
             else:
+                rec = recs[b]
                 rec[0], rec[1], rec[2] = res.best_cand, res.best_inter, res.best_union
             ready = torch.cuda.Event()
             ready.record()
