@@ -119,3 +119,40 @@ def test_opt_arti_tool_end_to_end(tmp_path):
         for r, p in zip(recs, ref):
             assert torch.equal(r["pred_rot_axis"], p.pred_rot_axis)
             assert [i["score"] for i in r["instances"]] == list(p.scores)
+
+
+def test_opt_arti_tool_prints_ap_before_and_after(tmp_path, capsys):
+    """--gt-json: the AP table of tools/opt_arti.py (evaluation.evaluate_for_arti_axis) before and after the
+    temporal optimisation, on a ground truth derived from the synthetic predictions themselves."""
+    import json
+    import re
+    from articulation3d_b200.axis import angle_offset_to_axis
+    from articulation3d_b200.tools import opt_arti
+    inp, out, gtp = str(tmp_path / "pred.pth"), str(tmp_path / "out"), str(tmp_path / "gt.json")
+    opt_arti.main(["--input", inp, "--output", out, "--synthetic", "1", "--tracks", "1", "--frames", "14",
+                   "--seed", "2021", "--device", DEV])
+    records = torch.load(inp, weights_only=False)
+    images, anns = [], []
+    for r in records:
+        images.append({"id": r["image_id"], "width": 640, "height": 480})
+        if not r["instances"]:
+            continue
+        ins = r["instances"][0]
+        x, y, w, h = ins["bbox"]
+        centre = torch.tensor([[x + w / 2, y + h / 2]], dtype=torch.float32)
+        line = angle_offset_to_axis(torch.as_tensor(r["pred_rot_axis"][:1]).float(), centre)[0].tolist()
+        cls = int(ins["category_id"])
+        anns.append({"id": len(anns) + 1, "image_id": r["image_id"], "category_id": cls + 1, "bbox": [x, y, w, h],
+                     "rot_axis": line if cls == 0 else None, "tran_axis": None, "normal": None})
+    json.dump({"images": images, "annotations": anns,
+               "categories": [{"id": 1, "name": "arti_rot"}, {"id": 2, "name": "arti_tran"}]}, open(gtp, "w"))
+    capsys.readouterr()
+    opt_arti.main(["--input", inp, "--output", out, "--device", DEV, "--gt-json", gtp])
+    text = capsys.readouterr().out
+    lines = [l for l in text.splitlines() if l.startswith("AP ")]
+    assert len(lines) == 2 and lines[0].startswith("AP before") and lines[1].startswith("AP after")
+    for l in lines:
+        vals = [float(v) for v in re.findall(r"- arti_\w+ ([0-9.]+)", l)]
+        assert vals and all(0.0 <= v <= 1.0 for v in vals)
+    # the boxes are the ground truth's own: detection AP of the untouched predictions is perfect
+    assert re.search(r"bbox - arti_\w+ 1\.0000", lines[0])
