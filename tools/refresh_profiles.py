@@ -113,7 +113,8 @@ for name in ("sanitizer_racecheck.txt", "sanitizer_memcheck.txt"):
         with open(src) as f, open(os.path.join(P, "r1_" + name), "w") as o:
             o.writelines(l for l in f if "Host Frame" not in l)
 for name, dst in (("bench_default.txt", "r1_bench_default.json"), ("bench_reference.txt", "r1_bench_reference.json"),
-                  ("bench_n2.txt", "r1_bench_n2.json"), ("bench_n4.txt", "r1_bench_n4.json")):
+                  ("bench_n2.txt", "r1_bench_n2.json"), ("bench_n4.txt", "r1_bench_n4.json"),
+                  ("bench_n8.txt", "r1_bench_n8.json")):
     src = os.path.join(G, name)
     if os.path.exists(src):
         lines = [l for l in open(src).read().splitlines() if l.startswith("{")]
