@@ -1,6 +1,10 @@
-"""Prototype (numpy, CPU) of the filtered projection: per candidate a plane-induced homography gives an
-approximate pixel coordinate; a rigorous running error bound decides whether truncating it is guaranteed
-to equal the reference's fp32 chain.  Prints max |q_fast - q_exact| / bound and the fallback rate."""
+"""Prototype (numpy, CPU) of the filtered projection, written before the kernel: per candidate a
+plane-induced homography gives an approximate pixel coordinate; a running error bound decides whether
+truncating it is guaranteed to equal the reference's fp32 chain (oracle/restated.py).  Prints the largest
+|q_fast - q_exact| / bound, the share of coordinates the bound cannot decide, and how many decided ones
+differ from the oracle (must be 0).  The kernel's bound has the same structure with slightly larger constants
+(saturating-FMA clamp, per-item coefficient): k_project<filter> in articulation3d_b200/csrc/a3d.cu.
+    python tools/filter_proto.py          # ~2 min"""
 import sys
 import numpy as np
 import torch
