@@ -252,3 +252,32 @@ def test_plan_tiles_covers_every_candidate_once(seed):
         for b in sizes:
             if jobs["pcd_cap"][a] > jobs["pcd_cap"][b] and jobs["n_cand"][a] >= tile and jobs["n_cand"][b] >= tile:
                 assert sizes[a] <= sizes[b] + 1
+
+
+def test_plan_tiles_argument_errors_and_degenerate_inputs():
+    """a3d_plan_tiles (host planner in the library): bad arguments give A3D_EINVAL with a message, empty and
+    many-wave inputs ask for uniform tiles (0 tiles, tile_cand = the largest tile)."""
+    lib = _lib.load()
+    tile = ctypes.c_int(-1)
+    jobs = np.zeros(3, dtype=_lib.JOB_DTYPE)
+    jobs["n_cand"] = [45, 45, 45]
+    jobs["pcd_cap"] = [1024, 2048, 4096]
+    out = np.zeros((2 * 148, 4), np.int32)
+    assert lib.a3d_plan_tiles(jobs.ctypes.data, 3, 6, 148, out.ctypes.data, 4, ctypes.byref(tile)) == -1     # map too small
+    assert b"tile_map_out" in lib.a3d_last_error_string()
+    assert lib.a3d_plan_tiles(jobs.ctypes.data, 3, 0, 148, out.ctypes.data, len(out), ctypes.byref(tile)) == -1   # tile_max < 1
+    assert lib.a3d_plan_tiles(None, 3, 6, 148, out.ctypes.data, len(out), ctypes.byref(tile)) == -1              # no jobs
+    bad = jobs.copy()
+    bad["n_cand"][1] = -5
+    assert lib.a3d_plan_tiles(bad.ctypes.data, 3, 6, 148, out.ctypes.data, len(out), ctypes.byref(tile)) == -1
+    assert lib.a3d_plan_tiles(jobs.ctypes.data, 0, 6, 148, out.ctypes.data, len(out), ctypes.byref(tile)) == 0 and tile.value == 6
+    many = np.zeros(400, dtype=_lib.JOB_DTYPE)
+    many["n_cand"] = 180
+    many["pcd_cap"] = 12000
+    assert lib.a3d_plan_tiles(many.ctypes.data, 400, 6, 148, out.ctypes.data, len(out), ctypes.byref(tile)) == 0 and tile.value == 6
+    # a valid small plan: every candidate once, one extra entry per job, most expensive first
+    n = lib.a3d_plan_tiles(jobs.ctypes.data, 3, 6, 148, out.ctypes.data, len(out), ctypes.byref(tile))
+    assert 3 < n <= 148 and 1 <= tile.value <= 6
+    m = out[:n]
+    assert int((m[:, 3] == 1).sum()) == 3 and int(m[m[:, 3] == 0][:, 2].sum()) == 135
+    assert m[0, 0] == 2                                    # the job with the largest source mask leads
