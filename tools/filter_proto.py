@@ -32,7 +32,7 @@ def homography(kinv, normal, off, A, b, f, cx, cy):
     return np.stack([Hu, Hv, Hw])
 
 
-def run(seed, mode, n_frames=20):
+def run(seed, mode, n_frames=20, frame_step=5, quiet=False):
     cfg = R_.OracleConfig()
     preds, _ = synth.make_video(seed, 3, n_frames, kinds=[0, 1, 0])
     kinv = cfg.K_inv()
@@ -40,7 +40,7 @@ def run(seed, mode, n_frames=20):
     Wd, Hd = cfg.width, cfg.height
     Dmax, cmax = max(Wd, Hd), max(cx, cy)
     stats = dict(n=0, unc=0, maxratio=0.0, wrong=0, eps=[])
-    for t in range(0, n_frames, 5):
+    for t in range(0, n_frames, frame_step):
         p = preds[t]
         for b_id in range(len(p.pred_boxes)):
             translation = mode == "translate"
@@ -120,8 +120,10 @@ def run(seed, mode, n_frames=20):
                         ratio = np.abs(qf[inr].astype(np.float64) - qe[inr].astype(np.float64)) / eps[inr]
                         stats["maxratio"] = max(stats["maxratio"], float(ratio.max()))
                 stats["eps"].append(float(np.median(eps)))
-    print(f"seed {seed} mode {mode}: coords {stats['n']}, uncertain {stats['unc'] / stats['n']:.5f}, "
-          f"wrong-certified {stats['wrong']}, max |dq|/eps {stats['maxratio']:.4f}, median eps {np.median(stats['eps']):.2e}")
+    if not quiet:
+        print(f"seed {seed} mode {mode}: coords {stats['n']}, uncertain {stats['unc'] / stats['n']:.5f}, "
+              f"wrong-certified {stats['wrong']}, max |dq|/eps {stats['maxratio']:.4f}, median eps {np.median(stats['eps']):.2e}")
+    return stats
 
 
 if __name__ == "__main__":
