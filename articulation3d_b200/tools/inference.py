@@ -3,7 +3,11 @@ detections.  The R-CNN itself is out of scope (it stays in the reference's detec
 code); without it this tool runs on the synthetic detector stub (``synth.make_video``),
 which emits the same ``Instances`` contract:
 
-    python -m articulation3d_b200.tools.inference --frames 30 --tracks 4 --output out/ [--save-obj]
+    python -m articulation3d_b200.tools.inference --frames 30 --tracks 4 --output out/ [--save-obj] [--save-textured-obj]
+
+``--save-obj`` writes the geometry-only quads of ``io.write_obj``; ``--save-textured-obj`` the reference's export
+(``save_obj_model``, tools/inference.py:44-168, :282: object, rotated copies, axis markers, background, one
+300x300 texture each) through ``articulation3d_b200.export`` — with a flat grey image, the stub has no video.
 """
 from __future__ import annotations
 
@@ -25,6 +29,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=2020)
     ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--save-obj", action="store_true")
+    ap.add_argument("--save-textured-obj", action="store_true")
     args = ap.parse_args(argv)
     random.seed(args.seed)                                   # tools/inference.py:172
     cfg = OptConfig()
@@ -39,6 +44,10 @@ def main(argv=None):
     if args.save_obj:
         for k in sorted({0, min(30, args.frames - 1), min(60, args.frames - 1), min(89, args.frames - 1)}):
             io.write_obj(os.path.join(args.output, f"frame{k}.obj"), opt_preds, planes, k, cfg)   # inference.py:282
+    if args.save_textured_obj:
+        from articulation3d_b200 import export
+        for k in sorted({0, min(30, args.frames - 1), min(60, args.frames - 1), min(89, args.frames - 1)}):
+            export.save_obj_model(args.output, opt_preds, k, image=None, cfg=cfg)                 # inference.py:282
     print(f"{args.frames} frames, {len(planes['rot'])} rot + {len(planes['trans'])} trans tracks "
           f"in {dt * 1e3:.1f} ms -> {args.output}")
 
