@@ -357,6 +357,10 @@ def gpu_arm(args, wl):
                        "packed_mask_bytes_per_gpu": m["packed_mask_bytes_per_gpu"], "l2": m["l2"],
                        "step": "one a3d_pass call (k_unproject, k_project, scoring kernel, k_finalize) on device-resident "
                                "inputs; roofline.kernels_ms from the same K steps issued as a3d_project | a3d_score",
+                       "kernels": "chosen by the library from the grid: projection = reference chain per point with "
+                                  "planned tiles up to two waves of CTAs (this workload), homography filter with proven "
+                                  "truncation beyond (the batched shard); scoring = integer-pipe AND+POPC here, "
+                                  "tcgen05 kind::i8 on the batched shard; identical results either way",
                        "parallelism": (f"videos sharded x{world}; per step one NCCL all_gather of 12 B/track-frame "
                                        f"records on a side stream (overlaps the next step)") if world > 1 else "single GPU"},
             "roofline": m["roofline"], "cpu_baseline": cpu, "e2e": e2e,
