@@ -140,7 +140,8 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W,
  *              homography source pixel -> projected pixel and its error bound, from which the
  *              filtered projection kernel takes every pixel it can PROVE equal to the reference
  *              chain's (the others run that chain; results are identical either way).  NULL or
- *              A3D_PROJECT_KERNEL=exact: the reference chain for every point.
+ *              A3D_PROJECT_KERNEL=exact: the reference chain for every point; by default the
+ *              filter is taken when the grid is more than two waves of CTAs.
  *   tile_map   optional [n_tiles][4] int32, 16-byte aligned: the caller's split of the work into
  *              CTAs, {job, first candidate, candidates (<= tile_cand), role}; role 1 marks the CTA
  *              that takes the job's exact-only candidates (one per job, first/count ignored).
