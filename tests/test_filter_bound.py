@@ -21,3 +21,12 @@ def test_bound_decides_only_what_the_reference_chain_confirms(mode):
     assert st["wrong"] == 0                               # every proven pixel equals the oracle's
     assert st["maxratio"] < 1.0                           # |q_cheap - q_ref| inside the bound wherever it matters
     assert st["unc"] / st["n"] < 0.08                     # incl. the candidates that map pixels onto themselves
+
+
+@pytest.mark.parametrize("seed", [1, 2, 4, 5])
+def test_bound_under_adversarial_geometry(seed):
+    """Grazing / fronto-parallel planes, planes centimetres from the camera, pivots 100 m away, full-circle
+    rotations, metres of translation, focal lengths of 40 and 6000 px: no proven pixel differs from the oracle's
+    chain and the observed error stays inside the bound."""
+    st = filter_proto.run_random(seed, quiet=True)
+    assert st["n"] > 100_000 and st["wrong"] == 0 and st["maxratio"] < 1.0
