@@ -83,6 +83,74 @@ def angle_offset_to_axis(angle_offsets, centers, H: int = 480, W: int = 640) -> 
     return torch.from_numpy(out)
 
 
+def _long_np(v: np.ndarray) -> np.ndarray:
+    """Vector form of ``_long``."""
+    v = np.asarray(v, dtype=np.float64)
+    ok = np.abs(v) < 9.223372036854775807e18
+    out = np.full(v.shape, _INT64_MIN, dtype=np.int64)
+    out[ok] = np.trunc(v[ok]).astype(np.int64)
+    return out
+
+
+def angle_offset_to_axis_rows(ao: np.ndarray, ce: np.ndarray, H: int = 480, W: int = 640) -> np.ndarray:
+    """``angle_offset_to_axis`` for many independent (line, centre) rows at once: the same fp32
+    operations in the same order, as numpy array arithmetic (IEEE per element, so the bits equal the
+    scalar loop's; tests/test_host_logic.py compares the two on random and edge rows).
+    ao (n,3) fp32 [sin, cos, offset], ce (n,2) fp32 -> (n,4) int64."""
+    ao = np.ascontiguousarray(ao, dtype=np.float32).reshape(-1, 3)
+    ce = np.ascontiguousarray(ce, dtype=np.float32).reshape(-1, 2)
+    n = len(ao)
+    out = np.empty((n, 4), dtype=np.int64)
+    if n == 0:
+        return out
+    with np.errstate(all="ignore"):
+        s, c, p = ao[:, 0], ao[:, 1], ao[:, 2]
+        x0, y0 = ce[:, 0], ce[:, 1]
+        p = p * _F(100)
+        angle = np.where(s == 0, _NEG_HALF_PI, -np.arctan(c / s)).astype(np.float32)
+        x = p * c + x0
+        y = p * s + y0
+        vert = angle == _NEG_HALF_PI
+        horiz = (angle == 0.0) & ~vert
+        k = np.tan(angle)
+        b = y - k * x
+        top = x - y / k
+        v = (b, k * _F(W - 1) + y - k * x, top, top + _F(H - 1) / k)
+        lim = (H, H, W, W)
+        have1 = np.zeros(n, dtype=bool)
+        have2 = np.zeros(n, dtype=bool)
+        p1 = np.zeros((n, 2), dtype=np.int64)
+        p2 = np.zeros((n, 2), dtype=np.int64)
+        for i in range(4):
+            ok = (v[i] >= 0) & (v[i] < lim[i])
+            t = np.zeros(n, dtype=np.int64)
+            t[ok] = np.trunc(v[i][ok]).astype(np.int64)
+            if i == 0:
+                px, py = np.zeros(n, dtype=np.int64), t
+            elif i == 1:
+                px, py = np.full(n, W - 1, dtype=np.int64), t
+            elif i == 2:
+                px, py = t, np.zeros(n, dtype=np.int64)
+            else:
+                px, py = t, np.full(n, H - 1, dtype=np.int64)
+            take2 = ok & have1 & ~have2 & ((px != p1[:, 0]) | (py != p1[:, 1]))
+            take1 = ok & ~have1
+            p1[take1, 0], p1[take1, 1] = px[take1], py[take1]
+            p2[take2, 0], p2[take2, 1] = px[take2], py[take2]
+            have1 |= take1
+            have2 |= take2
+        p2[~have2] = p1[~have2]
+        out[:, :2], out[:, 2:] = p1, p2
+        out[~have1] = (0, 0, 1, 1)
+        if vert.any():
+            xv = _long_np(x[vert])
+            out[vert] = np.stack([xv, np.zeros_like(xv), xv, np.full_like(xv, H - 1)], 1)
+        if horiz.any():
+            yh = _long_np(y[horiz])
+            out[horiz] = np.stack([np.zeros_like(yh), yh, np.full_like(yh, W - 1), yh], 1)
+    return out
+
+
 def axis_to_angle_offset(axis, center: torch.Tensor) -> torch.Tensor:
     """[[x1,y1,x2,y2] | None, ...] + (n,2) centres -> (n,4) fp32
     [sin, cos, offset/100, valid] of the line relative to the centre."""

@@ -54,6 +54,17 @@ class OptConfig:
     track_min_len: int = 10
     # mask binarisation of the scoring stage (utils/opt_utils.py:471)
     mask_thresh: float = 0.5
+    # Pearson r of a cluster whose angle list is constant (a static plane: zero variance AND zero
+    # covariance).  scipy.stats.linregress of the reference's era (<= 1.8) returns r = 0.0 there
+    # (-> R^2 = 0 < 0.3 -> has_rot False, score x0.6); scipy >= 1.9 returns NaN (-> `NaN < 0.3` is
+    # False -> has_rot True).  None = whatever the scipy installed beside this package does, i.e. what
+    # the unmodified reference would do in the same environment; 0.0 / float('nan') force either.
+    constant_track_r: float | None = None
+    # host schedule of the cluster phase: 'table' = one all-sources device pass + host replay,
+    # 'chain' = one device pass per round, 'auto' = table while it costs at most table_max_units
+    # (track-frame x candidate evaluations) of device work
+    schedule: str = "auto"
+    table_max_units: int = 96_000_000
 
     @property
     def cx(self) -> float:

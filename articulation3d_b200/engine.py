@@ -53,25 +53,44 @@ class MaskPool:
     bbox_nz: torch.Tensor | None = None
     popc_nz: torch.Tensor | None = None
     _src_points: np.ndarray | None = None
+    _nz_pending: tuple | None = None      # (bits_nz, bbox_nz, popc_nz) not yet compared with bits (PoolBuilder)
 
     def __len__(self):
         return self.bits.shape[0]
 
-    @property
-    def source_points(self) -> np.ndarray:
-        """Host copy of the source-pixel counts (sizes the point-cloud workspace); one
-        D2H per pool, cached."""
-        if self._src_points is None:
+    def _resolve(self):
+        """First host-side use of the pool: ONE D2H of the count vectors (the host needs the
+        source-pixel counts to size the point-cloud workspace).  Binary masks (the contract) give
+        identical ``> thresh`` and ``!= 0`` counts and the second bitmap is dropped.  Deferred to here
+        so that the upload and packing stay asynchronous behind the host's geometry work."""
+        if self._nz_pending is not None:
+            nz, bbox_nz, popc_nz = self._nz_pending
+            self._nz_pending = None
+            both = torch.stack((self.popc, popc_nz)).cpu().numpy()
+            if not np.array_equal(both[0], both[1]):
+                self.bits_nz, self.bbox_nz, self.popc_nz = nz, bbox_nz, popc_nz
+            self._src_points = both[1].astype(np.int64)
+        elif self._src_points is None:
             t = self.popc if self.popc_nz is None else self.popc_nz
             self._src_points = t.cpu().numpy().astype(np.int64)
+
+    @property
+    def source_points(self) -> np.ndarray:
+        """Host copy of the source-pixel counts; one D2H per pool, cached."""
+        if self._src_points is None or self._nz_pending is not None:
+            self._resolve()
         return self._src_points
 
     @property
     def source_bits(self):
+        if self._nz_pending is not None:
+            self._resolve()
         return self.bits if self.bits_nz is None else self.bits_nz
 
     @property
     def source_bbox(self):
+        if self._nz_pending is not None:
+            self._resolve()
         return self.bbox if self.bbox_nz is None else self.bbox_nz
 
 
@@ -117,6 +136,51 @@ def pack_masks(masks: torch.Tensor, thresh: float = 0.5, with_nonzero: bool = Fa
             if not torch.equal(popc_nz, popc):
                 pool.bits_nz, pool.bbox_nz, pool.popc_nz = nz, bbox_nz, popc_nz
     return pool
+
+
+class PoolBuilder:
+    """A MaskPool filled chunk by chunk: ``append`` packs a dense (k, H, W) CUDA chunk into the next k
+    slots of the preallocated bit planes (the chunk buffer can be reused right after, stream order),
+    ``finish`` computes popcounts / boxes once over the whole pool."""
+
+    def __init__(self, n: int, H: int, W: int, device, with_nonzero: bool = False, thresh: float = 0.5):
+        self.n, self.H, self.W, self.thresh = n, H, W, float(thresh)
+        self.device = torch.device(device)
+        pitch = _lib.pitch_words(W)
+        with torch.cuda.device(self.device):
+            self.bits = torch.empty(n, H, pitch, dtype=torch.int32, device=self.device)
+            self.nz = torch.empty_like(self.bits) if with_nonzero else None
+        self.fill = 0
+
+    def append(self, masks: torch.Tensor):
+        lib = _lib.load()
+        _require_cuda(masks, "masks")
+        if masks.dtype == torch.bool:
+            masks = masks.view(torch.uint8)
+        dt = {torch.float32: _lib.A3D_F32, torch.uint8: _lib.A3D_U8}.get(masks.dtype)
+        if dt is None:
+            raise TypeError(f"unsupported mask dtype {masks.dtype}")
+        masks = masks.contiguous()
+        k = int(masks.shape[0])
+        if self.fill + k > self.n or tuple(masks.shape[1:]) != (self.H, self.W):
+            raise ValueError("chunk does not fit the pool")
+        with torch.cuda.device(self.device):
+            _lib.check(lib.a3d_pack_masks(masks.data_ptr(), dt, k, self.H, self.W, self.thresh,
+                                          self.bits[self.fill:].data_ptr(),
+                                          self.nz[self.fill:].data_ptr() if self.nz is not None else None,
+                                          _stream_ptr()), "a3d_pack_masks")
+        self.fill += k
+
+    def finish(self) -> MaskPool:
+        if self.fill != self.n:
+            raise ValueError(f"pool holds {self.fill} of {self.n} masks")
+        with torch.cuda.device(self.device):
+            popc, bbox = mask_meta(self.bits, self.H, self.W)
+            pool = MaskPool(self.bits, popc, bbox, self.H, self.W)
+            if self.nz is not None:
+                popc_nz, bbox_nz = mask_meta(self.nz, self.H, self.W)
+                pool._nz_pending = (self.nz, bbox_nz, popc_nz)       # compared on first host-side use
+        return pool
 
 
 def pool_from_bits(bits: torch.Tensor, H: int, W: int) -> MaskPool:
@@ -260,6 +324,36 @@ def build_batch(sources, modes, normals, offsets, pivots, xforms, targets, src_p
     tgt_index = (np.concatenate([np.asarray(t, dtype=np.int32).reshape(-1) for t in targets])
                  if n else np.zeros(0, np.int32))
     return JobBatch(jobs, np.ascontiguousarray(xform), np.ascontiguousarray(tgt_index))
+
+
+def build_batch_rows(sources, modes, normals, offsets, pivots, xform, n_cand, tgt_index, n_tgt,
+                     src_points) -> JobBatch:
+    """``build_batch`` from arrays, without a python loop over jobs: sources/modes/offsets (S,),
+    normals/pivots (S,3), xform (sum n_cand, 12) fp32 in job order, n_cand/n_tgt (S,) counts,
+    tgt_index (sum n_tgt,) pool indices in job order."""
+    sources = np.asarray(sources, dtype=np.int64)
+    S = len(sources)
+    n_cand = np.asarray(n_cand, dtype=np.int64).reshape(S)
+    n_tgt = np.asarray(n_tgt, dtype=np.int64).reshape(S)
+    jobs = np.zeros(S, dtype=_lib.JOB_DTYPE)
+    if S:
+        jobs["src_mask"] = sources
+        jobs["mode"] = np.asarray(modes, dtype=np.int32)
+        jobs["n_cand"], jobs["n_tgt"] = n_cand, n_tgt
+        jobs["cand_begin"] = np.cumsum(n_cand) - n_cand
+        jobs["tgt_begin"] = np.cumsum(n_tgt) - n_tgt
+        jobs["normal"] = np.asarray(normals, dtype=np.float32).reshape(S, 3)
+        jobs["offset"] = np.asarray(offsets, dtype=np.float32).reshape(S)
+        jobs["pivot"] = np.asarray(pivots, dtype=np.float32).reshape(S, 3)
+        tab = n_cand * n_tgt
+        jobs["tab_begin"] = np.cumsum(tab) - tab
+        cap = (np.asarray(src_points, dtype=np.int64)[sources] + 31) & ~31
+        jobs["pcd_cap"] = cap
+        jobs["pcd_begin"] = np.cumsum(cap) - cap
+    xform = np.ascontiguousarray(np.asarray(xform, dtype=np.float32).reshape(-1, 12))
+    tgt_index = np.ascontiguousarray(np.asarray(tgt_index, dtype=np.int32).reshape(-1))
+    assert len(xform) == int(n_cand.sum()) and len(tgt_index) == int(n_tgt.sum())
+    return JobBatch(jobs, xform, tgt_index)
 
 
 @dataclass

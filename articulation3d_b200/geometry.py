@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .axis import angle_offset_to_axis
+from .axis import angle_offset_to_axis, angle_offset_to_axis_rows
 from .config import OptConfig
 
 
@@ -75,6 +75,72 @@ def source_geometry(p_instance, box_id: int, cfg: OptConfig, translation: bool,
         d = axis3d[1] - axis3d[0]
         d = d / np.linalg.norm(d)
     return SourceGeometry(normal, offset, pts, axis3d, d, axis3d[0].astype(np.float32))
+
+
+@dataclass
+class SourceGeometryRows:
+    """``SourceGeometry`` of many independent (frame, box) sources, as numpy arrays."""
+    normal: np.ndarray          # (n,3) fp32
+    offset: np.ndarray          # (n,)  fp32
+    pts: np.ndarray             # (n,4) int64 axis end-points of each source's own box
+    axis3d: np.ndarray          # (n,2,3) float64
+    dir_vec: np.ndarray         # (n,3) float64
+    pivot: np.ndarray           # (n,3) fp32
+
+    def __len__(self):
+        return len(self.offset)
+
+    def row(self, i: int, box_id: int, n_boxes: int) -> SourceGeometry:
+        """Row ``i`` as the per-source record (``pts`` holds the row of ``box_id`` only)."""
+        pts = torch.zeros(n_boxes, 4, dtype=torch.int64)
+        pts[box_id] = torch.from_numpy(self.pts[i])
+        return SourceGeometry(torch.from_numpy(self.normal[i].copy()), torch.tensor(self.offset[i]), pts,
+                              self.axis3d[i], self.dir_vec[i], self.pivot[i])
+
+
+def concat_rows(parts) -> SourceGeometryRows:
+    if len(parts) == 1:
+        return parts[0]
+    return SourceGeometryRows(*(np.concatenate([getattr(p, f) for p in parts])
+                                for f in ("normal", "offset", "pts", "axis3d", "dir_vec", "pivot")))
+
+
+def source_geometry_rows(planes: torch.Tensor, axis: torch.Tensor, centers: torch.Tensor,
+                         cfg: OptConfig) -> SourceGeometryRows:
+    """``source_geometry`` for n independent sources in one set of array operations.
+
+    planes (n,3) fp32 ``pred_planes`` rows; axis (n,3) fp32 ``[sin, cos, offset]`` rows
+    (``pred_rot_axis``, or ``pred_tran_axis`` with a zero offset column); centers (n,2) fp32 box
+    centres.  Every step is the per-source function's operation applied row-wise (row-wise torch
+    norms, elementwise numpy fp32 / fp64), except the length of the axis direction, which stays
+    one ``np.linalg.norm`` call per source: its BLAS dot product rounds differently from any
+    array reduction.  tests/test_host_logic.py checks bit equality with ``source_geometry``."""
+    plane = planes.detach().cpu().to(torch.float32).clone().reshape(-1, 3)
+    plane[:, [1, 2]] = plane[:, [2, 1]]            # [a, b, c] -> [a, -c, b]
+    plane[:, 1] = -plane[:, 1]
+    normal = F.normalize(plane, p=2).numpy()
+    offset = torch.norm(plane, p=2, dim=1).numpy()
+    pts = angle_offset_to_axis_rows(axis.detach().cpu().numpy(), centers.detach().cpu().numpy(),
+                                    H=cfg.height, W=cfg.width)
+    n = len(offset)
+    K = cfg.K_inv()
+    nn = normal.astype(np.float64)
+    off = offset.astype(np.float64)
+    axis3d = np.empty((n, 2, 3), dtype=np.float64)
+    with np.errstate(all="ignore"):
+        for e in range(2):
+            x = pts[:, 2 * e].astype(np.float64)
+            y = pts[:, 2 * e + 1].astype(np.float64)
+            rx = (K[0, 0] * x + K[0, 1] * y) + K[0, 2]
+            ry = (K[1, 0] * x + K[1, 1] * y) + K[1, 2]
+            rz = (K[2, 0] * x + K[2, 1] * y) + K[2, 2]
+            depth = off / ((nn[:, 0] * rx + nn[:, 1] * ry) + nn[:, 2] * rz)
+            axis3d[:, e, 0], axis3d[:, e, 1], axis3d[:, e, 2] = depth * rx, depth * ry, depth * rz
+        d = axis3d[:, 1] - axis3d[:, 0]
+        norm = np.linalg.norm
+        length = np.fromiter((norm(v) for v in d), dtype=np.float64, count=n)
+        d = d / length[:, None]
+    return SourceGeometryRows(normal, offset, pts, axis3d, d, axis3d[:, 0].astype(np.float32))
 
 
 # quaternion -> matrix entry e = two_s * (q_a q_b + sign * q_c q_d), diagonal entries 1 - e;

@@ -29,6 +29,7 @@ to the host eagerly.
 """
 from __future__ import annotations
 
+import os
 import random as _global_random
 from collections.abc import Mapping
 from dataclasses import dataclass, field
@@ -43,21 +44,41 @@ linregress = getattr(_scipy_linregress, "__wrapped__", _scipy_linregress)
 
 
 
-def _rvalue(y) -> np.float64:
+_vecdot = getattr(np, "vecdot", None) or (lambda a, b: np.add.reduce(a * b))      # numpy < 2 has no vecdot
+_installed_constant_r = None
+
+
+def _constant_r_of_installed_scipy() -> float:
+    """What ``scipy.stats.linregress`` of THIS environment returns as r for a constant series (NaN
+    since scipy 1.9, 0.0 before): the default for ``OptConfig.constant_track_r``."""
+    global _installed_constant_r
+    if _installed_constant_r is None:
+        import warnings
+        with warnings.catch_warnings(), np.errstate(all="ignore"):
+            warnings.simplefilter("ignore")
+            _installed_constant_r = float(_scipy_linregress(range(5), np.full(5, 0.5)).rvalue)
+    return _installed_constant_r
+
+
+def _rvalue(y, constant_r: float | None = None) -> np.float64:
     """Pearson r of ``y`` against 0..n-1, exactly as ``scipy.stats.linregress(range(n), y).rvalue``
-    computes it (float64; mean-removed dot products through ``np.vecdot``; clip to [-1, 1]; NaN when both
-    the covariance and a variance vanish, 0 when only a variance does) without the array-API plumbing
-    around it, which costs several times the arithmetic.  tests/test_host_logic.py checks bit equality."""
+    computes it (float64; mean-removed dot products through ``np.vecdot``; clip to [-1, 1]) without the
+    array-API plumbing around it, which costs several times the arithmetic.  The degenerate case
+    (constant ``y``: zero variance and zero covariance) is ``constant_r`` — see
+    ``OptConfig.constant_track_r``; None = the installed scipy's answer.  tests/test_host_logic.py checks
+    bit equality with scipy."""
     y = np.asarray(y).astype(np.float64)
     n = y.shape[0]
     x = np.arange(n, dtype=np.float64)
     x_ = x - np.mean(x, keepdims=True)
     y_ = y - np.mean(y, keepdims=True)
-    ssxm = np.vecdot(x_, x_) / n
-    ssym = np.vecdot(y_, y_) / n
-    ssxym = np.vecdot(x_, y_) / n
+    ssxm = _vecdot(x_, x_) / n
+    ssym = _vecdot(y_, y_) / n
+    ssxym = _vecdot(x_, y_) / n
     if ssxm == 0.0 or ssym == 0.0:
-        return np.float64(np.nan) if ssxym == 0 else np.float64(0.0)
+        if ssxym != 0:
+            return np.float64(0.0)
+        return np.float64(_constant_r_of_installed_scipy() if constant_r is None else constant_r)
     return np.clip(ssxym / np.sqrt(ssxm * ssym), -1.0, 1.0)
 
 
@@ -162,6 +183,18 @@ class RegMasks(Mapping):
 # the host control flow, as a generator of device jobs
 # ---------------------------------------------------------------------------
 @dataclass
+class SourceReq:
+    """One cluster-round job whose source geometry is still to be computed (the driver batches the
+    geometry of all pending requests into one set of array operations)."""
+    frame: int                     # source frame
+    box: int                       # its box
+    translation: bool
+    mode: int
+    grid: object                   # candidate grid of the round (all requests of one kind share it)
+    targets: list                  # pool indices, in id_list order
+
+
+@dataclass
 class JobSpec:
     source: int                    # pool index of the source mask
     mode: int
@@ -180,6 +213,18 @@ class JobResult:
     best_inter: np.ndarray
     best_union: np.ndarray
     masks: torch.Tensor | None = None     # (n_tgt, H, pitch) int32 device, if keep_masks
+    geo: "geometry.SourceGeometry | None" = None     # answer to a SourceReq: the source's geometry
+
+
+@dataclass
+class TrackTable:
+    """Cluster-phase answers for EVERY frame of a track as source (all-sources schedule): row =
+    source frame, column = target frame, both in ``frames`` order."""
+    frames: list
+    index: dict                    # frame -> row/column
+    cand: np.ndarray               # (T, T) int32 first candidate of maximal IoU
+    iou: np.ndarray                # (T, T) fp32 that IoU
+    geo: "geometry.SourceGeometryRows"
 
 
 @dataclass
@@ -187,11 +232,12 @@ class Stats:
     """What was evaluated, in the reference's accounting: one unit =
     one (visited frame, candidate) IoU."""
     units_visited: int = 0         # units the reference's loops evaluate
-    units_computed: int = 0        # units the device evaluated (all of id_list each round)
+    units_computed: int = 0        # units the device evaluated
     passes: int = 0
     jobs: int = 0
     h2d_bytes: int = 0             # masks + job descriptors copied host -> device
     d2h_bytes: int = 0             # per-target results copied device -> host
+    schedule: str = ""             # 'table' (all-sources pass + host replay) | 'chain' (a pass per round)
     detail: list = field(default_factory=list)
 
 
@@ -203,45 +249,85 @@ def _phase_setup(translation: bool, legacy: bool, cfg: OptConfig):
     return cfg.rot_cluster_grid, cfg.rot_final_grid, _lib.MODE_SEQ, _lib.MODE_COMPOSED
 
 
-def _candidates(geo: geometry.SourceGeometry, grid, mode: int):
-    """(A,12) transforms, the (A,1) fp32 angle tensor the reference indexes, and R."""
+def _angle_column(grid, mode: int) -> torch.Tensor:
+    """The (A,1) fp32 tensor the reference indexes for a cluster's angle list."""
     if mode == _lib.MODE_TRANSLATE:
-        return geometry.xforms_translate(grid, geo.dir_vec), torch.as_tensor(grid, dtype=torch.float32).unsqueeze(1), None
-    R = geometry.rotation_matrices(grid, geo.dir_vec)
-    angles = torch.FloatTensor(np.asarray(grid)[:, np.newaxis])
+        return torch.as_tensor(grid, dtype=torch.float32).unsqueeze(1)
+    return torch.FloatTensor(np.asarray(grid)[:, np.newaxis])
+
+
+def _xforms_rows(dir_vec: np.ndarray, pivot: np.ndarray, grid, mode: int):
+    """Candidate transforms of n sources at once: (n, A, 12) fp32 and R (n, A, 3, 3) or None."""
+    if mode == _lib.MODE_TRANSLATE:
+        return geometry.xforms_translate(grid, dir_vec), None
+    R = geometry.rotation_matrices(grid, dir_vec)
     if mode == _lib.MODE_SEQ:
-        return geometry.xforms_seq(R), angles, R
-    return geometry.xforms_composed(R, geo.pivot), angles, R
+        return geometry.xforms_seq(R), R
+    return geometry.xforms_composed(R, pivot), R
+
+
+class _VideoRows:
+    """Per-box prediction rows of one video, flattened once so that the geometry of any set of
+    (frame, box) sources is a gather plus one batched computation."""
+
+    def __init__(self, preds):
+        def flat(ts, width):
+            ts = [t.detach().cpu().to(torch.float32).reshape(-1, width) for t in ts]
+            return torch.cat(ts) if ts else torch.zeros(0, width)
+        counts = [int(p.pred_boxes.tensor.shape[0]) for p in preds]
+        self.base = np.zeros(len(preds) + 1, dtype=np.int64)
+        np.cumsum(counts, out=self.base[1:])
+        self.planes = flat([p.pred_planes for p in preds], 3)
+        self.rot_axis = flat([p.pred_rot_axis for p in preds], 3)
+        tran = flat([p.pred_tran_axis for p in preds], 2)
+        self.tran_axis = torch.cat((tran, torch.zeros(len(tran), 1)), 1)      # offset column = 0
+        boxes = flat([p.pred_boxes.tensor for p in preds], 4)
+        self.centers = (boxes[:, :2] + boxes[:, 2:]) / 2
+
+    def geometry(self, frames, boxes, translation: bool, cfg: OptConfig) -> geometry.SourceGeometryRows:
+        idx = torch.from_numpy(self.base[np.asarray(frames, dtype=np.int64)] + np.asarray(boxes, dtype=np.int64))
+        axis = self.tran_axis if translation else self.rot_axis
+        return geometry.source_geometry_rows(self.planes[idx], axis[idx], self.centers[idx], cfg)
 
 
 def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, stats: Stats,
-                legacy: bool = False):
+                legacy: bool = False, tables=None):
     """Cluster rounds, model selection and final assignment for a list of tracks
-    (reference :386-622 / :689-908 / legacy :113-340).  Mutates ``planes``."""
+    (reference :386-622 / :689-908 / legacy :113-340).  Mutates ``planes``.
+
+    A cluster round needs, for its randomly chosen source frame, the arg-max candidate and IoU of
+    every frame still in ``id_list``.  With ``tables`` (one ``TrackTable`` per track, computed for
+    all sources in one device pass beforehand) the round is a table lookup and the generator only
+    yields once, for the final-phase jobs; without, it yields a ``SourceReq`` per round and is sent
+    a ``JobResult``."""
     cgrid, fgrid, cmode, fmode = _phase_setup(translation, legacy, cfg)
     remove_inliers = not legacy
+    angles_c = _angle_column(cgrid, cmode)
+    thr, n_cand = float(np.float32(cfg.inlier_iou)), len(cgrid)
     finals = []
-    for plane in planes:
+    for ti, plane in enumerate(planes):
         ids = plane['ids']
         id_list = list(ids.keys())
         clusters = []
         geo_of = {}                       # source frame -> geometry (the final phase reuses its centre frame's)
+        tab = tables[ti] if tables is not None else None
         for _ in range(cfg.rounds):
             if len(id_list) == 0 and remove_inliers:
                 break
             select_idx = rng.choice(id_list)
             box_id = ids[select_idx]
-            geo = geo_of.get(select_idx)
-            if geo is None:
-                geo = geo_of[select_idx] = geometry.source_geometry(preds[select_idx], box_id, cfg, translation)
-            xf, angles, _ = _candidates(geo, cgrid, cmode)
             order = list(id_list)
-            res = yield JobSpec(pool_of[(select_idx, box_id)], cmode, geo.normal.numpy(), float(geo.offset),
-                                geo.pivot, xf, [pool_of[(i, ids[i])] for i in order])
+            if tab is not None:
+                r = tab.index[select_idx]
+                cols = [tab.index[f] for f in order]
+                ious, cands = tab.iou[r, cols].tolist(), tab.cand[r, cols].tolist()
+            else:
+                res = yield SourceReq(select_idx, box_id, translation, cmode, cgrid,
+                                      [pool_of[(i, ids[i])] for i in order])
+                geo_of[select_idx] = res.geo
+                # plain python lists: fp32 IoUs are exact as doubles, so `> 0.5` decides as the fp32 compare does
+                ious, cands = res.best_iou.tolist(), res.best_cand.tolist()
             row = {f: k for k, f in enumerate(order)}
-            # plain python lists: fp32 IoUs are exact as doubles, so `> 0.5` decides as the fp32 compare does
-            ious, cands = res.best_iou.tolist(), res.best_cand.tolist()
-            thr, n_cand = float(np.float32(cfg.inlier_iou)), len(xf)
             inliers, c_ids, c_ious = [], [], []
             it = 0
             while it < len(id_list):            # `for idx in id_list` with in-loop removal
@@ -256,7 +342,7 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
                     c_ids.append(cands[k])
                     c_ious.append(ious[k])
             clusters.append({'center_id': select_idx, 'inliners': inliers,
-                             'angles': angles[c_ids, 0].clone() if c_ids else torch.FloatTensor([]),
+                             'angles': angles_c[c_ids, 0].clone() if c_ids else torch.FloatTensor([]),
                              'ious': c_ious})
 
         rsqs = []
@@ -264,7 +350,7 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
             if len(cluster['inliners']) < cfg.min_inliers:
                 rsqs.append(0.0)
                 continue
-            rsqs.append(_rvalue(cluster['angles'].numpy()) ** 2)
+            rsqs.append(_rvalue(cluster['angles'].numpy(), cfg.constant_track_r) ** 2)
         rsqs = np.array(rsqs)
         if rsqs.max() < cfg.rsq_thresh:
             plane['has_rot'] = False
@@ -278,29 +364,35 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
         select_idx = final_cluster['center_id']
         box_id = ids[select_idx]
         p_instance = preds[select_idx]
-        geo = geo_of[select_idx] if not legacy else \
-            geometry.source_geometry(p_instance, box_id, cfg, translation, all_boxes=True)
-        xf, angles, R = _candidates(geo, fgrid, fmode)
-        frames = list(ids.keys())
-        spec = JobSpec(pool_of[(select_idx, box_id)], fmode, geo.normal.numpy(), float(geo.offset),
-                       geo.pivot, xf, [pool_of[(i, ids[i])] for i in frames], keep_masks=True)
-        finals.append((plane, spec, geo, xf, angles, R, frames, select_idx, box_id, p_instance, rsqs, clusters))
+        if legacy:
+            geo = geometry.source_geometry(p_instance, box_id, cfg, translation, all_boxes=True)
+        elif tab is not None:
+            geo = tab.geo.row(tab.index[select_idx], box_id, int(p_instance.pred_boxes.tensor.shape[0]))
+        else:
+            geo = geo_of[select_idx]
+        finals.append((plane, geo, select_idx, box_id, p_instance, rsqs, clusters))
 
     if not finals:
         return
-    results = yield [f[1] for f in finals]
-    for (plane, spec, geo, xf, angles, R, frames, select_idx, box_id, p_instance, rsqs, clusters), res in zip(finals, results):
-        stats.units_visited += len(xf) * len(frames)
-        H, W = cfg.height, cfg.width
+    angles_f = _angle_column(fgrid, fmode)
+    xf_all, R_all = _xforms_rows(np.stack([f[1].dir_vec for f in finals]), np.stack([f[1].pivot for f in finals]),
+                                 fgrid, fmode)
+    specs = []
+    for k, (plane, geo, select_idx, box_id, p_instance, rsqs, clusters) in enumerate(finals):
+        ids = plane['ids']
+        specs.append(JobSpec(pool_of[(select_idx, box_id)], fmode, geo.normal.numpy(), float(geo.offset),
+                             geo.pivot, xf_all[k], [pool_of[(i, b)] for i, b in ids.items()], keep_masks=True))
+    results = yield specs
+    H, W = cfg.height, cfg.width
+    for k, ((plane, geo, select_idx, box_id, p_instance, rsqs, clusters), res) in enumerate(zip(finals, results)):
+        frames = list(plane['ids'].keys())
+        stats.units_visited += len(fgrid) * len(frames)
         plane['reg_masks'] = RegMasks(frames, res.masks, H, W)
         if fmode == _lib.MODE_COMPOSED:
-            normal_trans = geometry.transform_normals(geo.normal, R)
-            plane['reg_normals'] = {}
-            for k, idx in enumerate(frames):
-                n = normal_trans[int(res.best_cand[k])].clone()
-                n[1] = -n[1]
-                n[[1, 2]] = n[[2, 1]]
-                plane['reg_normals'][idx] = n
+            normal_trans = geometry.transform_normals(geo.normal, R_all[k])
+            sel = normal_trans[torch.from_numpy(res.best_cand.astype(np.int64))]
+            sel = torch.stack((sel[:, 0], sel[:, 2], -sel[:, 1]), 1)          # [n0, n2, -n1]
+            plane['reg_normals'] = dict(zip(frames, sel.unbind(0)))
         if translation:
             plane['std_axis'] = p_instance.pred_tran_axis[box_id]
         elif legacy:
@@ -309,7 +401,7 @@ def _tracks_gen(preds, planes, cfg: OptConfig, translation: bool, rng, pool_of, 
             plane['std_axis'] = geo.pts[box_id]
         plane['fit'] = {
             'frames': frames, 'center_frame': select_idx, 'rsq': rsqs, 'clusters': clusters,
-            'angle_id': res.best_cand.copy(), 'angle': angles[:, 0].numpy()[res.best_cand],
+            'angle_id': res.best_cand.copy(), 'angle': angles_f[:, 0].numpy()[res.best_cand],
             'inter': res.best_inter.copy(), 'union': res.best_union.copy(), 'iou': res.best_iou.copy(),
         }
 
@@ -399,6 +491,10 @@ def _write_back(preds, planes, cfg: OptConfig, kind: str):
 # ---------------------------------------------------------------------------
 # device session: mask pool + job driver
 # ---------------------------------------------------------------------------
+_UPLOAD_CHUNK_BYTES = 1 << 29      # dense masks staged on the device per pack call
+_PROJ_BUDGET_BYTES = 6 << 30       # projected-mask workspace of one device pass
+
+
 class _Session:
     """Packed masks of every tracked box of a set of videos, resident on one GPU."""
 
@@ -407,7 +503,9 @@ class _Session:
         self.device = torch.device(device)
         self.ws = engine.Workspace(self.device)
         self.staging = engine.Staging(self.device)
+        self.videos = videos
         self.pool_of = []                   # per video: {(frame, box_id): pool index}
+        self._rows = {}
         chunks, rles, n = [], [], 0
         for preds, plane_lists in videos:
             need = {}
@@ -440,17 +538,63 @@ class _Session:
             self.pool = engine.rle_to_pool(rles, cfg.height, cfg.width, self.device)
             self.h2d_bytes += sum(len(r["counts"]) for r in rles)
             return
-        dev_chunks = []
+        self.pool = self._upload(chunks, n)
+
+    def _upload(self, chunks, n) -> engine.MaskPool:
+        """Dense per-frame masks -> packed pool.  The frames are copied (asynchronously when the host
+        tensors are pinned) into slices of ONE device staging block of at most _UPLOAD_CHUNK_BYTES and
+        packed from there into the preallocated pool; no concatenated fp32 copy of all masks exists."""
+        cfg = self.cfg
+        H, W = cfg.height, cfg.width
+        # mixed mask dtypes: everything is promoted to fp32 (never truncated to the first chunk's type)
+        kinds = {c.dtype for c in chunks}
+        if kinds <= {torch.uint8, torch.bool}:
+            dt = torch.uint8
+        else:
+            dt = torch.float32
+        per_mask = H * W * (4 if dt == torch.float32 else 1)
+        cap = max(1, min(n, _UPLOAD_CHUNK_BYTES // per_mask))
+        cap = max(cap, max(int(c.shape[0]) for c in chunks))
+        builder = engine.PoolBuilder(n, H, W, self.device, with_nonzero=(dt == torch.float32),
+                                     thresh=cfg.mask_thresh)
+        stage = torch.empty(cap, H, W, dtype=dt, device=self.device)
+        fill = 0
         for c in chunks:
-            if c.dtype not in (torch.float32, torch.uint8, torch.bool):
-                c = c.float()
+            if c.dtype == torch.bool:
+                c = c.view(torch.uint8) if c.is_contiguous() else c.to(torch.uint8)
+            if c.dtype != dt:
+                c = c.to(dt)
+            k = int(c.shape[0])
+            if fill + k > cap:
+                builder.append(stage[:fill])
+                fill = 0
             if not c.is_cuda:
                 self.h2d_bytes += c.numel() * c.element_size()
-            dev_chunks.append(c.to(self.device, non_blocking=True))
-        dt = dev_chunks[0].dtype
-        dense = torch.cat([c if c.dtype == dt else c.to(dt) for c in dev_chunks])
-        self.pool = engine.pack_masks(dense, cfg.mask_thresh, with_nonzero=(dt == torch.float32))
-        del dense, dev_chunks
+            stage[fill:fill + k].copy_(c, non_blocking=True)
+            fill += k
+        if fill:
+            builder.append(stage[:fill])
+        return builder.finish()
+
+    def rows(self, v: int) -> _VideoRows:
+        r = self._rows.get(v)
+        if r is None:
+            r = self._rows[v] = _VideoRows(self.videos[v][0])
+        return r
+
+    # -- device passes ------------------------------------------------------------------
+    def _pass(self, batch: engine.JobBatch, host_out: np.ndarray | None, stats: Stats | None):
+        """One device pass; the (4, n_tgt) result block is copied into pinned memory (D2H enqueued,
+        not waited for).  Returns (PassResult, pinned int32 tensor view)."""
+        dbatch = engine.DeviceBatch(batch, self.device, self.staging, self.cfg)
+        res = engine.run_pass(self.cfg, self.pool, dbatch, self.ws)
+        if stats is not None:
+            stats.passes += 1
+            stats.jobs += batch.n_jobs
+            stats.units_computed += batch.units
+            stats.h2d_bytes += batch.jobs.nbytes + batch.xform.nbytes + batch.tgt_index.nbytes
+            stats.d2h_bytes += 16 * len(batch.tgt_index)
+        return res
 
     def run(self, specs, stats: Stats | None = None):
         """One device pass over a list of JobSpec -> list of JobResult."""
@@ -458,30 +602,178 @@ class _Session:
                                    [s.normal for s in specs], [s.offset for s in specs],
                                    [s.pivot for s in specs], [s.xform for s in specs],
                                    [s.targets for s in specs], self.pool.source_points)
-        dbatch = engine.DeviceBatch(batch, self.device, self.staging, self.cfg)
-        res = engine.run_pass(self.cfg, self.pool, dbatch, self.ws)
+        res = self._pass(batch, None, stats)
         host = self.staging.results_host(res.block.numel())
         host.view(4, -1).copy_(res.block, non_blocking=True)                 # one D2H into pinned memory
+        masks = {}
+        for j, s in enumerate(specs):           # enqueued before the sync: the gathers overlap the D2H
+            if s.keep_masks:
+                a, n = int(batch.jobs[j]["tgt_begin"]), int(batch.jobs[j]["n_tgt"])
+                gidx = (res.best_cand[a:a + n].long() + int(batch.jobs[j]["cand_begin"]))
+                masks[j] = res.proj_bits.index_select(0, gidx)      # copy out of the workspace
         torch.cuda.current_stream().synchronize()
         packed = host.numpy().reshape(4, -1)
-        if stats is not None:
-            stats.h2d_bytes += batch.jobs.nbytes + batch.xform.nbytes + batch.tgt_index.nbytes
-            stats.d2h_bytes += packed.nbytes
         out = []
         for j, s in enumerate(specs):
             a, n = int(batch.jobs[j]["tgt_begin"]), int(batch.jobs[j]["n_tgt"])
-            r = JobResult(packed[0, a:a + n].copy(), packed[3, a:a + n].copy().view(np.float32),
-                          packed[1, a:a + n].copy(), packed[2, a:a + n].copy())
-            if s.keep_masks:
-                gidx = (res.best_cand[a:a + n].long() + int(batch.jobs[j]["cand_begin"]))
-                r.masks = res.proj_bits.index_select(0, gidx)       # copy out of the workspace
-            out.append(r)
-        return out, batch.units
+            out.append(JobResult(packed[0, a:a + n].copy(), packed[3, a:a + n].copy().view(np.float32),
+                                 packed[1, a:a + n].copy(), packed[2, a:a + n].copy(), masks.get(j)))
+        return out
+
+    def run_rows(self, sources, modes, geo: geometry.SourceGeometryRows, xform, n_tgt, tgt_index,
+                 stats: Stats | None = None) -> np.ndarray:
+        """Jobs given as arrays (one row of ``geo`` / ``xform[i]`` per job) -> (4, sum n_tgt) int32
+        results {cand, inter, union, iou bits}.  Split into as many device passes as the
+        projected-mask workspace budget asks for; all passes are enqueued before the one sync."""
+        S = len(sources)
+        n_tgt = np.asarray(n_tgt, dtype=np.int64)
+        A = xform.shape[1]
+        per_cand = self.cfg.height * _lib.pitch_words(self.cfg.width) * 4
+        per_pass = max(1, int(_PROJ_BUDGET_BYTES // (per_cand * max(A, 1))))
+        t_begin = np.zeros(S + 1, dtype=np.int64)
+        np.cumsum(n_tgt, out=t_begin[1:])
+        host = self.staging.results_host(4 * int(t_begin[-1])).view(4, -1)
+        src_points = self.pool.source_points
+        for lo in range(0, S, per_pass):
+            hi = min(S, lo + per_pass)
+            batch = engine.build_batch_rows(sources[lo:hi], modes[lo:hi], geo.normal[lo:hi], geo.offset[lo:hi],
+                                            geo.pivot[lo:hi], xform[lo:hi].reshape(-1, 12),
+                                            np.full(hi - lo, A), tgt_index[t_begin[lo]:t_begin[hi]],
+                                            n_tgt[lo:hi], src_points)
+            res = self._pass(batch, None, stats)
+            host[:, t_begin[lo]:t_begin[hi]].copy_(res.block, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()
+
+    # -- all-sources schedule -----------------------------------------------------------
+    def cluster_tables(self, lists, stats: Stats | None = None, legacy: bool = False):
+        """``lists``: [(video index, planes, translation)].  ONE scheduling step for the cluster phase of
+        all those track lists: every frame of every track is a source (job), its targets are all
+        frames of its track.  Returns one list of ``TrackTable`` per entry of ``lists``."""
+        cfg = self.cfg
+        groups = {}                                   # translation flag -> per-track bookkeeping
+        for li, (v, planes, translation) in enumerate(lists):
+            for ti, plane in enumerate(planes):
+                frames = list(plane['ids'].keys())
+                boxes = [plane['ids'][f] for f in frames]
+                groups.setdefault(bool(translation), []).append((li, ti, v, frames, boxes))
+        out = [[None] * len(planes) for _, planes, _ in lists]
+        for translation, tracks in groups.items():
+            cgrid, _, cmode, _ = _phase_setup(translation, legacy, cfg)
+            geos = []
+            by_video = {}
+            for k, (li, ti, v, frames, boxes) in enumerate(tracks):
+                by_video.setdefault(v, []).append(k)
+            # geometry of all sources: one batched computation per video's rows
+            geo_of_track = [None] * len(tracks)
+            for v, ks in by_video.items():
+                fr = np.concatenate([np.asarray(tracks[k][3], dtype=np.int64) for k in ks])
+                bx = np.concatenate([np.asarray(tracks[k][4], dtype=np.int64) for k in ks])
+                g = self.rows(v).geometry(fr, bx, translation, cfg)
+                o = 0
+                for k in ks:
+                    T = len(tracks[k][3])
+                    geo_of_track[k] = (g, o, o + T)
+                    o += T
+                geos.append((g, ks))
+            # one job list over all tracks, in track order
+            src, ntg, tgt, parts = [], [], [], []
+            for k, (li, ti, v, frames, boxes) in enumerate(tracks):
+                pool_of = self.pool_of[v]
+                tpool = np.fromiter((pool_of[(f, b)] for f, b in zip(frames, boxes)), dtype=np.int32,
+                                    count=len(frames))
+                T = len(frames)
+                src.append(tpool.astype(np.int64))
+                ntg.append(np.full(T, T, dtype=np.int64))
+                tgt.append(np.tile(tpool, T))
+                g, a, b = geo_of_track[k]
+                parts.append(geometry.SourceGeometryRows(g.normal[a:b], g.offset[a:b], g.pts[a:b], g.axis3d[a:b],
+                                                         g.dir_vec[a:b], g.pivot[a:b]))
+            geo = geometry.concat_rows(parts)
+            xform, _ = _xforms_rows(geo.dir_vec, geo.pivot, cgrid, cmode)
+            src = np.concatenate(src)
+            res = self.run_rows(src, np.full(len(src), cmode, dtype=np.int32), geo, xform, np.concatenate(ntg),
+                                np.concatenate(tgt), stats)
+            o = 0
+            for k, (li, ti, v, frames, boxes) in enumerate(tracks):
+                T = len(frames)
+                blk = res[:, o:o + T * T]
+                out[li][ti] = TrackTable(frames, {f: i for i, f in enumerate(frames)},
+                                         blk[0].reshape(T, T).copy(), blk[3].view(np.float32).reshape(T, T).copy(),
+                                         parts[k])
+                o += T * T
+        return out
+
+    def table_units(self, lists) -> int:
+        """Device work of the all-sources schedule for these track lists, in units."""
+        cfg = self.cfg
+        u = 0
+        for v, planes, translation in lists:
+            a = len(cfg.trans_grid) if translation else len(cfg.rot_cluster_grid)
+            u += sum(len(p['ids']) ** 2 for p in planes) * a
+        return u
 
 
-def _drive(gens, session: _Session, stats: Stats):
-    """Run generators in lock-step: every device pass carries the pending job of
-    each still-active generator."""
+def _answer_chain(session: _Session, reqs, stats: Stats):
+    """Chained schedule: one device pass for the pending requests of all generators.  ``reqs`` is a
+    list of (video index, SourceReq | [JobSpec]); returns the answers in order."""
+    cfg = session.cfg
+    answers = [None] * len(reqs)
+    # final-phase job lists go through the per-spec path (few jobs, winning masks kept)
+    spec_jobs = [(i, r) for i, (_, r) in enumerate(reqs) if isinstance(r, list)]
+    src_jobs = [(i, v, r) for i, (v, r) in enumerate(reqs) if not isinstance(r, list)]
+    if src_jobs:
+        # geometry of all pending sources, batched per (video, kind); jobs keep request order
+        geo_rows = [None] * len(src_jobs)
+        by = {}
+        for k, (i, v, r) in enumerate(src_jobs):
+            by.setdefault((v, r.translation), []).append(k)
+        for (v, translation), ks in by.items():
+            g = session.rows(v).geometry([src_jobs[k][2].frame for k in ks], [src_jobs[k][2].box for k in ks],
+                                         translation, cfg)
+            for j, k in enumerate(ks):
+                geo_rows[k] = (g, j)
+        for translation in (True, False):
+            ks = [k for k, (i, v, r) in enumerate(src_jobs) if r.translation == translation]
+            if not ks:
+                continue
+            mode, grid = src_jobs[ks[0]][2].mode, src_jobs[ks[0]][2].grid
+            parts = []
+            for k in ks:
+                g, j = geo_rows[k]
+                parts.append(geometry.SourceGeometryRows(g.normal[j:j + 1], g.offset[j:j + 1], g.pts[j:j + 1],
+                                                         g.axis3d[j:j + 1], g.dir_vec[j:j + 1], g.pivot[j:j + 1]))
+            geo = geometry.concat_rows(parts)
+            xform, _ = _xforms_rows(geo.dir_vec, geo.pivot, grid, mode)
+            src = np.array([session.pool_of[src_jobs[k][1]][(src_jobs[k][2].frame, src_jobs[k][2].box)] for k in ks],
+                           dtype=np.int64)
+            ntg = np.array([len(src_jobs[k][2].targets) for k in ks], dtype=np.int64)
+            tgt = np.concatenate([np.asarray(src_jobs[k][2].targets, dtype=np.int32) for k in ks])
+            res = session.run_rows(src, np.full(len(ks), mode, dtype=np.int32), geo, xform, ntg, tgt, stats)
+            o = 0
+            for j, k in enumerate(ks):
+                i, v, r = src_jobs[k]
+                n = int(ntg[j])
+                n_boxes = int(session.videos[v][0][r.frame].pred_boxes.tensor.shape[0])
+                answers[i] = JobResult(res[0, o:o + n].copy(), res[3, o:o + n].copy().view(np.float32),
+                                       res[1, o:o + n].copy(), res[2, o:o + n].copy(),
+                                       geo=geo.row(j, r.box, n_boxes))
+                o += n
+    if spec_jobs:
+        flat, spans = [], []
+        for i, specs in spec_jobs:
+            spans.append((i, len(flat), len(specs)))
+            flat.extend(specs)
+        results = session.run(flat, stats)
+        for i, lo, n in spans:
+            answers[i] = results[lo:lo + n]
+    return answers
+
+
+def _drive(gens, session: _Session, stats: Stats, video_of=None):
+    """Run generators in lock-step: every scheduling step carries the pending request of each
+    still-active generator (``video_of[i]`` = video index of generator i)."""
+    video_of = video_of or [0] * len(gens)
     pending = {}
     for i, g in enumerate(gens):
         try:
@@ -490,21 +782,25 @@ def _drive(gens, session: _Session, stats: Stats):
             pass
     while pending:
         keys = list(pending.keys())
-        specs, spans = [], []
-        for k in keys:                       # a request is one JobSpec or a list of them
-            req = pending[k]
-            group = req if isinstance(req, list) else [req]
-            spans.append((len(specs), len(group), isinstance(req, list)))
-            specs.extend(group)
-        results, units = session.run(specs, stats)
-        stats.passes += 1
-        stats.jobs += len(specs)
-        stats.units_computed += units
-        for k, (lo, n, is_list) in zip(keys, spans):
+        answers = _answer_chain(session, [(video_of[k], pending[k]) for k in keys], stats)
+        for k, ans in zip(keys, answers):
             try:
-                pending[k] = gens[k].send(results[lo:lo + n] if is_list else results[lo])
+                pending[k] = gens[k].send(ans)
             except StopIteration:
                 del pending[k]
+
+
+def _use_tables(session: _Session, lists, cfg: OptConfig) -> bool:
+    """Schedule choice.  'table': the cluster phase of every track is answered from one all-sources
+    device pass (T x more device work, no host<->device round trip per round) — right when few videos
+    share the device and the rounds' latency dominates.  'chain': one pass per round carrying one job per
+    video — right for big batches, where the device work dominates."""
+    mode = os.environ.get("A3D_SCHEDULE") or cfg.schedule
+    if mode == "table":
+        return True
+    if mode == "chain":
+        return False
+    return session.table_units(lists) <= cfg.table_max_units
 
 
 def _default_device(device):
@@ -518,32 +814,55 @@ def _default_device(device):
 # ---------------------------------------------------------------------------
 # public API (reference signatures)
 # ---------------------------------------------------------------------------
+def _run_lists(session: _Session, video_lists, cfg: OptConfig, stats: Stats, legacy: bool = False):
+    """Drive track lists to completion.  ``video_lists``: per video a list of stages
+    ``(preds_fn, planes, translation, rng, after)``; the stages of a video run in order (their RNG
+    consumption is sequential), videos advance in lock-step.  ``preds_fn()`` gives the stage's input
+    predictions, ``after()`` is called when the stage is done (write-back)."""
+    lists = [(v, planes, translation) for v, stages in enumerate(video_lists)
+             for (_, planes, translation, _, _) in stages if planes]
+    tables = {}
+    if lists and session.pool is not None and _use_tables(session, lists, cfg):
+        stats.schedule = "table"
+        for (v, planes, translation), tabs in zip(lists, session.cluster_tables(lists, stats, legacy=legacy)):
+            tables[(v, translation)] = tabs
+    elif lists:
+        stats.schedule = "chain"
+
+    def video_gen(v, stages):
+        for preds_fn, planes, translation, rng, after in stages:
+            yield from _tracks_gen(preds_fn(), planes, cfg, translation, rng, session.pool_of[v], stats,
+                                   legacy=legacy, tables=tables.get((v, translation)))
+            after()
+
+    _drive([video_gen(v, stages) for v, stages in enumerate(video_lists)], session, stats,
+           video_of=list(range(len(video_lists))))
+
+
 def optimize_planes_3d_trans(preds, planes, frames=None, cfg=None, device=None, rng=None,
                              _session=None, stats=None):
     """Translation tracks (reference utils/opt_utils.py:685-959)."""
-    cfg, stats = cfg or OptConfig(), stats or Stats()
+    cfg, stats = cfg or OptConfig(), stats if stats is not None else Stats()
     session = _session or _Session([(preds, [planes])], cfg, _default_device(device))
-    _drive([_tracks_gen(preds, planes, cfg, True, rng or _global_random, session.pool_of[0], stats)],
-           session, stats)
+    _run_lists(session, [[(lambda: preds, planes, True, rng or _global_random, lambda: None)]], cfg, stats)
     return _write_back(preds, planes, cfg, 'trans')
 
 
 def optimize_planes_3dc(preds, planes, frames=None, cfg=None, device=None, rng=None,
                         _session=None, stats=None):
     """Rotation tracks with 3-D clustering (reference utils/opt_utils.py:382-682)."""
-    cfg, stats = cfg or OptConfig(), stats or Stats()
+    cfg, stats = cfg or OptConfig(), stats if stats is not None else Stats()
     session = _session or _Session([(preds, [planes])], cfg, _default_device(device))
-    _drive([_tracks_gen(preds, planes, cfg, False, rng or _global_random, session.pool_of[0], stats)],
-           session, stats)
+    _run_lists(session, [[(lambda: preds, planes, False, rng or _global_random, lambda: None)]], cfg, stats)
     return _write_back(preds, planes, cfg, 'rot')
 
 
 def optimize_planes_3d(preds, planes, cfg=None, device=None, rng=None, stats=None):
     """Legacy method '3d' (reference utils/opt_utils.py:112-379)."""
-    cfg, stats = cfg or OptConfig(), stats or Stats()
+    cfg, stats = cfg or OptConfig(), stats if stats is not None else Stats()
     session = _Session([(preds, [planes])], cfg, _default_device(device))
-    _drive([_tracks_gen(preds, planes, cfg, False, rng or _global_random, session.pool_of[0], stats,
-                        legacy=True)], session, stats)
+    _run_lists(session, [[(lambda: preds, planes, False, rng or _global_random, lambda: None)]], cfg, stats,
+               legacy=True)
     return _write_back(preds, planes, cfg, 'legacy')
 
 
@@ -566,6 +885,21 @@ def optimize_planes_average(preds, planes):
     return list(preds)
 
 
+def _video_stages(preds, planes, cfg, rng, out):
+    """The '3dc' method of one video as two stages: translation tracks on ``preds``, then rotation
+    tracks on the translation stage's output (reference :968-970).  ``out[0]`` receives the result."""
+    state = {"mid": None}
+
+    def after_trans():
+        state["mid"] = _write_back(preds, planes['trans'], cfg, 'trans')
+
+    def after_rot():
+        out[0] = _write_back(state["mid"], planes['rot'], cfg, 'rot')
+
+    return [(lambda: preds, planes['trans'], True, rng, after_trans),
+            (lambda: state["mid"], planes['rot'], False, rng, after_rot)]
+
+
 def optimize_planes(preds, planes, method, frames=None, cfg=None, device=None, stats=None):
     """Reference dispatcher (utils/opt_utils.py:962-974).  ``planes`` is the dict
     ``track_planes`` returns for '3dc', a list of tracks for 'average' / '3d'."""
@@ -578,10 +912,9 @@ def optimize_planes(preds, planes, method, frames=None, cfg=None, device=None, s
         stats = stats if stats is not None else Stats()
         session = _Session([(preds, [planes['trans'], planes['rot']])], cfg, _default_device(device))
         stats.h2d_bytes += session.h2d_bytes
-        opt_preds = optimize_planes_3d_trans(preds, planes['trans'], frames=frames, cfg=cfg,
-                                             _session=session, stats=stats)
-        return optimize_planes_3dc(opt_preds, planes['rot'], frames=frames, cfg=cfg,
-                                   _session=session, stats=stats)
+        out = [None]
+        _run_lists(session, [_video_stages(preds, planes, cfg, _global_random, out)], cfg, stats)
+        return out[0]
     else:
         raise NotImplementedError
 
@@ -591,23 +924,14 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
     ``(preds, planes)``; video i draws its source frames from
     ``random.Random(seeds[i])`` (the reference seeds one process per video,
     tools/inference.py:172), so the result of every video equals
-    ``random.seed(seeds[i]); optimize_planes(preds, planes, '3dc')``.  All videos
-    advance in lock-step: one device pass per chain step carries one job per
-    video."""
+    ``random.seed(seeds[i]); optimize_planes(preds, planes, '3dc')``.  All videos share one
+    device session; their cluster phases are answered from one all-sources pass (few videos) or
+    advance in lock-step, one job per video per device pass (many videos)."""
     cfg = cfg or OptConfig()
     stats = stats if stats is not None else Stats()
     session = _Session([(p, [pl['trans'], pl['rot']]) for p, pl in videos], cfg, _default_device(device))
     stats.h2d_bytes += session.h2d_bytes
-    rngs = [_global_random.Random(s) for s in seeds]
-
-    def video_gen(i):
-        preds, planes = videos[i]
-        yield from _tracks_gen(preds, planes['trans'], cfg, True, rngs[i], session.pool_of[i], stats)
-        mid = _write_back(preds, planes['trans'], cfg, 'trans')
-        outs[i] = mid
-        yield from _tracks_gen(mid, planes['rot'], cfg, False, rngs[i], session.pool_of[i], stats)
-        outs[i] = _write_back(mid, planes['rot'], cfg, 'rot')
-
-    outs = [None] * len(videos)
-    _drive([video_gen(i) for i in range(len(videos))], session, stats)
-    return outs
+    outs = [[None] for _ in videos]
+    _run_lists(session, [_video_stages(p, pl, cfg, _global_random.Random(s), o)
+                         for (p, pl), s, o in zip(videos, seeds, outs)], cfg, stats)
+    return [o[0] for o in outs]

@@ -238,8 +238,16 @@ def test_many_jobs_one_pass_equals_single_jobs(key, monkeypatch):
         assert np.array_equal(all_tab[t0:t0 + tn], r1.inter_tab.cpu().numpy())
 
 
+@pytest.fixture(params=["table", "chain"])
+def schedule(request, monkeypatch):
+    """Both host schedules of the cluster phase: one all-sources device pass + host replay, and one
+    device pass per round.  They must give identical results (same RNG draws, same clusters)."""
+    monkeypatch.setenv("A3D_SCHEDULE", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", gu.golden_cases())
-def test_optimize_planes_matches_reference_golden(name):
+def test_optimize_planes_matches_reference_golden(name, schedule):
     """End to end through the drop-in API against outputs of the unmodified reference."""
     z = gu.load(name)
     preds = gu.arrays_to_preds(z, Instances, Boxes)
@@ -249,10 +257,13 @@ def test_optimize_planes_matches_reference_golden(name):
     out = opt_utils.optimize_planes(preds, planes, '3dc', device=DEV, stats=stats)
     gu.check_against_golden(z, planes, out)
     assert stats.units_visited > 0 and stats.units_computed >= stats.units_visited
+    assert stats.schedule == schedule
+    if schedule == "table":                      # cluster table + one final pass per track list
+        assert stats.passes <= 4
 
 
 @pytest.mark.parametrize("seed,n_tracks,n_frames,drop", [(41, 4, 30, 0.0), (42, 5, 24, 0.1)])
-def test_optimize_planes_matches_oracle(seed, n_tracks, n_frames, drop):
+def test_optimize_planes_matches_oracle(seed, n_tracks, n_frames, drop, schedule):
     preds, _ = synth.make_video(seed, n_tracks, n_frames, drop_prob=drop)
     a, b = synth.clone_preds(preds), synth.clone_preds(preds)
     random.seed(seed)
@@ -292,7 +303,7 @@ def test_optimize_planes_matches_oracle(seed, n_tracks, n_frames, drop):
         np.testing.assert_allclose(x.pred_tran_axis.numpy(), y.pred_tran_axis.numpy(), rtol=1e-4, atol=1e-7)
 
 
-def test_legacy_and_average_methods_match_oracle():
+def test_legacy_and_average_methods_match_oracle(schedule):
     preds, _ = synth.make_video(51, 2, 14, kinds=[0, 0])
     for method in ("3d", "average"):
         a, b = synth.clone_preds(preds), synth.clone_preds(preds)
@@ -313,7 +324,7 @@ def test_legacy_and_average_methods_match_oracle():
             assert torch.equal(x.pred_rot_axis, y.pred_rot_axis)
 
 
-def test_optimize_videos_equals_per_video_calls():
+def test_optimize_videos_equals_per_video_calls(schedule):
     vids, seeds = [], [5, 6, 7]
     for s in seeds:
         preds, _ = synth.make_video(100 + s, 3, 16, kinds=[0, 1, 0])

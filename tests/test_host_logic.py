@@ -155,9 +155,13 @@ def test_removal_quirk_known_answer():
     def answer(sp):
         n = len(sp.targets)
         visits.append(n)
-        return opt_utils.JobResult(np.arange(n, dtype=np.int32) % len(sp.xform),
+        if isinstance(sp, opt_utils.SourceReq):         # a cluster round: the driver also hands back the geometry
+            n_cand, geo = len(sp.grid), geometry.source_geometry(preds[sp.frame], sp.box, cfg, False)
+        else:
+            n_cand, geo = len(sp.xform), None
+        return opt_utils.JobResult(np.arange(n, dtype=np.int32) % n_cand,
                                    np.full(n, 0.9, np.float32), np.ones(n, np.int32), np.ones(n, np.int32),
-                                   masks=torch.zeros(n, 1, 4, dtype=torch.int32))
+                                   masks=torch.zeros(n, 1, 4, dtype=torch.int32), geo=geo)
 
     try:
         while True:
@@ -281,3 +285,97 @@ def test_plan_tiles_argument_errors_and_degenerate_inputs():
     m = out[:n]
     assert int((m[:, 3] == 1).sum()) == 3 and int(m[m[:, 3] == 0][:, 2].sum()) == 135
     assert m[0, 0] == 2                                    # the job with the largest source mask leads
+
+
+def test_batched_source_geometry_is_bit_equal_to_per_source():
+    """geometry.source_geometry_rows / axis.angle_offset_to_axis_rows (array arithmetic over many sources)
+    against the per-source functions they vectorise, on synthetic clips and on perturbed axes that hit
+    the vertical / horizontal / missed-image branches."""
+    from articulation3d_b200 import axis as axis_mod
+    cfg = OptConfig()
+    rng = np.random.default_rng(1)
+    for seed in range(4):
+        preds, _ = synth.make_video(seed, 4, 12, cfg, kinds=[0, 1, 2, 0])
+        for trans in (False, True):
+            P, A, Cn, refs = [], [], [], []
+            for p in preds:
+                if seed >= 2:
+                    n = len(p.pred_rot_axis)
+                    p.pred_rot_axis = p.pred_rot_axis.clone()
+                    p.pred_rot_axis[:, 0] *= torch.tensor(rng.choice([0.0, 1.0, 1e-9, -1.0], size=n), dtype=torch.float32)
+                    p.pred_rot_axis[:, 1] *= torch.tensor(rng.choice([0.0, 1.0, 1.0], size=n), dtype=torch.float32)
+                    p.pred_rot_axis[:, 2] += torch.tensor(rng.standard_normal(n) * 3, dtype=torch.float32)
+                for b in range(len(p.pred_boxes)):
+                    refs.append((geometry.source_geometry(p, b, cfg, trans), b))
+                    P.append(p.pred_planes[b])
+                    Cn.append(p.pred_boxes.get_centers()[b])
+                    A.append(torch.cat((p.pred_tran_axis[b], torch.zeros(1))) if trans else p.pred_rot_axis[b])
+            R = geometry.source_geometry_rows(torch.stack(P), torch.stack(A), torch.stack(Cn), cfg)
+            for i, (g, b) in enumerate(refs):
+                assert np.array_equal(g.normal.numpy(), R.normal[i]) and float(g.offset) == float(R.offset[i])
+                assert np.array_equal(g.pts[b].numpy(), R.pts[i])
+                assert np.array_equal(g.axis3d, R.axis3d[i], equal_nan=True)
+                assert np.array_equal(g.dir_vec, R.dir_vec[i], equal_nan=True)
+                assert np.array_equal(g.pivot, R.pivot[i], equal_nan=True)
+                one = R.row(i, b, 4)
+                assert torch.equal(one.pts[b], g.pts[b]) and torch.equal(one.normal, g.normal)
+    # random lines, including degenerate ones, through the axis function alone
+    ao = rng.standard_normal((4000, 3)).astype(np.float32)
+    ao[::7, 0] = 0
+    ao[::11, 1] = 0
+    ao[::13, 2] = np.inf
+    ao[::17, 2] = np.nan
+    ce = (rng.random((4000, 2)) * [640, 480]).astype(np.float32)
+    want = axis_mod.angle_offset_to_axis(torch.from_numpy(ao), torch.from_numpy(ce)).numpy()
+    assert np.array_equal(axis_mod.angle_offset_to_axis_rows(ao, ce), want)
+
+
+def test_batched_candidate_transforms_equal_per_source():
+    cfg = OptConfig()
+    rng = np.random.default_rng(3)
+    d = rng.standard_normal((9, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    piv = rng.standard_normal((9, 3)).astype(np.float32)
+    R = geometry.rotation_matrices(cfg.rot_cluster_grid, d)
+    C = geometry.xforms_composed(geometry.rotation_matrices(cfg.rot_final_grid, d), piv)
+    Tr = geometry.xforms_translate(cfg.trans_grid, d)
+    for i in range(9):
+        assert np.array_equal(R[i], geometry.rotation_matrices(cfg.rot_cluster_grid, d[i]))
+        assert np.array_equal(C[i], geometry.xforms_composed(geometry.rotation_matrices(cfg.rot_final_grid, d[i]), piv[i]))
+        assert np.array_equal(Tr[i], geometry.xforms_translate(cfg.trans_grid, d[i]))
+
+
+def test_constant_track_r_switch():
+    """a constant angle list (static plane) is the degenerate case of linregress: r = 0.0 with
+    the scipy of the reference's era, NaN with scipy >= 1.9.  The default follows the installed scipy
+    (what the unmodified reference would do here); OptConfig.constant_track_r forces either."""
+    from scipy.stats import linregress as sp
+    y = np.full(7, 0.1047, np.float32)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        installed = float(sp(range(7), y).rvalue)
+    got = float(opt_utils._rvalue(y))
+    assert (np.isnan(installed) and np.isnan(got)) or installed == got
+    assert float(opt_utils._rvalue(y, 0.0)) == 0.0 and np.isnan(float(opt_utils._rvalue(y, float("nan"))))
+    # what it decides: with r = 0 a static track is filtered (has_rot False), with NaN it is kept
+    for r, keep in ((0.0, False), (float("nan"), True)):
+        rsqs = np.array([float(opt_utils._rvalue(y, r)) ** 2])
+        assert (not (rsqs.max() < OptConfig().rsq_thresh)) == keep
+
+
+def test_build_batch_rows_equals_build_batch():
+    rng = np.random.default_rng(5)
+    S = 5
+    n_cand, n_tgt = np.array([3, 3, 3, 3, 3]), np.array([2, 4, 1, 3, 2])
+    pts = rng.integers(1, 500, size=20)
+    src = rng.integers(0, 20, size=S)
+    normals, pivots = rng.standard_normal((S, 3)).astype(np.float32), rng.standard_normal((S, 3)).astype(np.float32)
+    offs = rng.random(S).astype(np.float32)
+    xf = rng.standard_normal((S, 3, 12)).astype(np.float32)
+    tg = [rng.integers(0, 20, size=k).astype(np.int32) for k in n_tgt]
+    a = engine.build_batch(list(src), [1] * S, list(normals), list(offs), list(pivots), list(xf), tg, pts)
+    b = engine.build_batch_rows(src, np.ones(S, np.int32), normals, offs, pivots, xf.reshape(-1, 12), n_cand,
+                                np.concatenate(tg), n_tgt, pts)
+    assert a.jobs.tobytes() == b.jobs.tobytes()
+    assert np.array_equal(a.xform, b.xform) and np.array_equal(a.tgt_index, b.tgt_index)

@@ -27,9 +27,10 @@ def run():
 
 
 run()
-t0 = time.perf_counter()
-st = run()
-print("wall ms", 1e3 * (time.perf_counter() - t0), st.passes, st.units_visited, st.units_computed)
+for _ in range(4):
+    t0 = time.perf_counter()
+    st = run()
+    print("wall ms %.2f" % (1e3 * (time.perf_counter() - t0)), st.schedule, st.passes, st.units_visited, st.units_computed)
 pr = cProfile.Profile()
 pr.enable()
 run()
