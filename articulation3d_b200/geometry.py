@@ -143,36 +143,40 @@ def source_geometry_rows(planes: torch.Tensor, axis: torch.Tensor, centers: torc
     return SourceGeometryRows(normal, offset, pts, axis3d, d, axis3d[:, 0].astype(np.float32))
 
 
-# quaternion -> matrix entry e = two_s * (q_a q_b + sign * q_c q_d), diagonal entries 1 - e;
-# indices into the flattened 4x4 table of products of q = (r, i, j, k)
-_QM_FIRST = torch.tensor([10, 6, 7, 6, 5, 11, 7, 11, 5])          # jj ij ik | ij ii jk | ik jk ii
-_QM_SECOND = torch.tensor([15, 12, 8, 12, 15, 4, 8, 4, 10])       # kk kr jr | kr kk ir | jr ir jj
-_QM_SIGN = torch.tensor([1., -1., 1., 1., 1., -1., -1., 1., 1.], dtype=torch.float64)
-_QM_DIAG = torch.tensor([0, 4, 8])
-
-
 def _axis_angle_to_matrix(axis_angle: torch.Tensor) -> torch.Tensor:
     """Rotation matrices of axis-angle vectors via unit quaternions, in the input
     dtype (float64 here) — the construction pytorch3d's ``axis_angle_to_matrix``
     documents: q = [cos(t/2), v sin(t/2)/t] (Taylor 1/2 - t^2/48 for |t| < 1e-6),
     R from two_s = 2/|q|^2, e.g. R00 = 1 - two_s (jj + kk), R01 = two_s (ij - kr).
-    The nine entries are evaluated together from the table of pairwise products — the same
-    multiplications, additions (x - y as x + (-1) y) and order per entry, so the same bits."""
+    The two reductions (|v|, |q|^2) are torch's; the nine entries are evaluated column-wise on the
+    quaternion components — per entry the same multiplications and additions in the same order
+    (IEEE elementwise, so the same bits; tests/test_host_logic.py compares with the oracle's form)."""
     t = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
     half = t * 0.5
-    small = t.abs() < 1e-6
-    if bool(small.any()):
-        k = torch.empty_like(t)
-        k[~small] = torch.sin(half[~small]) / t[~small]
-        k[small] = 0.5 - (t[small] * t[small]) / 48
-    else:                                   # same elementwise values, without the masked gathers/scatters
-        k = torch.sin(half) / t
-    q = torch.cat([torch.cos(half), axis_angle * k], dim=-1)
-    two_s = 2.0 / (q * q).sum(-1, keepdim=True)
-    prod = (q.unsqueeze(-1) * q.unsqueeze(-2)).flatten(-2)
-    m = two_s * (prod.index_select(-1, _QM_FIRST) + _QM_SIGN.to(q.dtype) * prod.index_select(-1, _QM_SECOND))
-    m[..., _QM_DIAG] = 1 - m[..., _QM_DIAG]
-    return m.reshape(q.shape[:-1] + (3, 3))
+    with np.errstate(all="ignore"):
+        tn = t.numpy()
+        k = (torch.sin(half) / t).numpy()           # torch's sin: numpy's float64 sin differs in the last ulp
+        small = np.abs(tn) < 1e-6
+        if small.any():
+            k = np.where(small, 0.5 - (tn * tn) / 48, k)
+        q = torch.cat([torch.cos(half), axis_angle * torch.from_numpy(k)], dim=-1)
+        two_s = (2.0 / (q * q).sum(-1)).numpy()
+        qn = q.numpy()
+        r, i, j, kk = qn[..., 0], qn[..., 1], qn[..., 2], qn[..., 3]
+        ii, jj, k2 = i * i, j * j, kk * kk
+        ij, ik, jk = i * j, i * kk, j * kk
+        ir, jr, kr = i * r, j * r, kk * r
+        m = np.empty(qn.shape[:-1] + (3, 3), dtype=qn.dtype)
+        m[..., 0, 0] = 1 - two_s * (jj + k2)
+        m[..., 0, 1] = two_s * (ij - kr)
+        m[..., 0, 2] = two_s * (ik + jr)
+        m[..., 1, 0] = two_s * (ij + kr)
+        m[..., 1, 1] = 1 - two_s * (ii + k2)
+        m[..., 1, 2] = two_s * (jk - ir)
+        m[..., 2, 0] = two_s * (ik - jr)
+        m[..., 2, 1] = two_s * (jk + ir)
+        m[..., 2, 2] = 1 - two_s * (ii + jj)
+    return torch.from_numpy(m)
 
 
 def rotation_matrices(grid, dir_vec) -> np.ndarray:

@@ -109,40 +109,66 @@ def _box_iou_f32(a, b) -> float:
     return float(f(inter / f(f(area_a + area_b) - inter)))
 
 
+def _box_iou_f32_arrays(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """``_box_iou_f32`` over broadcastable (..., 4) fp32 arrays: the same fp32 operations per pair."""
+    with np.errstate(all="ignore"):
+        iw = np.minimum(a[..., 2], b[..., 2]) - np.maximum(a[..., 0], b[..., 0])
+        ih = np.minimum(a[..., 3], b[..., 3]) - np.maximum(a[..., 1], b[..., 1])
+        inter = iw * ih
+        area_a = (a[..., 2] - a[..., 0]) * (a[..., 3] - a[..., 1])
+        area_b = (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
+        iou = inter / ((area_a + area_b) - inter)
+        return np.where((iw > 0) & (ih > 0), iou, np.float32(0.0)).astype(np.float32)
+
+
 def track_planes(preds, cfg: OptConfig | None = None):
     """Greedy online box tracker -> {'rot': [...], 'trans': [...]}; each track is
     {'bbox', 'ids': {frame: box_id}, 'latest_frame'}.  A box joins the FIRST live
     track of its class (class 1 -> 'trans') whose latest box overlaps it with
     IoU > 0.5 and whose gap is <= 5 frames; tracks shorter than 10 frames are
-    dropped.  Box IoUs are evaluated on fp32 scalars (same roundings as the
-    reference's tensor ops) instead of one tiny tensor program per pair."""
+    dropped (reference utils/opt_utils.py:1156-1208).
+
+    A track's latest box is always a box of one of the last ``gap + 1`` frames (the current one
+    included: a second box of a frame can match a track the first one just joined), so all box IoUs
+    the greedy loop can ask for are evaluated up front in one fp32 array computation (the reference's
+    operations per pair, same roundings) and the sequential part is list look-ups."""
     cfg = cfg or OptConfig()
+    gap, thr = int(cfg.track_max_gap), cfg.track_iou
+    T = len(preds)
+    rows = [p.pred_boxes.tensor.detach().cpu().numpy().astype(np.float32, copy=False).reshape(-1, 4) for p in preds]
+    counts = [len(r) for r in rows]
+    nb = max(counts, default=0)
     planes = {'rot': [], 'trans': []}
-    for idx, p_instance in enumerate(preds):
-        pred_classes = p_instance.pred_classes
-        pred_boxes = p_instance.pred_boxes
-        rows = pred_boxes.tensor.detach().cpu().numpy().astype(np.float32, copy=False)
-        for box_id in range(rows.shape[0]):
-            cur = rows[box_id]
-            cat = 'trans' if pred_classes[box_id] == 1 else 'rot'
-            matched = False
-            for plane in planes[cat]:
-                if idx - plane['latest_frame'] > cfg.track_max_gap:
-                    continue
-                if _box_iou_f32(cur, plane['_row']) > cfg.track_iou:
-                    plane['ids'][idx] = box_id
-                    plane['bbox'] = pred_boxes[box_id]
-                    plane['_row'] = cur
-                    plane['latest_frame'] = idx
-                    matched = True
-                    break
-            if not matched:
-                planes[cat].append({'bbox': pred_boxes[box_id], 'ids': {idx: box_id}, 'latest_frame': idx,
-                                    '_row': cur})
+    if nb:
+        boxes = np.zeros((T, nb, 4), dtype=np.float32)
+        for t, r in enumerate(rows):
+            boxes[t, :len(r)] = r
+        iou = []                                   # iou[d][t][i][j]: box i of frame t vs box j of frame t - d
+        for d in range(min(gap, T - 1) + 1):
+            m = np.zeros((T, nb, nb), dtype=np.float32)
+            m[d:] = _box_iou_f32_arrays(boxes[d:, :, None, :], boxes[:T - d, None, :, :])
+            iou.append(m.tolist())
+        for idx in range(T):
+            cls = np.asarray(preds[idx].pred_classes).reshape(-1).tolist()
+            for box_id in range(counts[idx]):
+                cat = 'trans' if cls[box_id] == 1 else 'rot'
+                matched = False
+                for plane in planes[cat]:
+                    d = idx - plane['latest_frame']
+                    if d > gap:
+                        continue
+                    if iou[d][idx][box_id][plane['_box']] > thr:
+                        plane['ids'][idx] = box_id
+                        plane['_box'] = box_id
+                        plane['latest_frame'] = idx
+                        matched = True
+                        break
+                if not matched:
+                    planes[cat].append({'bbox': None, 'ids': {idx: box_id}, 'latest_frame': idx, '_box': box_id})
     for cat in planes:
         planes[cat] = [p for p in planes[cat] if len(p['ids']) >= cfg.track_min_len]
         for p in planes[cat]:
-            del p['_row']
+            p['bbox'] = preds[p['latest_frame']].pred_boxes[p.pop('_box')]
     return planes
 
 
@@ -441,50 +467,57 @@ def _has(p_instance, name: str) -> bool:
 
 
 def _write_back(preds, planes, cfg: OptConfig, kind: str):
-    """kind: 'rot' | 'trans' | 'legacy'."""
-    # rotation tracks: the fitted axis re-expressed relative to every frame's box centre.  The
-    # reference does this one (frame, track) at a time (:646-651); the arithmetic is elementwise
-    # fp32, so one call per track over all its frames gives the same bits.
-    new_axis = {}
-    if kind == 'rot':
-        for ti, plane in enumerate(planes):
-            if not plane['has_rot'] or not plane['ids']:
-                continue
-            frames = list(plane['ids'].keys())
-            centers = torch.stack([preds[f].pred_boxes.tensor[plane['ids'][f]] for f in frames])
-            centers = (centers[:, :2] + centers[:, 2:]) / 2
+    """kind: 'rot' | 'trans' | 'legacy'.  The reference walks frames x tracks with one small tensor
+    operation per (frame, track) (:624-682, :910-959); the arithmetic is elementwise fp32, so here all
+    boxes of the video sit in flat arrays, every track is one gather / scatter, and the per-frame
+    outputs are disjoint slices of those arrays (same values, same bits)."""
+    n_frames = len(preds)
+    counts = [int(p.pred_boxes.tensor.shape[0]) for p in preds]
+    base = np.zeros(n_frames + 1, dtype=np.int64)
+    np.cumsum(counts, out=base[1:])
+    n = int(base[-1])
+    classes = (np.concatenate([np.asarray(p.pred_classes).reshape(-1) for p in preds]) if n_frames
+               else np.zeros(0, dtype=np.int64))
+    if kind == 'legacy':
+        chosen = np.zeros(n, dtype=bool)
+    else:                                            # the other articulation type is never filtered
+        chosen = classes == (1 if kind == 'rot' else 0)
+    rot_axis = plane_rows = centers = None
+    if kind == 'rot' and n_frames:
+        rot_axis = torch.cat([p.pred_rot_axis for p in preds])          # new storage = the reference's clones
+        plane_rows = torch.cat([p.pred_planes for p in preds])
+        b = torch.cat([p.pred_boxes.tensor for p in preds])
+        centers = (b[:, :2] + b[:, 2:]) / 2
+    for plane in planes:
+        ids = plane['ids']
+        if not ids:
+            continue
+        rows = base[np.fromiter(ids.keys(), dtype=np.int64, count=len(ids))] + \
+            np.fromiter(ids.values(), dtype=np.int64, count=len(ids))
+        if not plane['has_rot']:
+            chosen[rows] = False
+            continue
+        chosen[rows] = True
+        if kind == 'rot':
             line = plane['std_axis'].unsqueeze(0).numpy().tolist()
-            new_axis[ti] = dict(zip(frames, axis_to_angle_offset(line * len(frames), centers)[:, :3]))
+            r = torch.from_numpy(rows)
+            rot_axis[r] = axis_to_angle_offset(line * len(ids), centers[r])[:, :3]
+        elif kind == 'trans':
+            for f, bx in ids.items():
+                preds[f].pred_tran_axis[bx] = plane['std_axis']     # in place, like the reference
+    scores = (np.concatenate([np.asarray(p.scores).reshape(-1) for p in preds]) if n_frames
+              else np.zeros(0))
+    if scores.dtype.kind != 'f':
+        scores = scores.astype(np.float64)
+    decay = cfg.legacy_score_decay if kind == 'legacy' else cfg.score_decay
+    scores[~chosen] = scores[~chosen] * decay
     opt_preds = []
     for idx, p_instance in enumerate(preds):
-        pred_boxes = p_instance.pred_boxes
-        pred_classes = p_instance.pred_classes
-        chosen = [False] * pred_boxes.tensor.shape[0]
-        if kind != 'legacy':
-            keep_class = 1 if kind == 'rot' else 0          # the other articulation type is never filtered
-            for i in range(pred_classes.size):
-                if pred_classes[i] == keep_class:
-                    chosen[i] = True
+        lo, hi = int(base[idx]), int(base[idx + 1])
         if kind == 'rot':
-            p_instance.pred_rot_axis = p_instance.pred_rot_axis.clone()
-            p_instance.pred_planes = p_instance.pred_planes.clone()
-        for ti, plane in enumerate(planes):
-            if idx not in plane['ids']:
-                continue
-            box_id = plane['ids'][idx]
-            if not plane['has_rot']:
-                chosen[box_id] = False
-                continue
-            chosen[box_id] = True
-            if kind == 'rot':
-                p_instance.pred_rot_axis[box_id] = new_axis[ti][idx]
-            elif kind == 'trans':
-                p_instance.pred_tran_axis[box_id] = plane['std_axis']     # in place, like the reference
-        chosen = np.array(chosen, dtype=bool)
-        scores = np.copy(p_instance.scores)
-        decay = cfg.legacy_score_decay if kind == 'legacy' else cfg.score_decay
-        scores[~chosen] = scores[~chosen] * decay
-        opt_preds.append(_rebuild(p_instance, scores))
+            p_instance.pred_rot_axis = rot_axis[lo:hi]
+            p_instance.pred_planes = plane_rows[lo:hi]
+        opt_preds.append(_rebuild(p_instance, scores[lo:hi]))
     return opt_preds
 
 

@@ -379,3 +379,82 @@ def test_build_batch_rows_equals_build_batch():
                                 np.concatenate(tg), n_tgt, pts)
     assert a.jobs.tobytes() == b.jobs.tobytes()
     assert np.array_equal(a.xform, b.xform) and np.array_equal(a.tgt_index, b.tgt_index)
+
+
+def test_track_planes_stress_matches_oracle():
+    """Frames with duplicated / overlapping boxes (a second box of a frame matching a track the first one
+    just joined), gaps up to and beyond the limit, empty frames, both classes."""
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        T = 40
+        preds = []
+        anchors = rng.random((4, 2)) * [400, 300] + 40
+        for t in range(T):
+            rows, cls = [], []
+            for k in range(4):
+                if rng.random() < 0.25:
+                    continue
+                for _ in range(1 + int(rng.random() < 0.3)):        # sometimes the same box twice (jittered)
+                    c = anchors[k] + rng.normal(0, 4 + 6 * trial / 5, 2)
+                    w, h = 80 + rng.normal(0, 6), 60 + rng.normal(0, 6)
+                    rows.append([c[0], c[1], c[0] + w, c[1] + h])
+                    cls.append(k % 2)
+            if t % 13 == 12:
+                rows, cls = [], []
+            inst = Instances((480, 640))
+            inst.pred_boxes = Boxes(torch.tensor(rows, dtype=torch.float32).reshape(-1, 4))
+            inst.pred_classes = np.array(cls, dtype=np.int64)
+            preds.append(inst)
+        a = opt_utils.track_planes(preds)
+        b = restated.track_planes(preds)
+        for cat in ("rot", "trans"):
+            assert [p['ids'] for p in a[cat]] == [p['ids'] for p in b[cat]]
+            assert [p['latest_frame'] for p in a[cat]] == [p['latest_frame'] for p in b[cat]]
+            for p, q in zip(a[cat], b[cat]):
+                assert torch.equal(p['bbox'].tensor, q['bbox'].tensor)
+        assert sum(len(a[c]) for c in a) > 0
+
+
+def test_write_back_matches_oracle(monkeypatch):
+    """opt_utils._write_back (flat-array form) against the oracle's frame x track loops, with the same
+    decided tracks: scores, rewritten rotation axes, in-place translation axes, untouched fields."""
+    cfg = OptConfig()
+    preds, _ = synth.make_video(31, 5, 16, cfg, kinds=[0, 1, 0, 1, 2], drop_prob=0.15)
+    rng = np.random.default_rng(2)
+
+    def decide(planes, translation, src_preds):
+        for plane in planes:
+            plane['has_rot'] = bool(rng.random() < 0.6)
+            if plane['has_rot']:
+                f0 = next(iter(plane['ids']))
+                plane['std_axis'] = (src_preds[f0].pred_tran_axis[plane['ids'][f0]] if translation
+                                     else torch.tensor(rng.integers(0, 480, 4), dtype=torch.int64))
+
+    for kind, translation in (("trans", True), ("rot", False)):
+        a, b = synth.clone_preds(preds), synth.clone_preds(preds)
+        pa, pb = opt_utils.track_planes(a)[kind], restated.track_planes(b)[kind]
+        state = rng.bit_generator.state
+        decide(pa, translation, a)
+        rng.bit_generator.state = state
+        decide(pb, translation, b)
+        monkeypatch.setattr(restated, "_optimize_tracks", lambda *args, **kw: None)
+        want = (restated.optimize_planes_3d_trans if translation else restated.optimize_planes_3dc)(b, pb)
+        got = opt_utils._write_back(a, pa, cfg, kind)
+        assert len(got) == len(want)
+        for x, y, xin, yin in zip(got, want, a, b):
+            assert np.array_equal(x.scores, y.scores) and x.scores.dtype == y.scores.dtype
+            assert torch.equal(x.pred_rot_axis, y.pred_rot_axis) and torch.equal(x.pred_tran_axis, y.pred_tran_axis)
+            assert torch.equal(x.pred_planes, y.pred_planes)
+            assert x.pred_boxes is xin.pred_boxes and x.pred_masks is xin.pred_masks
+            assert torch.equal(xin.pred_tran_axis, yin.pred_tran_axis) and torch.equal(xin.pred_rot_axis, yin.pred_rot_axis)
+
+
+def test_axis_angle_matrices_equal_oracle_form():
+    """geometry._axis_angle_to_matrix (column-wise numpy form) against the oracle's statement of
+    pytorch3d's construction, incl. the small-angle branch and a zero vector: same float64 bits."""
+    rng = np.random.default_rng(0)
+    aa = torch.from_numpy(rng.standard_normal((300, 45, 3)) * np.exp(rng.standard_normal((300, 45, 1)) * 3))
+    aa[::9] *= 1e-8
+    aa[5, 3] = 0
+    a, b = geometry._axis_angle_to_matrix(aa), restated.axis_angle_to_matrix64(aa)
+    assert torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))
