@@ -140,10 +140,21 @@ def load_predictions(path: str):
     return torch.load(path, map_location="cpu", weights_only=False)
 
 
+def video_key(file_name: str):
+    """(video id, frame offset) of a record's file name ``<youtube id>_<shot>_<frame>_<offset>.png``:
+    video id = ``{youtube_id}_{shot_id}_{frame_id}`` with the 11-character YouTube id, exactly as
+    tools/opt_arti.py:60-76 builds it (two clips cut from the same YouTube video are two videos)."""
+    stem = file_name.split('/')[-1].replace('.png', '')
+    parts = stem.split('_')
+    shot_id, frame_id, frame_offset = int(parts[-3]), int(parts[-2]), int(parts[-1])
+    return '{}_{}_{}'.format(stem[:11], shot_id, frame_id), frame_offset
+
+
 def group_by_video(predictions):
-    """video id = first 11 characters of file_name, as tools/opt_arti.py:60-76."""
+    """Records grouped per video id (``video_key``), each group ordered by frame offset; videos in
+    order of first appearance (tools/opt_arti.py:60-76)."""
     out = {}
     for p in predictions:
-        name = p["file_name"].split("/")[-1]
-        out.setdefault(name[:11], []).append(p)
-    return out
+        vid, off = video_key(p["file_name"])
+        out.setdefault(vid, {})[off] = p            # a repeated offset replaces the record, as the reference's dict does
+    return {vid: [frames[k] for k in sorted(frames)] for vid, frames in out.items()}

@@ -52,20 +52,21 @@ def pack_records(video_ids, planes_list):
 
 def all_gather_rows(local: torch.Tensor, group=None) -> torch.Tensor:
     """Concatenate 2-D int32 tables of different lengths from all ranks (rank order).
-    One size exchange + one padded all_gather; works with nccl (CUDA tensors) and gloo."""
+    One size exchange + ONE padded ``all_gather_into_tensor``; works with nccl (CUDA tensors) and gloo."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
     n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    sizes = torch.zeros(world, dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    sizes = sizes.tolist()
     mx = max(sizes + [1])
-    padded = torch.zeros(mx, local.shape[1], dtype=local.dtype, device=local.device)
+    cols = local.shape[1]
+    padded = torch.zeros(mx, cols, dtype=local.dtype, device=local.device)
     padded[: local.shape[0]] = local
-    out = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(out, padded, group=group)
-    return torch.cat([o[:s] for o, s in zip(out, sizes)])
+    out = torch.empty(world * mx, cols, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * mx: r * mx + s] for r, s in enumerate(sizes)])
 
 
 def optimize_videos_sharded(videos, seeds, cfg=None, device=None, optimize_fn=None, group=None):

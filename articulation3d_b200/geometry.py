@@ -137,8 +137,8 @@ def source_geometry_rows(planes: torch.Tensor, axis: torch.Tensor, centers: torc
             depth = off / ((nn[:, 0] * rx + nn[:, 1] * ry) + nn[:, 2] * rz)
             axis3d[:, e, 0], axis3d[:, e, 1], axis3d[:, e, 2] = depth * rx, depth * ry, depth * rz
         d = axis3d[:, 1] - axis3d[:, 0]
-        norm = np.linalg.norm
-        length = np.fromiter((norm(v) for v in d), dtype=np.float64, count=n)
+        # np.linalg.norm of a 1-D vector is sqrt(v.dot(v)); the dot product stays the per-source BLAS call
+        length = np.sqrt(np.fromiter((v.dot(v) for v in d), dtype=np.float64, count=n))
         d = d / length[:, None]
     return SourceGeometryRows(normal, offset, pts, axis3d, d, axis3d[:, 0].astype(np.float32))
 
@@ -148,44 +148,40 @@ def _axis_angle_to_matrix(axis_angle: torch.Tensor) -> torch.Tensor:
     dtype (float64 here) — the construction pytorch3d's ``axis_angle_to_matrix``
     documents: q = [cos(t/2), v sin(t/2)/t] (Taylor 1/2 - t^2/48 for |t| < 1e-6),
     R from two_s = 2/|q|^2, e.g. R00 = 1 - two_s (jj + kk), R01 = two_s (ij - kr).
-    The two reductions (|v|, |q|^2) are torch's; the nine entries are evaluated column-wise on the
-    quaternion components — per entry the same multiplications and additions in the same order
-    (IEEE elementwise, so the same bits; tests/test_host_logic.py compares with the oracle's form)."""
+    Returns (..., 9) row-major entries.  All steps are torch ops (its sin/cos and its reductions: numpy's
+    float64 sin differs in the last ulp); the nine entries are evaluated on contiguous component
+    planes — per entry the same multiplications and additions in the same order as the oracle's form
+    (tests/test_host_logic.py compares the bits)."""
     t = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
     half = t * 0.5
-    with np.errstate(all="ignore"):
-        tn = t.numpy()
-        k = (torch.sin(half) / t).numpy()           # torch's sin: numpy's float64 sin differs in the last ulp
-        small = np.abs(tn) < 1e-6
-        if small.any():
-            k = np.where(small, 0.5 - (tn * tn) / 48, k)
-        q = torch.cat([torch.cos(half), axis_angle * torch.from_numpy(k)], dim=-1)
-        two_s = (2.0 / (q * q).sum(-1)).numpy()
-        qn = q.numpy()
-        r, i, j, kk = qn[..., 0], qn[..., 1], qn[..., 2], qn[..., 3]
-        ii, jj, k2 = i * i, j * j, kk * kk
-        ij, ik, jk = i * j, i * kk, j * kk
-        ir, jr, kr = i * r, j * r, kk * r
-        m = np.empty(qn.shape[:-1] + (3, 3), dtype=qn.dtype)
-        m[..., 0, 0] = 1 - two_s * (jj + k2)
-        m[..., 0, 1] = two_s * (ij - kr)
-        m[..., 0, 2] = two_s * (ik + jr)
-        m[..., 1, 0] = two_s * (ij + kr)
-        m[..., 1, 1] = 1 - two_s * (ii + k2)
-        m[..., 1, 2] = two_s * (jk - ir)
-        m[..., 2, 0] = two_s * (ik - jr)
-        m[..., 2, 1] = two_s * (jk + ir)
-        m[..., 2, 2] = 1 - two_s * (ii + jj)
-    return torch.from_numpy(m)
+    k = torch.sin(half) / t
+    small = t.abs() < 1e-6
+    if bool(small.any()):
+        k = torch.where(small, 0.5 - (t * t) / 48, k)
+    q = torch.cat([torch.cos(half), axis_angle * k], dim=-1)
+    two_s = 2.0 / (q * q).sum(-1)
+    qt = q.movedim(-1, 0).contiguous()
+    r, i, j, kk = qt[0], qt[1], qt[2], qt[3]
+    ii, jj, k2 = i * i, j * j, kk * kk
+    ij, ik, jk = i * j, i * kk, j * kk
+    ir, jr, kr = i * r, j * r, kk * r
+    return torch.stack((1 - two_s * (jj + k2), two_s * (ij - kr), two_s * (ik + jr),
+                        two_s * (ij + kr), 1 - two_s * (ii + k2), two_s * (jk - ir),
+                        two_s * (ik - jr), two_s * (jk + ir), 1 - two_s * (ii + jj)), -1)
+
+
+def _rotation_entries(grid, dir_vec) -> torch.Tensor:
+    """(A,) grid x (..., 3) float64 axis -> (..., A, 9) float64 entries: fp32 angles times the float64
+    axis, matrix in float64."""
+    angles = torch.as_tensor(np.asarray(grid), dtype=torch.float32)[:, None]       # (A,1)
+    d = torch.as_tensor(np.asarray(dir_vec, dtype=np.float64))
+    return _axis_angle_to_matrix(angles * d[..., None, :])
 
 
 def rotation_matrices(grid, dir_vec) -> np.ndarray:
-    """(A,) grid x (..., 3) float64 axis -> (..., A, 3, 3) fp32.  fp32 angles times the
-    float64 axis, matrix in float64, stored fp32 (what ``Rotate`` keeps)."""
-    angles = torch.as_tensor(np.asarray(grid), dtype=torch.float32)[:, None]       # (A,1)
-    d = torch.as_tensor(np.asarray(dir_vec, dtype=np.float64))
-    aa = angles * d[..., None, :]                                                  # float64
-    return _axis_angle_to_matrix(aa).to(torch.float32).numpy()
+    """(A,) grid x (..., 3) float64 axis -> (..., A, 3, 3) fp32 (what ``Rotate`` keeps)."""
+    m = _rotation_entries(grid, dir_vec)
+    return m.to(torch.float32).reshape(m.shape[:-1] + (3, 3)).numpy()
 
 
 def xforms_seq(R: np.ndarray) -> np.ndarray:
@@ -193,6 +189,14 @@ def xforms_seq(R: np.ndarray) -> np.ndarray:
     out = np.zeros(R.shape[:-2] + (12,), dtype=np.float32)
     out[..., :9] = R.reshape(R.shape[:-2] + (9,))
     return out
+
+
+def xforms_seq_from_dirs(grid, dir_vec) -> np.ndarray:
+    """``xforms_seq(rotation_matrices(grid, dir_vec))`` without the intermediate copies."""
+    m = _rotation_entries(grid, dir_vec)
+    out = torch.zeros(m.shape[:-1] + (12,), dtype=torch.float32)
+    out[..., :9] = m                                  # float64 -> fp32 rounding, as Rotate stores it
+    return out.numpy()
 
 
 def xforms_composed(R: np.ndarray, pivot: np.ndarray) -> np.ndarray:

@@ -31,6 +31,7 @@ from __future__ import annotations
 
 import os
 import random as _global_random
+import threading
 from collections.abc import Mapping
 from dataclasses import dataclass, field
 
@@ -286,9 +287,9 @@ def _xforms_rows(dir_vec: np.ndarray, pivot: np.ndarray, grid, mode: int):
     """Candidate transforms of n sources at once: (n, A, 12) fp32 and R (n, A, 3, 3) or None."""
     if mode == _lib.MODE_TRANSLATE:
         return geometry.xforms_translate(grid, dir_vec), None
-    R = geometry.rotation_matrices(grid, dir_vec)
     if mode == _lib.MODE_SEQ:
-        return geometry.xforms_seq(R), R
+        return geometry.xforms_seq_from_dirs(grid, dir_vec), None
+    R = geometry.rotation_matrices(grid, dir_vec)
     return geometry.xforms_composed(R, pivot), R
 
 
@@ -562,16 +563,48 @@ class _Session:
                     n += 1
             self.pool_of.append(index)
         self.h2d_bytes = 0
+        self.n_masks = n
+        self._pool = None
+        self._uploader = self._upload_error = self._upload_done = None
         if n == 0:
-            self.pool = None
             return
         if rles:
             if chunks:
                 raise ValueError("mixing dense pred_masks and pred_rle frames is not supported")
-            self.pool = engine.rle_to_pool(rles, cfg.height, cfg.width, self.device)
+            self._pool = engine.rle_to_pool(rles, cfg.height, cfg.width, self.device)
             self.h2d_bytes += sum(len(r["counts"]) for r in rles)
             return
-        self.pool = self._upload(chunks, n)
+        self.h2d_bytes += sum(c.numel() * c.element_size() for c in chunks if not c.is_cuda)
+        # The upload runs on its own stream from a helper thread, so the host-side preparation of the first
+        # pass (source geometry, candidate transforms) and — with several videos — the device passes of the
+        # previous video overlap the H2D copies, also when the driver makes the copy calls block.
+        self._upload_stream = torch.cuda.Stream(device=self.device)
+        self._uploader = threading.Thread(target=self._upload_worker, args=(chunks, n), daemon=True)
+        self._uploader.start()
+
+    @property
+    def pool(self):
+        """The packed mask pool; the first access waits for the upload thread and orders the current
+        stream after the upload stream."""
+        if self._uploader is not None:
+            self._uploader.join()
+            self._uploader = None
+            if self._upload_error is not None:
+                raise self._upload_error
+            torch.cuda.current_stream(self.device).wait_event(self._upload_done)
+            for t in (self._pool.bits, self._pool.popc, self._pool.bbox) + tuple(self._pool._nz_pending or ()):
+                t.record_stream(torch.cuda.current_stream(self.device))
+        return self._pool
+
+    def _upload_worker(self, chunks, n):
+        try:
+            torch.cuda.set_device(self.device)
+            with torch.cuda.stream(self._upload_stream):
+                self._pool = self._upload(chunks, n)
+                self._upload_done = torch.cuda.Event()
+                self._upload_done.record()
+        except BaseException as e:                     # re-raised by the thread that asks for the pool
+            self._upload_error = e
 
     def _upload(self, chunks, n) -> engine.MaskPool:
         """Dense per-frame masks -> packed pool.  The frames are copied (asynchronously when the host
@@ -601,8 +634,6 @@ class _Session:
             if fill + k > cap:
                 builder.append(stage[:fill])
                 fill = 0
-            if not c.is_cuda:
-                self.h2d_bytes += c.numel() * c.element_size()
             stage[fill:fill + k].copy_(c, non_blocking=True)
             fill += k
         if fill:
@@ -737,14 +768,13 @@ class _Session:
                 o += T * T
         return out
 
-    def table_units(self, lists) -> int:
-        """Device work of the all-sources schedule for these track lists, in units."""
-        cfg = self.cfg
-        u = 0
-        for v, planes, translation in lists:
-            a = len(cfg.trans_grid) if translation else len(cfg.rot_cluster_grid)
-            u += sum(len(p['ids']) ** 2 for p in planes) * a
-        return u
+def _table_units(lists, cfg: OptConfig) -> int:
+    """Device work of the all-sources schedule for these track lists, in units."""
+    u = 0
+    for _, planes, translation in lists:
+        a = len(cfg.trans_grid) if translation else len(cfg.rot_cluster_grid)
+        u += sum(len(p['ids']) ** 2 for p in planes) * a
+    return u
 
 
 def _answer_chain(session: _Session, reqs, stats: Stats):
@@ -823,17 +853,18 @@ def _drive(gens, session: _Session, stats: Stats, video_of=None):
                 del pending[k]
 
 
-def _use_tables(session: _Session, lists, cfg: OptConfig) -> bool:
+def _use_tables(lists, cfg: OptConfig) -> bool:
     """Schedule choice.  'table': the cluster phase of every track is answered from one all-sources
-    device pass (T x more device work, no host<->device round trip per round) — right when few videos
-    share the device and the rounds' latency dominates.  'chain': one pass per round carrying one job per
-    video — right for big batches, where the device work dominates."""
+    device pass (T x more device work, no host<->device round trip per round) — right when the rounds'
+    latency dominates, and whenever the masks arrive as dense host arrays (their H2D copy then costs more
+    than the table pass, which hides behind it).  'chain': one pass per round carrying one job per
+    video — right for big batches of cheap inputs, where the device work dominates."""
     mode = os.environ.get("A3D_SCHEDULE") or cfg.schedule
     if mode == "table":
         return True
     if mode == "chain":
         return False
-    return session.table_units(lists) <= cfg.table_max_units
+    return _table_units(lists, cfg) <= cfg.table_max_units
 
 
 def _default_device(device):
@@ -847,7 +878,8 @@ def _default_device(device):
 # ---------------------------------------------------------------------------
 # public API (reference signatures)
 # ---------------------------------------------------------------------------
-def _run_lists(session: _Session, video_lists, cfg: OptConfig, stats: Stats, legacy: bool = False):
+def _run_lists(session: _Session, video_lists, cfg: OptConfig, stats: Stats, legacy: bool = False,
+               use_tables: bool | None = None):
     """Drive track lists to completion.  ``video_lists``: per video a list of stages
     ``(preds_fn, planes, translation, rng, after)``; the stages of a video run in order (their RNG
     consumption is sequential), videos advance in lock-step.  ``preds_fn()`` gives the stage's input
@@ -855,7 +887,7 @@ def _run_lists(session: _Session, video_lists, cfg: OptConfig, stats: Stats, leg
     lists = [(v, planes, translation) for v, stages in enumerate(video_lists)
              for (_, planes, translation, _, _) in stages if planes]
     tables = {}
-    if lists and session.pool is not None and _use_tables(session, lists, cfg):
+    if lists and session.n_masks and (use_tables if use_tables is not None else _use_tables(lists, cfg)):
         stats.schedule = "table"
         for (v, planes, translation), tabs in zip(lists, session.cluster_tables(lists, stats, legacy=legacy)):
             tables[(v, translation)] = tabs
@@ -962,9 +994,26 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
     advance in lock-step, one job per video per device pass (many videos)."""
     cfg = cfg or OptConfig()
     stats = stats if stats is not None else Stats()
-    session = _Session([(p, [pl['trans'], pl['rot']]) for p, pl in videos], cfg, _default_device(device))
-    stats.h2d_bytes += session.h2d_bytes
+    device = _default_device(device)
     outs = [[None] for _ in videos]
+    per_video = [[(v, pl['trans'], True), (v, pl['rot'], False)] for v, (p, pl) in enumerate(videos)]
+    dense = all(_has(f, 'pred_masks') for p, _ in videos for f in p[:1])
+    if videos and dense and all(_use_tables(l, cfg) for l in per_video):
+        # all-sources schedule, one session per video, software-pipelined: while video v is optimised
+        # (table pass, host replay, final pass, write-back), the helper thread of session v+1 uploads and
+        # packs the next video's masks on its own stream
+        def open_session(v):
+            p, pl = videos[v]
+            return _Session([(p, [pl['trans'], pl['rot']])], cfg, device)
+        nxt = open_session(0)
+        for v, ((p, pl), seed) in enumerate(zip(videos, seeds)):
+            session, nxt = nxt, (open_session(v + 1) if v + 1 < len(videos) else None)
+            stats.h2d_bytes += session.h2d_bytes
+            _run_lists(session, [_video_stages(p, pl, cfg, _global_random.Random(seed), outs[v])], cfg, stats,
+                       use_tables=True)
+        return [o[0] for o in outs]
+    session = _Session([(p, [pl['trans'], pl['rot']]) for p, pl in videos], cfg, device)
+    stats.h2d_bytes += session.h2d_bytes
     _run_lists(session, [_video_stages(p, pl, cfg, _global_random.Random(s), o)
                          for (p, pl), s, o in zip(videos, seeds, outs)], cfg, stats)
     return [o[0] for o in outs]

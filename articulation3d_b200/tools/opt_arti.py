@@ -52,7 +52,6 @@ def main(argv=None):
     groups = adapter.group_by_video(adapter.load_predictions(args.input))
     videos, order = [], []
     for vid, recs in groups.items():
-        recs = sorted(recs, key=frame_index)
         preds = io.records_to_preds(recs, conf_threshold=args.conf_threshold, masks="rle")
         videos.append((preds, opt_utils.track_planes(preds, cfg)))
         order.append((vid, recs))

@@ -74,16 +74,18 @@ class PassInputs:
 
 
 def build_pass(wl: Workload, seed0: int, device, source_frame: int | None = None,
-               progress=None, mode: int = _lib.MODE_SEQ) -> PassInputs:
+               progress=None, mode: int = _lib.MODE_SEQ, video_ids=None) -> PassInputs:
     """Render every track of ``wl`` on the device, pack the masks, and describe one pass with the
     middle frame of each track as source: cluster-phase three-step rotations (``MODE_SEQ``, the
-    default), final-phase composed rotations or translations along the axis direction."""
+    default), final-phase composed rotations or translations along the axis direction.
+    ``video_ids``: the videos of the workload this device holds (default all); video v is always the
+    scene of seed ``seed0 + v``, so shards of any world size add up to the same workload."""
     cfg = wl.cfg()
     T = wl.frames
     s = T // 2 if source_frame is None else source_frame
     bits, srcs, normals, offsets, pivots, dirs = [], [], [], [], [], []
     n = 0
-    for v in range(wl.videos):
+    for v in (range(wl.videos) if video_ids is None else video_ids):
         scene = synth.make_scene(seed0 + v, wl.tracks, T, cfg, kinds=[synth.KIND_ROT] * wl.tracks)
         for k in range(wl.tracks):
             masks = synth.render_track_masks(scene, k, cfg, device=device)            # (T,H,W) bool
@@ -104,8 +106,14 @@ def build_pass(wl: Workload, seed0: int, device, source_frame: int | None = None
             n += T
         if progress:
             progress(v)
-    pool = engine.pool_from_bits(torch.cat(bits), cfg.height, cfg.width)
-    del bits
+    H, pitch = cfg.height, _lib.pitch_words(cfg.width)
+    all_bits = torch.empty(n, H, pitch, dtype=torch.int32, device=device)      # no second copy of the pool
+    o = 0
+    while bits:
+        b = bits.pop(0)
+        all_bits[o:o + b.shape[0]] = b
+        o += b.shape[0]
+    pool = engine.pool_from_bits(all_bits, cfg.height, cfg.width)
     if mode == _lib.MODE_TRANSLATE:
         xf = geometry.xforms_translate(np.linspace(-1.0, 1.0, wl.cand, endpoint=False), np.stack(dirs))
     else:

@@ -102,7 +102,7 @@ def test_opt_arti_tool_end_to_end(tmp_path):
     opt_arti.main(["--input", inp, "--output", out, "--synthetic", "2", "--tracks", "3", "--frames", "14",
                    "--seed", "2020", "--save-obj", "--device", DEV])
     for v in range(2):
-        vid = f"synthetic{v:02d}"
+        vid = f"synthetic{v:02d}_0_0"
         tracks = json.load(open(f"{out}/{vid}_tracks.json"))
         recs = torch.load(f"{out}/{vid}_predictions_opt.pth", weights_only=False)
         assert len(recs) == 14 and any(f.endswith(".obj") for f in __import__("os").listdir(out))

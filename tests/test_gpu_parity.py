@@ -486,7 +486,7 @@ def test_randomised_shapes_against_c_oracle(seed, kernel, monkeypatch):
         ax = rng.randn(k, 3)
         ax /= np.linalg.norm(ax, axis=1, keepdims=True)
         ang = rng.uniform(-np.pi, np.pi, k)
-        return geometry._axis_angle_to_matrix(torch.from_numpy(ax * ang[:, None])).to(torch.float32).numpy()
+        return geometry._axis_angle_to_matrix(torch.from_numpy(ax * ang[:, None])).to(torch.float32).numpy().reshape(-1, 3, 3)
 
     specs = []
     for j in range(5):

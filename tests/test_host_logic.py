@@ -341,6 +341,7 @@ def test_batched_candidate_transforms_equal_per_source():
     Tr = geometry.xforms_translate(cfg.trans_grid, d)
     for i in range(9):
         assert np.array_equal(R[i], geometry.rotation_matrices(cfg.rot_cluster_grid, d[i]))
+        assert np.array_equal(geometry.xforms_seq_from_dirs(cfg.rot_cluster_grid, d)[i], geometry.xforms_seq(R[i]))
         assert np.array_equal(C[i], geometry.xforms_composed(geometry.rotation_matrices(cfg.rot_final_grid, d[i]), piv[i]))
         assert np.array_equal(Tr[i], geometry.xforms_translate(cfg.trans_grid, d[i]))
 
@@ -450,11 +451,11 @@ def test_write_back_matches_oracle(monkeypatch):
 
 
 def test_axis_angle_matrices_equal_oracle_form():
-    """geometry._axis_angle_to_matrix (column-wise numpy form) against the oracle's statement of
+    """geometry._axis_angle_to_matrix (component-plane form) against the oracle's statement of
     pytorch3d's construction, incl. the small-angle branch and a zero vector: same float64 bits."""
     rng = np.random.default_rng(0)
     aa = torch.from_numpy(rng.standard_normal((300, 45, 3)) * np.exp(rng.standard_normal((300, 45, 1)) * 3))
     aa[::9] *= 1e-8
     aa[5, 3] = 0
-    a, b = geometry._axis_angle_to_matrix(aa), restated.axis_angle_to_matrix64(aa)
+    a, b = geometry._axis_angle_to_matrix(aa).reshape(300, 45, 3, 3), restated.axis_angle_to_matrix64(aa)
     assert torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))

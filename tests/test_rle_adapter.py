@@ -59,9 +59,14 @@ def test_create_instances_contract():
     assert np.array_equal(inst.pred_masks[0].numpy() > 0.5, m)
     lazy = adapter.create_instances(dets, (h, w), planes, rot, tran, masks="rle")
     assert not lazy.has("pred_masks") and len(lazy.pred_rle) == 2
-    groups = adapter.group_by_video([{"file_name": "a/abcdefghijk_1_20_5.png"}, {"file_name": "abcdefghijk_1_20_15.png"},
-                                     {"file_name": "zzzzzzzzzzz_0_0_5.png"}])
-    assert sorted(groups) == ["abcdefghijk", "zzzzzzzzzzz"] and len(groups["abcdefghijk"]) == 2
+    # two shots of the same YouTube id are two videos; frames are ordered by their offset
+    recs = [{"file_name": "a/abcdefghijk_1_20_15.png"}, {"file_name": "abcdefghijk_1_20_5.png"},
+            {"file_name": "zzzzzzzzzzz_0_0_5.png"}, {"file_name": "x/abcdefghijk_2_300_7.png"},
+            {"file_name": "x/abcdefghijk_2_300_6.png"}, {"file_name": "abc_def_hij_3_4_0.png"}]
+    groups = adapter.group_by_video(recs)
+    assert list(groups) == ["abcdefghijk_1_20", "zzzzzzzzzzz_0_0", "abcdefghijk_2_300", "abc_def_hij_3_4"]
+    assert [r["file_name"] for r in groups["abcdefghijk_1_20"]] == ["abcdefghijk_1_20_5.png", "a/abcdefghijk_1_20_15.png"]
+    assert [r["file_name"][-5:] for r in groups["abcdefghijk_2_300"]] == ["6.png", "7.png"]
 
 
 def test_ray_table_matches_reference_loop_on_a_subgrid():
