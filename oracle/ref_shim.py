@@ -35,6 +35,15 @@ import sys
 import types
 import warnings
 
+# The reference's CPU execution goes through BLAS (``K @ pcd.T``, the batched
+# 4x4 products of Transform3d).  MKL picks a kernel per CPU model: on AVX-512
+# parts its sgemm contracts ``f*X + cx*Z`` into an FMA, which moves ~30 % of the
+# fp32 values by one ulp and ~1e-3 of the truncated pixels.  MKL's documented
+# cross-CPU reproducible mode removes the machine dependence (separately
+# rounded products, summed left to right -- the order oracle/restated.py and the
+# CUDA kernels state explicitly).  It must be set before the first MKL call.
+os.environ.setdefault("MKL_CBWR", "COMPATIBLE")
+
 import numpy as np
 import torch
 

@@ -1,6 +1,10 @@
 import os
 import sys
 
+# before torch/MKL run anything: the live-reference tests execute the reference's
+# BLAS calls, and MKL's per-CPU kernels differ in FMA use (see oracle/ref_shim.py)
+os.environ.setdefault("MKL_CBWR", "COMPATIBLE")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
