@@ -2178,7 +2178,8 @@ int a3d_pack_masks(const void* src, int dtype, int64_t n, int H, int W, float th
     const int pitch = pitch_words(W);
     const int64_t rows = n * H;
     const int64_t want = (rows + 7) / 8;
-    const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+    const int cap_ctas = device_sm_count() * 16;
+    const int grid = (int)(want < cap_ctas ? want : cap_ctas);
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype != A3D_F32 && dtype != A3D_U8) return fail(A3D_EINVAL, "a3d_pack_masks: unknown dtype %d", dtype);
     const size_t esz = dtype == A3D_F32 ? 4 : 1;
@@ -2192,7 +2193,7 @@ int a3d_pack_masks(const void* src, int dtype, int64_t n, int H, int W, float th
             if (bits_nz) A3D_CUDA_TRY(cudaMemsetAsync(bits_nz, 0, (size_t)rows * pitch * 4, s));
         }
         const int64_t wantv = (rows * segs + 31) / 32;
-        const int gridv = (int)(wantv < 148 * 16 ? (wantv > 0 ? wantv : 1) : 148 * 16);
+        const int gridv = (int)(wantv < cap_ctas ? (wantv > 0 ? wantv : 1) : cap_ctas);
         if (dtype == A3D_F32)
             k_pack_vec<float><<<gridv, 256, 0, s>>>((const float*)src, rows, W, pitch, thresh, bits_gt, bits_nz);
         else
@@ -2247,7 +2248,7 @@ int a3d_pass(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max
     // 256-job shard they measured 7 % slower than plain stream order (2.82 vs 2.63 ms), so only passes whose
     // projection grid fits about two waves use them (A3D_PDL=0 | 1 forces).
     const char* env_pdl = getenv("A3D_PDL");
-    const bool pdl = env_pdl ? env_pdl[0] == '1' : (long long)n_jobs * (max_cand > 0 ? max_cand : 1) <= 6 * 296;
+    const bool pdl = env_pdl ? env_pdl[0] == '1' : (long long)n_jobs * (max_cand > 0 ? max_cand : 1) <= 12LL * device_sm_count();
     int rc = project_impl(cam, jobs, n_jobs, max_cand, tile_cand, src_bits ? src_bits : pool_bits,
                           src_bits ? src_bbox : pool_bbox, xform, pcd_ws, pcd_count, hom_ws, tile_map, n_tiles,
                           proj_bits, proj_popc, proj_bbox, stream, pdl);
@@ -2302,7 +2303,7 @@ static int project_impl(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jo
     if (usmem > (size_t)device_smem_optin())
         return fail(A3D_ELIMIT, "a3d_project: %dx%d mask does not fit shared memory", c.H, c.W);
     // few jobs: spread each job's phase 2 over several CTAs so all SMs have work
-    int usplit = (2 * 148 + n_jobs - 1) / n_jobs;
+    int usplit = (2 * device_sm_count() + n_jobs - 1) / n_jobs;
     usplit = usplit < 1 ? 1 : (usplit > 32 ? 32 : usplit);
     const dim3 ugrid((unsigned)n_jobs, (unsigned)usplit);
     if (c.sparse) {
@@ -2459,7 +2460,7 @@ static int score_impl(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_t
         // (26.9 vs 30.7 us on C2).  A3D_SCORE_WC overrides for A/B runs.
         const char* env_wc = getenv("A3D_SCORE_WC");
         const long long blocks44 = (long long)n_jobs * ((max_tgt + kScoreTT - 1) / kScoreTT) * ((max_cand + 15) / 16);
-        int wc = blocks44 < 6 * 148 ? 2 : 4;
+        int wc = blocks44 < 6LL * device_sm_count() ? 2 : 4;
         if (env_wc && (env_wc[0] == '2' || env_wc[0] == '4')) wc = env_wc[0] - '0';
         const int tt_tiles = (max_tgt + kScoreTT - 1) / kScoreTT, ct_tiles = (max_cand + 4 * wc - 1) / (4 * wc);
         const long long nblocks = (long long)n_jobs * tt_tiles * ct_tiles;

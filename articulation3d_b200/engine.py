@@ -192,7 +192,7 @@ def pool_from_bits(bits: torch.Tensor, H: int, W: int) -> MaskPool:
     return MaskPool(bits.contiguous(), popc, bbox, H, W)
 
 
-def plan_tiles(jobs: np.ndarray, max_tile: int, sm_count: int = 148, fixed: float = 21500.0, per_cand: float = 3000.0):
+def plan_tiles(jobs: np.ndarray, max_tile: int, sm_count: int | None = None, fixed: float = 21500.0, per_cand: float = 3000.0):
     """Split of a pass into projection CTAs when the grid is about one wave: jobs whose source masks
     differ in size get tiles of different size, so that every CTA carries about the same number of
     (point, candidate) pairs and the SMs finish together (uniform tiles leave the kernel waiting for the
@@ -206,6 +206,8 @@ def plan_tiles(jobs: np.ndarray, max_tile: int, sm_count: int = 148, fixed: floa
     n = len(jobs)
     if n == 0:
         return max_tile, None
+    if sm_count is None:
+        sm_count = plan_sm_count()
     ncand = jobs["n_cand"].astype(np.int64)
     cost = jobs["pcd_cap"].astype(np.float64) + per_cand
     min_ctas = int((-(-ncand // max_tile)).sum())
@@ -264,9 +266,11 @@ def plan_sm_count(device=None) -> int:
     return max(1, sms)
 
 
-def plan_tiles_native(jobs: np.ndarray, max_tile: int, sm_count: int = 148):
+def plan_tiles_native(jobs: np.ndarray, max_tile: int, sm_count: int | None = None):
     """``plan_tiles`` through the library's host planner (a3d_plan_tiles): same result, microseconds."""
     lib = _lib.load()
+    if sm_count is None:
+        sm_count = plan_sm_count()
     buf = _plan_buf.get(sm_count)
     if buf is None:
         buf = _plan_buf[sm_count] = np.empty((2 * sm_count, 4), dtype=np.int32)
@@ -380,7 +384,7 @@ class DeviceBatch:
         if cfg is not None and os.environ.get("A3D_TILE_PLAN") != "uniform":
             plan = plan_tiles_native(batch.jobs, max_tile(cfg), plan_sm_count(device))
             if plan[1] is None:
-                plan = (choose_tile(cfg, int(batch.xform.shape[0]), batch.n_jobs), None)
+                plan = (choose_tile(cfg, int(batch.xform.shape[0]), batch.n_jobs, plan_sm_count(device)), None)
             self._plans[(cfg.height, cfg.width)] = plan
         tmap = plan[1] if plan is not None and plan[1] is not None else np.zeros((0, 4), np.int32)
         self.n_jobs = batch.n_jobs
@@ -414,11 +418,11 @@ class DeviceBatch:
         key = (cfg.height, cfg.width)
         if key not in self._plans:
             if os.environ.get("A3D_TILE_PLAN") == "uniform":
-                self._plans[key] = (choose_tile(cfg, self.n_cand_total, self.n_jobs), None)
+                self._plans[key] = (choose_tile(cfg, self.n_cand_total, self.n_jobs, plan_sm_count(self.device)), None)
             else:
                 tile, tmap = plan_tiles_native(self.host.jobs, max_tile(cfg), plan_sm_count(self.device))
                 if tmap is None:
-                    tile = choose_tile(cfg, self.n_cand_total, self.n_jobs)
+                    tile = choose_tile(cfg, self.n_cand_total, self.n_jobs, plan_sm_count(self.device))
                 else:
                     self._tmap_dev[key] = torch.from_numpy(tmap).to(self.device)
                 self._plans[key] = (tile, tmap)
@@ -486,11 +490,13 @@ def max_tile(cfg: OptConfig) -> int:
     return t
 
 
-def choose_tile(cfg: OptConfig, n_cand_total: int, n_jobs: int = 1, sm_count: int = 148) -> int:
+def choose_tile(cfg: OptConfig, n_cand_total: int, n_jobs: int = 1, sm_count: int | None = None) -> int:
     """Candidates per projection CTA for uniform tiles.  Large batches take as many as shared memory
     holds (the point cloud is read once per CTA); small batches pick the tile that minimises
     waves x (per-CTA overhead + tile) so no SM runs two CTAs while others idle."""
     mt = max_tile(cfg)
+    if sm_count is None:
+        sm_count = plan_sm_count()
     per_job = -(-n_cand_total // max(n_jobs, 1))
     best, best_cost = mt, None
     for tile in range(mt, 0, -1):

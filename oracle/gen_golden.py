@@ -267,6 +267,65 @@ def main_eval():
         print(f"wrote {path} ({os.path.getsize(path) // 1024} KB):", out["arti_axis"], out["recognition"])
 
 
+# --------------------------------------------------------------------------
+# row f1: the reference's own override_depth / get_K_inv_dot_xy_1  (utils/arti_vis.py:101-149)
+# --------------------------------------------------------------------------
+DEPTH_CASES = {"depth_a": (41, 3, 12, [0, 1, 0], (0, 5, 11)), "depth_b": (42, 2, 10, [1, 0], (3, 9))}
+
+
+def depth_case_inputs(name: str):
+    """Seeded inputs of a depth fixture, regenerated identically wherever the fixture is read: per frame
+    the detections' RLE masks (+ one empty mask) with their plane rows, and a depth map of integer
+    millimetres (``RandomState.randint`` is platform independent; the fixture stores a checksum)."""
+    from articulation3d_b200 import rle, synth
+    seed, n_tracks, n_frames, kinds, frames = DEPTH_CASES[name]
+    preds, _ = synth.make_video(seed, n_tracks, n_frames, kinds=kinds)
+    rng = np.random.RandomState(seed)
+    H, W = preds[0].image_size
+    records, depths = [], []
+    for f in frames:
+        p = preds[f]
+        n = int(p.pred_masks.shape[0])
+        dets = [{"segmentation": rle.encode(p.pred_masks[k].numpy() > 0.5)} for k in range(n)]
+        dets.append({"segmentation": rle.encode(np.zeros((H, W), bool))})            # empty mask keeps its plane
+        planes = torch.cat([p.pred_planes, torch.tensor([[0.3, 1.0, -0.2]])])
+        records.append({"instances": dets, "pred_plane": planes})
+        # a tilted surface with millimetre noise, 1.5 .. 4.5 m
+        yy, xx = np.mgrid[0:H, 0:W]
+        mm = 1500 + (2 * xx + 3 * yy) % 2000 + rng.randint(0, 1000, size=(H, W))
+        depths.append((mm.astype(np.float64) / 1000.0).astype(np.float32))
+    return records, np.stack(depths)
+
+
+def main_depth():
+    """tests/golden/depth/*.npz: outputs of the reference's static ``PlaneRCNN_Branch.override_depth`` and of
+    its ``get_K_inv_dot_xy_1`` run under the shim; ``mask_util.decode`` (pycocotools, absent) is rebound to
+    the oracle's RLE decoder [3P-unverified]."""
+    import importlib
+    from oracle import restated
+    if not ref_shim.available():
+        raise SystemExit("reference not present; fixtures can only be generated in the build container")
+    ref_shim.load_reference()
+    av = importlib.import_module("articulation3d.utils.arti_vis")
+    av.mask_util.decode = restated.rle_decode
+    os.makedirs(os.path.join(GOLDEN_DIR, "depth"), exist_ok=True)
+    rays64 = av.PlaneRCNN_Branch.get_K_inv_dot_xy_1(None)                      # (3, 480, 640) float64
+    rays = torch.FloatTensor(rays64)                                           # arti_vis.py:52
+    for name in DEPTH_CASES:
+        records, depths = depth_case_inputs(name)
+        res = {"depth_checksum": np.float64(depths.astype(np.float64).sum()),
+               "rays_probe": rays64[:, ::37, ::41].copy(), "n_frames": np.int64(len(records))}
+        for i, rec in enumerate(records):
+            xyz = rays * torch.from_numpy(depths[i])                           # depth2XYZ, arti_vis.py:90-99
+            inst = {"instances": rec["instances"], "pred_plane": rec["pred_plane"].clone()}
+            out = av.PlaneRCNN_Branch.override_depth(xyz, inst)
+            res[f"f{i}_pred_plane_in"] = rec["pred_plane"].numpy()
+            res[f"f{i}_pred_plane_out"] = out["pred_plane"].numpy()
+        path = os.path.join(GOLDEN_DIR, "depth", f"{name}.npz")
+        np.savez_compressed(path, **res)
+        print(f"wrote {path}:", res["f0_pred_plane_out"].tolist())
+
+
 def main():
     from articulation3d_b200 import synth
     if not ref_shim.available():
@@ -285,4 +344,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main_diag() if "--diag" in sys.argv else (main_eval() if "--eval" in sys.argv else main())
+    if "--diag" in sys.argv:
+        main_diag()
+    elif "--eval" in sys.argv:
+        main_eval()
+    elif "--depth" in sys.argv:
+        main_depth()
+    else:
+        main()

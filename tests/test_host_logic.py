@@ -231,9 +231,9 @@ def test_plan_tiles_covers_every_candidate_once(seed):
     jobs["pcd_cap"] = (rng.randint(0, 60000, size=n) + 31) & ~31
     jobs["cand_begin"] = np.cumsum(np.r_[0, jobs["n_cand"][:-1]])
     max_tile = int(rng.randint(1, 7))
-    tile, tmap = engine.plan_tiles(jobs, max_tile)
+    tile, tmap = engine.plan_tiles(jobs, max_tile, sm_count=148)
     # the library's host planner (a3d_plan_tiles) is the same statement in C
-    tile_c, tmap_c = engine.plan_tiles_native(jobs, max_tile)
+    tile_c, tmap_c = engine.plan_tiles_native(jobs, max_tile, sm_count=148)
     assert tile_c == tile and (tmap is None) == (tmap_c is None)
     if tmap is not None:
         assert np.array_equal(tmap, tmap_c)

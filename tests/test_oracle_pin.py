@@ -80,3 +80,25 @@ def test_restated_oracle_matches_live_reference(seed, n_tracks, n_frames, drop, 
 
     planes, out, choices, lin, _ = run_restated(synth.clone_preds(preds), seed, monkeypatch)
     gu.check_against_golden(Z(ref), planes, out, choices, lin)
+
+
+@pytest.mark.parametrize("name", ["depth_a", "depth_b"])
+def test_override_depth_oracle_matches_reference_fixture(name, golden_dir):
+    """Row f1: oracle/restated.override_depth / get_K_inv_dot_xy_1 against the outputs of the reference's own
+    static ``PlaneRCNN_Branch.override_depth`` (utils/arti_vis.py:101-149), tests/golden/depth/*.npz."""
+    import os
+    import torch
+    from oracle import restated
+    from oracle.gen_golden import depth_case_inputs
+    z = np.load(os.path.join(golden_dir, "depth", f"{name}.npz"))
+    records, depths = depth_case_inputs(name)
+    assert float(depths.astype(np.float64).sum()) == float(z["depth_checksum"])      # same inputs as the generator's
+    rays64 = restated.get_K_inv_dot_xy_1()
+    assert np.array_equal(rays64[:, ::37, ::41], z["rays_probe"])
+    rays = torch.FloatTensor(rays64)
+    assert len(records) == int(z["n_frames"])
+    for i, rec in enumerate(records):
+        assert np.array_equal(rec["pred_plane"].numpy(), z[f"f{i}_pred_plane_in"])
+        out = restated.override_depth(rays * torch.from_numpy(depths[i]),
+                                      {"instances": rec["instances"], "pred_plane": rec["pred_plane"].clone()})
+        np.testing.assert_allclose(out["pred_plane"].numpy(), z[f"f{i}_pred_plane_out"], rtol=1e-6, atol=1e-7)
