@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("A3D_LIB") or os.path.join(_HERE, "csrc", "liba3d.so")
 
 A3D_F32, A3D_U8 = 0, 1
+OUT_FULL, OUT_BBOX_ROWS = 0, 1      # A3D_OUT_*: what a3d_project / a3d_pass write of every projected mask
 MODE_SEQ, MODE_COMPOSED, MODE_TRANSLATE = 0, 1, 2
 PCD_PLANES = 5          # A3D_PCD_PLANES: floats of point-cloud workspace per point
 HOM_FLOATS = 12         # A3D_HOM_FLOATS: floats of homography workspace per candidate
@@ -41,7 +42,7 @@ assert JOB_DTYPE.itemsize == 72, JOB_DTYPE.itemsize
 EXPORTS = (
     "a3d_version", "a3d_last_error_string", "a3d_pitch_words", "a3d_project_max_tile",
     "a3d_pack_masks", "a3d_mask_meta", "a3d_project", "a3d_score", "a3d_pass", "a3d_emit_masks",
-    "a3d_rle_to_bits", "a3d_plane_offsets", "a3d_plan_tiles",
+    "a3d_rle_to_bits", "a3d_plane_offsets", "a3d_plan_tiles", "a3d_gather_masks",
 )
 
 _lib = None
@@ -75,17 +76,19 @@ def load():
     lib.a3d_mask_meta.restype = C.c_int
     lib.a3d_mask_meta.argtypes = [vp, i64, i32, i32, vp, vp, vp]
     lib.a3d_project.restype = C.c_int
-    lib.a3d_project.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]
+    lib.a3d_project.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp]
     lib.a3d_score.restype = C.c_int
     lib.a3d_score.argtypes = [i32, i32, vp, i32, i32, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                               vp, vp, vp, vp, vp]
     lib.a3d_pass.restype = C.c_int
     lib.a3d_pass.argtypes = [C.POINTER(Camera), vp, i32, i32, i32, i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp,
-                             vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+                             vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     lib.a3d_plan_tiles.restype = C.c_int
     lib.a3d_plan_tiles.argtypes = [vp, i32, i32, i32, vp, i32, C.POINTER(C.c_int)]
     lib.a3d_emit_masks.restype = C.c_int
     lib.a3d_emit_masks.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp]
+    lib.a3d_gather_masks.restype = C.c_int
+    lib.a3d_gather_masks.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
     lib.a3d_rle_to_bits.restype = C.c_int
     lib.a3d_rle_to_bits.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     lib.a3d_plane_offsets.restype = C.c_int

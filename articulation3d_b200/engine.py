@@ -41,6 +41,32 @@ def camera_struct(cfg: OptConfig) -> _lib.Camera:
     return cam
 
 
+POINTS_PER_ITEM = 8          # k_project item size: k_unproject pads every source row to a multiple of it
+
+
+class SourcePoints(np.ndarray):
+    """Per-mask source pixel counts (what ``MaskPool.source_points`` returns) with the capacities of the
+    row-padded point clouds riding along: ``caps[i]`` = points + 7 per row of the source box, rounded up to
+    32 (``a3d_job_t.pcd_cap``)."""
+    caps = None
+
+    @classmethod
+    def make(cls, points, rows=None):
+        pts = np.asarray(points, dtype=np.int64)
+        # without the box heights: every row holds at least one point
+        rows = pts if rows is None else np.minimum(np.asarray(rows, dtype=np.int64), pts)
+        out = pts.view(cls)
+        out.caps = (pts + (POINTS_PER_ITEM - 1) * rows + 31) & ~31
+        return out
+
+
+def point_caps(src_points) -> np.ndarray:
+    """Point-cloud capacities for ``a3d_job_t.pcd_cap`` from a ``MaskPool.source_points`` array (or, for a
+    plain array of pixel counts, the worst case of one point per row)."""
+    caps = getattr(src_points, "caps", None)
+    return caps if caps is not None else SourcePoints.make(src_points).caps
+
+
 @dataclass
 class MaskPool:
     """Bit-packed masks resident in HBM plus their popcounts / bounding boxes."""
@@ -60,19 +86,26 @@ class MaskPool:
 
     def _resolve(self):
         """First host-side use of the pool: ONE D2H of the count vectors (the host needs the
-        source-pixel counts to size the point-cloud workspace).  Binary masks (the contract) give
-        identical ``> thresh`` and ``!= 0`` counts and the second bitmap is dropped.  Deferred to here
-        so that the upload and packing stay asynchronous behind the host's geometry work."""
+        source-pixel counts and the rows of the source boxes to size the point-cloud workspace).  Binary
+        masks (the contract) give identical ``> thresh`` and ``!= 0`` counts and the second bitmap is
+        dropped.  Deferred to here so that the upload and packing stay asynchronous behind the host's
+        geometry work."""
+        def rows_of(bbox):
+            return (bbox[:, 1] - bbox[:, 0] + 1).clamp_(min=0)
         if self._nz_pending is not None:
             nz, bbox_nz, popc_nz = self._nz_pending
             self._nz_pending = None
-            both = torch.stack((self.popc, popc_nz)).cpu().numpy()
+            both = torch.stack((self.popc, popc_nz, rows_of(self.bbox), rows_of(bbox_nz))).cpu().numpy()
             if not np.array_equal(both[0], both[1]):
                 self.bits_nz, self.bbox_nz, self.popc_nz = nz, bbox_nz, popc_nz
-            self._src_points = both[1].astype(np.int64)
+            pts, rows = both[1].astype(np.int64), both[3].astype(np.int64)
         elif self._src_points is None:
-            t = self.popc if self.popc_nz is None else self.popc_nz
-            self._src_points = t.cpu().numpy().astype(np.int64)
+            t, bb = (self.popc, self.bbox) if self.popc_nz is None else (self.popc_nz, self.bbox_nz)
+            both = torch.stack((t, rows_of(bb))).cpu().numpy()
+            pts, rows = both[0].astype(np.int64), both[1].astype(np.int64)
+        else:
+            return
+        self._src_points = SourcePoints.make(pts, rows)
 
     @property
     def source_points(self) -> np.ndarray:
@@ -306,6 +339,7 @@ def build_batch(sources, modes, normals, offsets, pivots, xforms, targets, src_p
     source pixel counts of the pool (``MaskPool.source_points``)."""
     n = len(sources)
     jobs = np.zeros(n, dtype=_lib.JOB_DTYPE)
+    caps = point_caps(src_points)
     cand = tgt = tab = pcd = 0
     for i in range(n):
         a, t = len(xforms[i]), len(targets[i])
@@ -317,7 +351,7 @@ def build_batch(sources, modes, normals, offsets, pivots, xforms, targets, src_p
         jobs[i]["offset"] = np.float32(offsets[i])
         jobs[i]["pivot"] = np.asarray(pivots[i], dtype=np.float32)
         jobs[i]["tab_begin"] = tab
-        cap = (int(src_points[sources[i]]) + 31) & ~31
+        cap = int(caps[sources[i]])
         jobs[i]["pcd_begin"], jobs[i]["pcd_cap"] = pcd, cap
         pcd += cap
         cand += a
@@ -351,7 +385,7 @@ def build_batch_rows(sources, modes, normals, offsets, pivots, xform, n_cand, tg
         jobs["pivot"] = np.asarray(pivots, dtype=np.float32).reshape(S, 3)
         tab = n_cand * n_tgt
         jobs["tab_begin"] = np.cumsum(tab) - tab
-        cap = (np.asarray(src_points, dtype=np.int64)[sources] + 31) & ~31
+        cap = point_caps(src_points)[sources]
         jobs["pcd_cap"] = cap
         jobs["pcd_begin"] = np.cumsum(cap) - cap
     xform = np.ascontiguousarray(np.asarray(xform, dtype=np.float32).reshape(-1, 12))
@@ -371,6 +405,12 @@ class PassResult:
     proj_bbox: torch.Tensor       # (n_cand_total, 4) int32
     inter_tab: torch.Tensor | None
     block: torch.Tensor | None = None     # (4, n_tgt_total) int32: the four best_* rows, contiguous
+    rows_only: bool = False               # proj_bits holds only the rows of each mask's proj_bbox (A3D_OUT_BBOX_ROWS)
+
+    def masks(self, index: torch.Tensor | None = None) -> torch.Tensor:
+        """Projected masks ``index`` (global candidate slots; None = all) as fully defined packed images,
+        copied out of the pass workspace."""
+        return gather_masks(self.proj_bits, self.proj_bbox if self.rows_only else None, index)
 
 
 class DeviceBatch:
@@ -464,6 +504,8 @@ class Workspace:
         buf = self._bufs.get(name)
         if buf is None or buf.numel() < n or buf.dtype != dtype:
             buf = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            if os.environ.get("A3D_WS_POISON"):          # tests: nothing may depend on what a fresh buffer holds
+                buf.view(torch.uint8).fill_(0xAB)
             self._bufs[name] = buf
         return buf[:n].view(*shape)
 
@@ -507,10 +549,34 @@ def choose_tile(cfg: OptConfig, n_cand_total: int, n_jobs: int = 1, sm_count: in
     return int(best)
 
 
+def default_out_mode() -> int:
+    """Projected masks are written as the rows of their bounding boxes only (everything the scoring reads);
+    ``A3D_PROJ_OUT=full`` writes every word, as ``a3d_project`` called directly with A3D_OUT_FULL does."""
+    return _lib.OUT_FULL if os.environ.get("A3D_PROJ_OUT") == "full" else _lib.OUT_BBOX_ROWS
+
+
+def gather_masks(bits: torch.Tensor, bbox: torch.Tensor | None, index: torch.Tensor | None) -> torch.Tensor:
+    """``bits[index]`` (n, H, pitch) with the rows outside each mask's ``bbox`` zeroed (a3d_gather_masks)."""
+    lib = _lib.load()
+    _require_cuda(bits, "bits")
+    H, pitch = int(bits.shape[1]), int(bits.shape[2])
+    n = int(index.numel()) if index is not None else int(bits.shape[0])
+    out = torch.empty(n, H, pitch, dtype=torch.int32, device=bits.device)
+    if index is not None:
+        index = index.to(torch.int32).contiguous()
+    with torch.cuda.device(bits.device):
+        _lib.check(lib.a3d_gather_masks(bits.data_ptr(), bbox.data_ptr() if bbox is not None else None,
+                                        index.data_ptr() if index is not None else None, n, H, pitch * 32,
+                                        out.data_ptr(), _stream_ptr()), "a3d_gather_masks")
+    return out
+
+
 def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace | None = None,
-             want_table: bool = False, tile_cand: int | None = None) -> PassResult:
+             want_table: bool = False, tile_cand: int | None = None, out_mode: int | None = None) -> PassResult:
     """project + score one batch, asynchronously on the current stream."""
     lib = _lib.load()
+    out_mode = default_out_mode() if out_mode is None else out_mode
+    rows_only = out_mode == _lib.OUT_BBOX_ROWS
     dev = pool.bits.device
     ws = ws or Workspace(dev)
     H, W = cfg.height, cfg.width
@@ -551,14 +617,14 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
                                     proj_bbox.data_ptr(), key_ws.data_ptr(),
                                     inter_tab.data_ptr() if inter_tab is not None else None,
                                     best_cand.data_ptr(), best_inter.data_ptr(), best_union.data_ptr(),
-                                    best_iou.data_ptr(), stream), "a3d_pass")
+                                    best_iou.data_ptr(), out_mode, stream), "a3d_pass")
             return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab,
-                              results)
+                              results, rows_only)
         _lib.check(lib.a3d_project(C.byref(cam), dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_cand, tile,
                                    pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(),
                                    dbatch.xform.data_ptr(), pcd_ws.data_ptr(), pcd_count.data_ptr(), hom_ws.data_ptr(),
                                    tmap_ptr, n_tiles,
-                                   proj_bits.data_ptr(), proj_popc.data_ptr(), proj_bbox.data_ptr(), stream),
+                                   proj_bits.data_ptr(), proj_popc.data_ptr(), proj_bbox.data_ptr(), out_mode, stream),
                    "a3d_project")
         _lib.check(lib.a3d_score(H, W, dbatch.jobs.data_ptr(), dbatch.n_jobs, dbatch.max_tgt, dbatch.max_cand, nt,
                                  len(pool), nc, pool.bits.data_ptr(), pool.popc.data_ptr(), pool.bbox.data_ptr(),
@@ -568,7 +634,7 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
                                  best_cand.data_ptr(), best_inter.data_ptr(), best_union.data_ptr(),
                                  best_iou.data_ptr(), stream), "a3d_score")
     return PassResult(best_cand, best_inter, best_union, best_iou, proj_bits, proj_popc, proj_bbox, inter_tab,
-                      results)
+                      results, rows_only)
 
 
 def emit_masks(bits: torch.Tensor, index: torch.Tensor | None, H: int, W: int,

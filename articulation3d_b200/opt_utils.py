@@ -673,8 +673,8 @@ class _Session:
         for j, s in enumerate(specs):           # enqueued before the sync: the gathers overlap the D2H
             if s.keep_masks:
                 a, n = int(batch.jobs[j]["tgt_begin"]), int(batch.jobs[j]["n_tgt"])
-                gidx = (res.best_cand[a:a + n].long() + int(batch.jobs[j]["cand_begin"]))
-                masks[j] = res.proj_bits.index_select(0, gidx)      # copy out of the workspace
+                gidx = res.best_cand[a:a + n] + int(batch.jobs[j]["cand_begin"])
+                masks[j] = res.masks(gidx)                          # copy out of the workspace
         torch.cuda.current_stream().synchronize()
         packed = host.numpy().reshape(4, -1)
         out = []

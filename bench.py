@@ -474,7 +474,8 @@ def _run_split(engine, inp, ws, evs):
     _lib.check(lib.a3d_project(C.byref(cam), db.jobs.data_ptr(), db.n_jobs, db.max_cand, tile,
                                pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(), db.xform.data_ptr(),
                                pcd_ws.data_ptr(), pcd_count.data_ptr(), hom_ws.data_ptr(), tmap_ptr, n_tiles,
-                               proj_bits.data_ptr(), proj_popc.data_ptr(), proj_bbox.data_ptr(), stream),
+                               proj_bits.data_ptr(), proj_popc.data_ptr(), proj_bbox.data_ptr(),
+                               engine.default_out_mode(), stream),
                "a3d_project")
     if evs:
         evs[1].record()
@@ -483,7 +484,8 @@ def _run_split(engine, inp, ws, evs):
                              db.tgt_index.data_ptr(), proj_bits.data_ptr(), proj_popc.data_ptr(),
                              proj_bbox.data_ptr(), key_ws.data_ptr(), None, outs[0].data_ptr(),
                              outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(), stream), "a3d_score")
-    return engine.PassResult(outs[0], outs[1], outs[2], outs[3], proj_bits, proj_popc, proj_bbox, None)
+    return engine.PassResult(outs[0], outs[1], outs[2], outs[3], proj_bits, proj_popc, proj_bbox, None,
+                             rows_only=engine.default_out_mode() == _lib.OUT_BBOX_ROWS)
 
 
 def _host_clip(wl, seed, dev, tracks=None, frames=None):

@@ -22,6 +22,9 @@ def projection_kernel(request, monkeypatch):
     """Every test of this module runs with both projection kernels (the library's default picks one from
     the grid size): the reference chain for every point, and the homography filter with proven truncation."""
     monkeypatch.setenv("A3D_PROJECT_KERNEL", request.param)
+    # fresh pass buffers hold 0xAB bytes: projected masks are written as the rows of their boxes only
+    # (A3D_OUT_BBOX_ROWS), and no kernel may read a word outside them
+    monkeypatch.setenv("A3D_WS_POISON", "1")
     return request.param
 
 
@@ -99,7 +102,7 @@ def _device_job(preds, frame, box, cfg, mode, grid, pool, src_idx, targets, tile
 def _check_pass(res, batch, proj_want, tgt_masks, W):
     """proj_want (A,H,W) bool, tgt_masks (T,H,W) bool."""
     A, T = proj_want.shape[0], tgt_masks.shape[0]
-    got = _unpack(res.proj_bits[:A], W)
+    got = _unpack(res.masks()[:A], W)
     assert got.shape == proj_want.shape
     diff = int((got != proj_want).sum())
     assert diff == 0, f"{diff} projected pixels differ"
@@ -411,7 +414,7 @@ def test_full_size_properties_and_kernel_agreement(wl_name, monkeypatch):
             proj = c_oracle.project(cfg.K_inv(), cfg.focal_length, cfg.cx, cfg.cy, cfg.height, cfg.width,
                                     bits[int(jb["src_mask"])], jb["normal"], float(jb["offset"]), jb["pivot"],
                                     int(jb["mode"]), xf)
-            got = res.proj_bits[int(jb["cand_begin"]): int(jb["cand_begin"]) + A].cpu().numpy().view(np.uint32)
+            got = res.masks(torch.arange(int(jb["cand_begin"]), int(jb["cand_begin"]) + A, device=DEV)).cpu().numpy().view(np.uint32)
             assert np.array_equal(got, proj)
             tg = inp.batch.tgt_index[int(jb["tgt_begin"]): int(jb["tgt_begin"]) + T]
             inter, uni, best, iou = c_oracle.score(cfg.height, cfg.width, bits[tg], proj)
@@ -506,7 +509,7 @@ def test_randomised_shapes_against_c_oracle(seed, kernel, monkeypatch):
     batch = engine.build_batch(*zip(*specs), pool.source_points)
     res = engine.run_pass(cfg, pool, engine.DeviceBatch(batch, DEV), want_table=True)
     torch.cuda.synchronize()
-    got_bits = res.proj_bits.cpu().numpy().view(np.uint32)
+    got_bits = res.masks().cpu().numpy().view(np.uint32)
     tab = res.inter_tab.cpu().numpy()
     for j, (src, mode, normal, offset, pivot, xf, tg) in enumerate(specs):
         jb = batch.jobs[j]
@@ -612,7 +615,7 @@ def test_filtered_projection_equals_exact_chain(mode, shape, monkeypatch):
         monkeypatch.setenv("A3D_PROJECT_SCHED", "persistent" if "/" in kernel else "cta")
         res = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, want_table=True, tile_cand=tile)
         torch.cuda.synchronize()
-        out[(kernel, tile)] = [t.cpu().numpy().copy() for t in (res.proj_bits, res.proj_popc, res.proj_bbox,
+        out[(kernel, tile)] = [t.cpu().numpy().copy() for t in (res.masks(), res.proj_popc, res.proj_bbox,
                                                                  res.inter_tab, res.best_cand)]
     ref = out[("exact", None)]
     assert ref[1].sum() > 0
@@ -667,7 +670,75 @@ def test_filter_kernel_adversarial_geometry(seed, monkeypatch):
         monkeypatch.setenv("A3D_PROJECT_KERNEL", kernel)
         res = engine.run_pass(cfg, pool, engine.DeviceBatch(batch, DEV))
         torch.cuda.synchronize()
-        out[kernel] = [t.cpu().numpy().copy() for t in (res.proj_bits, res.proj_popc, res.proj_bbox, res.best_inter)]
+        out[kernel] = [t.cpu().numpy().copy() for t in (res.masks(), res.proj_popc, res.proj_bbox, res.best_inter)]
     for a, b in zip(out["exact"], out["filter"]):
         assert np.array_equal(a, b)
     assert out["exact"][1].max() > 0
+
+
+def test_bbox_rows_output_equals_full_output(monkeypatch):
+    """A3D_OUT_BBOX_ROWS (the pass default: only the rows of each projected mask's box are written) against
+    A3D_OUT_FULL: identical statistics, scores, and — through a3d_gather_masks — identical masks; outside the
+    boxes the rows-only buffer still holds the poison bytes it was allocated with."""
+    from articulation3d_b200 import workloads
+    wl = workloads.Workload("probe", "3 videos x 3 tracks x 14 frames, 40 candidates", 3, 3, 14, 40)
+    inp = workloads.build_pass(wl, 77, DEV)
+    full = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, engine.Workspace(DEV), want_table=True, out_mode=_lib.OUT_FULL)
+    rows = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, engine.Workspace(DEV), want_table=True,
+                           out_mode=_lib.OUT_BBOX_ROWS)
+    torch.cuda.synchronize()
+    assert rows.rows_only and not full.rows_only
+    for name in ("proj_popc", "proj_bbox", "inter_tab", "best_cand", "best_inter", "best_union"):
+        assert torch.equal(getattr(full, name), getattr(rows, name)), name
+    assert torch.equal(full.best_iou.view(torch.int32), rows.best_iou.view(torch.int32))
+    assert torch.equal(full.proj_bits, rows.masks()) and torch.equal(full.proj_bits, full.masks())
+    idx = torch.tensor([5, 0, 17, 5], device=DEV)
+    assert torch.equal(rows.masks(idx), full.proj_bits[idx])
+    raw = rows.proj_bits.cpu().numpy().view(np.uint32)
+    bb = rows.proj_bbox.cpu().numpy()
+    k = int(np.argmax(bb[:, 1] - bb[:, 0]))                      # a non-empty mask
+    assert bb[k, 0] > 0 or bb[k, 1] < inp.cfg.height - 1
+    outside = np.ones(inp.cfg.height, bool)
+    outside[bb[k, 0]: bb[k, 1] + 1] = False
+    assert (raw[k][outside] == 0xABABABAB).all()
+
+
+@pytest.mark.parametrize("name,videos,tracks,frames,cand,W,H,mode", [
+    ("c3_slice", 4, 8, 120, 180, 640, 480, _lib.MODE_SEQ),              # 32 jobs of configs[2]'s shape
+    ("c4_slice", 2, 4, 24, 720, 1024, 768, _lib.MODE_SEQ),              # configs[3]: 720 rotations at 1024x768
+    ("c4_trans_slice", 2, 4, 24, 20, 1024, 768, _lib.MODE_TRANSLATE),   # ... and its 20 translation candidates
+])
+def test_c_oracle_on_every_job_of_baseline_shaped_slices(name, videos, tracks, frames, cand, W, H, mode):
+    """BASELINE-shaped passes against the C oracle on EVERY job (not a sample): projected masks, the full
+    intersection table, unions, arg-max and the IoU bits — exact.  The library picks the kernels it would
+    pick in production (filter / tensor-core scoring on the big grids) unless the module fixture forces one."""
+    from articulation3d_b200 import workloads
+    from oracle import c_oracle
+    wl = workloads.Workload(name, name, videos, tracks, frames, cand, W, H)
+    inp = workloads.build_pass(wl, 500 + cand, DEV, mode=mode)
+    res = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, want_table=True)
+    torch.cuda.synchronize()
+    cfg = inp.cfg
+    bits = inp.pool.bits.cpu().numpy().view(np.uint32)
+    got_all = res.masks().cpu().numpy().view(np.uint32)
+    tab_all = res.inter_tab.cpu().numpy()
+    cand_all, inter_all, union_all = (t.cpu().numpy() for t in (res.best_cand, res.best_inter, res.best_union))
+    iou_all = res.best_iou.cpu().numpy()
+    assert inp.batch.n_jobs == videos * tracks
+    nonempty = 0
+    for jb in inp.batch.jobs:
+        A, T = int(jb["n_cand"]), int(jb["n_tgt"])
+        c0, t0, b0 = int(jb["cand_begin"]), int(jb["tgt_begin"]), int(jb["tab_begin"])
+        proj = c_oracle.project(cfg.K_inv(), cfg.focal_length, cfg.cx, cfg.cy, cfg.height, cfg.width,
+                                bits[int(jb["src_mask"])], jb["normal"], float(jb["offset"]), jb["pivot"],
+                                int(jb["mode"]), inp.batch.xform[c0:c0 + A])
+        assert np.array_equal(got_all[c0:c0 + A], proj)
+        nonempty += int(proj.any())
+        tg = inp.batch.tgt_index[t0:t0 + T]
+        inter, uni, best, iou = c_oracle.score(cfg.height, cfg.width, bits[tg], proj)
+        assert np.array_equal(tab_all[b0:b0 + T * A].reshape(T, A), inter)
+        assert np.array_equal(cand_all[t0:t0 + T], best)
+        assert np.array_equal(inter_all[t0:t0 + T], inter[np.arange(T), best])
+        assert np.array_equal(union_all[t0:t0 + T], uni[np.arange(T), best])
+        assert np.array_equal(iou_all[t0:t0 + T].view(np.uint32), iou.view(np.uint32))
+    assert nonempty == inp.batch.n_jobs

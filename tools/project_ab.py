@@ -39,7 +39,8 @@ def project():
                                pool.source_bits.data_ptr(), pool.source_bbox.data_ptr(), db.xform.data_ptr(),
                                pcd_ws.data_ptr(), pcd_count.data_ptr(), hom_ws.data_ptr(), tmap_ptr, n_tiles, proj_bits.data_ptr(),
                                proj_popc.data_ptr(),
-                               proj_bbox.data_ptr(), torch.cuda.current_stream().cuda_stream), "a3d_project")
+                               proj_bbox.data_ptr(), int(os.environ.get("AB_OUT_MODE", "0")), torch.cuda.current_stream().cuda_stream),
+               "a3d_project")
 
 
 ref = None
