@@ -488,7 +488,7 @@ def _run_split(engine, inp, ws, evs):
                              rows_only=engine.default_out_mode() == _lib.OUT_BBOX_ROWS)
 
 
-def _host_clip(wl, seed, dev, tracks=None, frames=None):
+def _host_clip(wl, seed, dev, tracks=None, frames=None, pin=True):
     """One clip of the workload's shape as HOST predictions: rendered on the device (the CPU renderer takes
     seconds per track), masks moved to pinned host memory."""
     from articulation3d_b200 import synth
@@ -496,7 +496,7 @@ def _host_clip(wl, seed, dev, tracks=None, frames=None):
     tracks, frames = tracks or wl.tracks, frames or wl.frames
     preds, _ = synth.make_video(seed, tracks, frames, cfg, kinds=[synth.KIND_ROT] * tracks, device=dev)
     for p in preds:
-        p.pred_masks = p.pred_masks.cpu().pin_memory()
+        p.pred_masks = p.pred_masks.cpu().pin_memory() if pin else p.pred_masks.cpu()
     torch.cuda.synchronize()
     return preds, cfg
 
@@ -570,6 +570,19 @@ def _e2e(wl, dev, rank, world, dist, steps, videos_per_rank):
                   f"units = visited (frame, candidate) pairs as the reference counts them",
            "videos": n_videos, "schedule": sched, "device_passes_per_step_rank0": passes // steps,
            "gathered_records": {"track_frames": n_frame_rec, "tracks": n_track_rec}}
+    # SURVEY test tier T5 on the real thing: the records every rank received must equal what ONE GPU computes
+    # for all the videos (rank 0 renders the other ranks' clips from their seeds and runs them alone; untimed)
+    if world > 1:
+        ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        if rank == 0:
+            everyone = {v: (clips[v] if v in clips else _host_clip(wl, 2020 + v, dev, pin=False)[0]) for v in range(n_videos)}
+            vids = [(everyone[v], opt_utils.track_planes(everyone[v], cfg)) for v in range(n_videos)]
+            opt_utils.optimize_videos(vids, seeds, cfg=cfg, device=dev)
+            fr1, tr1 = a3d_dist.pack_records(list(range(n_videos)), [pl for _, pl in vids])
+            ok[0] = int(torch.equal(fr1, fr.cpu()) and torch.equal(tr1, tr.cpu()))
+            restore()
+        dist.broadcast(ok, 0)
+        out["records_equal_single_gpu_run"] = bool(int(ok.item()))
     # the reference arm's clip through the same API (rank 0, one video): the two arms on identical input
     if rank == 0:
         from articulation3d_b200 import workloads
