@@ -751,56 +751,6 @@ constexpr uint32_t kMagicBits = 0x4B400000u;          // bit pattern of kMagic
           "r"(fc.p32), "r"(basec)                                                                                \
         : "memory")
 
-// The same point with the u and v coordinates carried as one packed f32x2 (FFMA2 / FADD2: one issue slot for
-// both coordinates): 3 FFMA2 + 1 FADD2 + 2 FFMA + 2 FFMA.SAT instead of 10 FFMA + 2 FADD.  Identical values:
-// every packed operation is the IEEE fma / add of its two lanes.  A3D_FILTER_PACKED selects it at build time.
-#ifndef A3D_FILTER_PACKED
-#define A3D_FILTER_PACKED 0
-#endif
-#define A3D_FILTER_POINT_P(X, KBIT)                                                                              \
-    asm volatile(                                                                                                \
-        "{\n\t.reg .pred p;\n\t.reg .f32 u, v, w, r, ar, sx, sy, tx, ty, dx, dy, adx, ady, nthr;\n\t"            \
-        ".reg .b64 xx, uv, s2, t2, n2, d2;\n\t.reg .b32 bi, wi, ad, bt, one;\n\t"                                \
-        "mov.b64 xx, {%1, %1};\n\t"                                                                              \
-        "fma.rn.f32x2 uv, %2, xx, %3;\n\t"                                                                       \
-        "fma.rn.f32 w, %4, %1, %5;\n\t"                                                                          \
-        "rcp.approx.ftz.f32 r, w;\n\t"                                                                           \
-        "mov.b64 {u, v}, uv;\n\t"                                                                                \
-        "fma.rn.sat.f32 sx, u, r, %6;\n\t"                                                                       \
-        "fma.rn.sat.f32 sy, v, r, %7;\n\t"                                                                       \
-        "mov.b64 s2, {sx, sy};\n\t"                                                                              \
-        "fma.rn.f32x2 t2, s2, %8, %9;\n\t"                                                                       \
-        "sub.rn.f32x2 n2, %9, t2;\n\t"                                                                           \
-        "fma.rn.f32x2 d2, s2, %8, n2;\n\t"                                                                       \
-        "mov.b64 {tx, ty}, t2;\n\t"                                                                              \
-        "mov.b64 {dx, dy}, d2;\n\t"                                                                              \
-        "abs.f32 ar, r;\n\t"                                                                                     \
-        "fma.rn.f32 nthr, %10, ar, %11;\n\t"                                                                     \
-        "neg.f32 nthr, nthr;\n\t"                                                                                \
-        "abs.f32 adx, dx;\n\t"                                                                                   \
-        "abs.f32 ady, dy;\n\t"                                                                                   \
-        "setp.le.f32 p, adx, nthr;\n\t"                                                                          \
-        "setp.le.and.f32 p, ady, nthr, p;\n\t"                                                                   \
-        "mov.b32 bi, tx;\n\t"                                                                                    \
-        "mov.b32 wi, ty;\n\t"                                                                                    \
-        "mad.lo.u32 bi, wi, %12, bi;\n\t"                                                                        \
-        "shr.u32 wi, bi, 5;\n\t"                                                                                 \
-        "mad.lo.u32 ad, wi, 4, %13;\n\t"                                                                         \
-        "selp.b32 one, 1, 0, p;\n\t"                                                                             \
-        "shf.l.wrap.b32 bt, 0, one, bi;\n\t"                                                                     \
-        "red.shared.or.b32 [ad], bt;\n\t"                                                                        \
-        "@!p or.b32 %0, %0, " #KBIT ";\n\t}"                                                                     \
-        : "+r"(unproven)                                                                                         \
-        : "f"(X), "l"(h03), "l"(uvy), "f"(h6), "f"(wy), "f"(fc.chx), "f"(fc.chy), "l"(wh), "l"(mg), "f"(ce),     \
-          "f"(fc.c0h), "r"(fc.p32), "r"(basec)                                                                   \
-        : "memory")
-
-__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-
 // Phase A of one (item, candidate): the 8 points of an item share their source row, so the row terms of
 // the three homography rows are item constants.  Returns the unproven points as a bit mask.
 __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjPX], const float y, const float C,
@@ -821,20 +771,6 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
     const float ce = __fadd_ru(C, hc.y);
     const uint32_t basec = cm - fc.kfold;
     uint32_t unproven = 0;
-#if A3D_FILTER_PACKED
-    {
-        const unsigned long long h03 = pack_f32x2(h0, h3), uvy = pack_f32x2(uy, vy);
-        const unsigned long long wh = pack_f32x2(fc.wmax, fc.hmax), mg = pack_f32x2(12582912.f, 12582912.f);
-        A3D_FILTER_POINT_P(xs[0], 1);
-        A3D_FILTER_POINT_P(xs[1], 2);
-        A3D_FILTER_POINT_P(xs[2], 4);
-        A3D_FILTER_POINT_P(xs[3], 8);
-        A3D_FILTER_POINT_P(xs[4], 16);
-        A3D_FILTER_POINT_P(xs[5], 32);
-        A3D_FILTER_POINT_P(xs[6], 64);
-        A3D_FILTER_POINT_P(xs[7], 128);
-    }
-#else
     {
         const float U0 = fmaf(h0, xs[0], uy), V0 = fmaf(h3, xs[0], vy), W0 = fmaf(h6, xs[0], wy);
         A3D_FILTER_POINT(U0, V0, W0, 1);
@@ -853,7 +789,6 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
         const float U7 = fmaf(h0, xs[7], uy), V7 = fmaf(h3, xs[7], vy), W7 = fmaf(h6, xs[7], wy);
         A3D_FILTER_POINT(U7, V7, W7, 128);
     }
-#endif
     return unproven;
 }
 

@@ -14,8 +14,16 @@ reference's.  Two third-party pieces are absent from this image and from /root/r
 [3P-unverified]: ``skimage.measure.find_contours`` (mask outline; here ``cv2.findContours`` on pixel
 centres: the outline runs half a pixel inside skimage's) and ``mapbox_earcut`` (here a plain ear-clipping
 triangulation: the same polygon, a different but equally valid set of triangles).  pytorch3d's ``Meshes`` /
-``ico_sphere`` are replaced by arrays and the 12-vertex icosahedron.  Without those libraries the
-reference cannot be run here, so this module is pinned by structural tests only (tests/test_export.py).
+``ico_sphere`` are replaced by arrays and the 12-vertex icosahedron.
+
+Parity: tests/test_export.py compares every written file — .obj, .mtl, the 300x300 textures — byte for byte
+with what the reference's OWN ``save_obj_model`` / ``get_single_image_mesh_arti`` / ``save_obj`` write for the
+same predictions and frame (oracle/ref_export.py executes them unmodified under the import shim, with the
+outline and triangulation routines above bound in place of skimage / earcut and small stand-ins for the
+pytorch3d containers; fixtures tests/golden/export/*.json, plus a live comparison where /root/reference
+exists).  That pins the plane conversion, the mesh camera, the rectifying homography and its textures, uv
+coordinates, winding, rotated copies, axis markers, tints, mesh order and the file text; which outline and
+which triangulation skimage / earcut would have chosen stays [3P-unverified].
 """
 from __future__ import annotations
 
@@ -53,7 +61,7 @@ def _get_pcd(verts_xy, normal, offset, K) -> np.ndarray:
     """utils/vis.py:86-102 in float64 with an explicit K."""
     v = np.asarray(verts_xy, dtype=np.float64).reshape(-1, 2)
     ray = np.linalg.inv(K) @ np.hstack((v, np.ones((len(v), 1)))).T
-    depth = float(offset) / (np.asarray(normal, dtype=np.float64) @ ray)
+    depth = offset / np.dot(normal, ray)                # fp32 normal / offset promote to float64 here
     return depth.reshape(-1, 1) * ray.T
 
 
@@ -144,10 +152,13 @@ def plane_mesh(plane_param, mask, image, cfg: OptConfig, webvis: bool = False):
     """-> (verts (V,3) fp32, faces (F,3) int64, uvs (V,2) fp32, texture (300,300,3) uint8) or None when the
     mask has no ring.  ``plane_param`` is the detector's ``[a, b, c]`` (utils/vis.py:258-261)."""
     cv2 = _cv2()
-    p = np.array(plane_param, dtype=np.float64).reshape(3)
-    p = np.array([p[0], -p[2], p[1]])
-    offset = np.linalg.norm(p)
-    normal = p / offset
+    # fp32 as in the reference (the detector's planes are fp32 tensors, utils/vis.py:257-261); get_pcd then
+    # promotes the fp32 normal / offset to float64
+    p = np.array(plane_param, dtype=np.float32).reshape(1, 3)
+    p[:, [1, 2]] = p[:, [2, 1]]
+    p[:, 1] = -p[:, 1]
+    offsets = np.linalg.norm(p, ord=2, axis=1)
+    normal, offset = (p / offsets.reshape(-1, 1))[0], offsets[0]
     rings = mask_to_polygons(mask)
     if not rings:
         return None
@@ -191,14 +202,14 @@ def plane_mesh(plane_param, mask, image, cfg: OptConfig, webvis: bool = False):
 
 def icosahedron(radius: float = 0.1, centre=(0.0, 0.0, 0.0)):
     """``ico_sphere(0)`` scaled and moved (tools/inference.py:75-86): 12 vertices, 20 faces."""
-    t = (1.0 + 5.0 ** 0.5) / 2.0
-    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
-                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
-    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    a, b = 0.5257, 0.8507                                   # pytorch3d's level-0 table, four decimals [3P-unverified]
+    v = np.array([[-a, b, 0], [a, b, 0], [-a, -b, 0], [a, -b, 0], [0, -a, b], [0, a, b], [0, -a, -b], [0, a, -b],
+                  [b, 0, -a], [b, 0, a], [-b, 0, -a], [-b, 0, a]], dtype=np.float32)
     f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
                   [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5],
                   [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
-    return (v * radius + np.asarray(centre, dtype=np.float64)).astype(np.float32), f
+    # Scale(0.1) then Translate(centre), each an fp32 step (tools/inference.py:72-86)
+    return (v * np.float32(radius)) + np.asarray(centre, dtype=np.float64).astype(np.float32), f
 
 
 # ---------------------------------------------------------------------------------------------------

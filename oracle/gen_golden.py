@@ -326,6 +326,58 @@ def main_depth():
         print(f"wrote {path}:", res["f0_pred_plane_out"].tolist())
 
 
+# --------------------------------------------------------------------------
+# row f3: the reference's own .obj export  (tools/inference.py:44-168, utils/vis.py:256-393,
+# utils/mesh_utils.py:126-266) run by oracle/ref_export.py
+# --------------------------------------------------------------------------
+EXPORT_CASES = {"export_a": (5, 2, 12, [0, 1], 3, "l", False), "export_b": (6, 3, 10, [0, 0, 1], 7, "r", True)}
+
+
+def export_case_inputs(name: str):
+    """Seeded inputs of an export fixture: the clip's predictions and a random RGB frame."""
+    from articulation3d_b200 import synth
+    seed, n_tracks, n_frames, kinds, frame_id, axis_dir, webvis = EXPORT_CASES[name]
+    preds, _ = synth.make_video(seed, n_tracks, n_frames, kinds=kinds)
+    image = np.random.RandomState(seed).randint(0, 256, size=(480, 640, 3)).astype(np.uint8)
+    return preds, image, frame_id, axis_dir, webvis
+
+
+def export_digest(folder: str) -> dict:
+    """sha256 of every file an export wrote, plus the element counts of the .obj (for a readable failure)."""
+    import hashlib
+    out = {}
+    for root, _, files in os.walk(folder):
+        for fn in sorted(files):
+            path = os.path.join(root, fn)
+            with open(path, "rb") as f:
+                out[os.path.relpath(path, folder)] = hashlib.sha256(f.read()).hexdigest()
+    with open(os.path.join(folder, "arti_pred.obj")) as f:
+        lines = f.read().splitlines()
+    out["_counts"] = {k: sum(1 for ln in lines if ln.startswith(k + " ")) for k in ("v", "vt", "f", "usemtl")}
+    out["_meshes"] = sum(1 for ln in lines if ln.startswith("# mesh"))
+    return out
+
+
+def main_export():
+    import json
+    import tempfile
+    from articulation3d_b200 import synth
+    from oracle import ref_export
+    if not ref_shim.available():
+        raise SystemExit("reference not present; fixtures can only be generated in the build container")
+    os.makedirs(os.path.join(GOLDEN_DIR, "export"), exist_ok=True)
+    for name in EXPORT_CASES:
+        preds, image, frame_id, axis_dir, webvis = export_case_inputs(name)
+        rp = synth.clone_preds(preds, ref_shim.Instances, ref_shim.Boxes)
+        with tempfile.TemporaryDirectory() as tmp:
+            folder = ref_export.run_reference_export(rp, [image] * len(preds), frame_id, tmp, axis_dir=axis_dir, webvis=webvis)
+            digest = export_digest(folder)
+        path = os.path.join(GOLDEN_DIR, "export", f"{name}.json")
+        with open(path, "w") as f:
+            json.dump(digest, f, indent=1, sort_keys=True)
+        print(f"wrote {path}:", digest["_counts"], digest["_meshes"], "meshes")
+
+
 def main():
     from articulation3d_b200 import synth
     if not ref_shim.available():
@@ -350,5 +402,7 @@ if __name__ == "__main__":
         main_eval()
     elif "--depth" in sys.argv:
         main_depth()
+    elif "--export" in sys.argv:
+        main_export()
     else:
         main()

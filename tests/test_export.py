@@ -1,6 +1,6 @@
-"""Row f3 of SURVEY.md §8f: the textured .obj export (articulation3d_b200/export.py).  The reference's export
-cannot run here (pytorch3d, skimage, mapbox_earcut absent), so these are structural tests: valid
-triangulations, the file layout of utils/mesh_utils.py:_save, and the geometry of the rotated copies."""
+"""Row f3 of SURVEY.md §8f: the textured .obj export (articulation3d_b200/export.py).  Structural tests (valid
+triangulations, the file layout of utils/mesh_utils.py:_save, the geometry of the rotated copies) and, at the
+end, byte-for-byte comparisons with the files the reference's own export writes (oracle/ref_export.py)."""
 import os
 import re
 
@@ -121,3 +121,43 @@ def test_frame_without_predictions_is_skipped(tmp_path, capsys):
     empty.pred_rot_axis = torch.zeros(0, 3)
     assert export.save_obj_model(str(tmp_path), [empty], 0, cfg=cfg) is None
     assert "no prediction" in capsys.readouterr().out
+
+
+# ---------------------------------------------------------------------------------------------------
+# pinned against the reference's own export (oracle/ref_export.py runs tools/inference.py:save_obj_model,
+# utils/vis.py:get_single_image_mesh_arti and utils/mesh_utils.py:save_obj unmodified; only the outline and
+# the triangulation routines, absent third-party code, are the product's)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["export_a", "export_b"])
+def test_export_equals_reference_fixture(name, tmp_path, golden_dir):
+    """Every file the export writes — .obj, .mtl, the nine 300x300 textures — byte for byte against the digest
+    of what the reference's own export wrote for the same predictions and frame (tests/golden/export/*.json,
+    generated by oracle/gen_golden.py --export)."""
+    import json
+    from oracle.gen_golden import export_case_inputs, export_digest
+    with open(os.path.join(golden_dir, "export", f"{name}.json")) as f:
+        want = json.load(f)
+    preds, image, frame_id, axis_dir, webvis = export_case_inputs(name)
+    obj = export.save_obj_model(str(tmp_path), preds, frame_id, image=image, axis_dir=axis_dir, webvis=webvis)
+    got = export_digest(os.path.dirname(obj))
+    assert got["_counts"] == want["_counts"] and got["_meshes"] == want["_meshes"]
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert got[k] == want[k], f"{k} differs from the reference's file"
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("seed,frame_id,axis_dir", [(11, 2, "l"), (12, 9, "r")])
+def test_export_equals_live_reference(seed, frame_id, axis_dir, tmp_path):
+    """The same comparison against the reference executed now (only where /root/reference exists)."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference sources not on this box")
+    from oracle import ref_export
+    from oracle.gen_golden import export_digest
+    preds, _ = synth.make_video(seed, 2, 12, kinds=[0, 1])
+    image = np.random.RandomState(seed).randint(0, 256, size=(480, 640, 3)).astype(np.uint8)
+    rp = synth.clone_preds(preds, ref_shim.Instances, ref_shim.Boxes)
+    ref_dir = ref_export.run_reference_export(rp, [image] * len(preds), frame_id, str(tmp_path / "ref"), axis_dir=axis_dir)
+    obj = export.save_obj_model(str(tmp_path / "own"), preds, frame_id, image=image, axis_dir=axis_dir)
+    assert export_digest(os.path.dirname(obj)) == export_digest(ref_dir)

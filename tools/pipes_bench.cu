@@ -6,6 +6,7 @@
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/_build/pipes_bench tools/pipes_bench.cu
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #define ITERS 2048
@@ -16,7 +17,8 @@ enum Op { FFMA, FFMA2, FADD, FMUL, IMAD, LOP3, IADD3, SHF, FSETP_SEL, FMNMX, MUF
           MIX_FFMA_MUFU8, N_OPS };
 
 template <int OP>
-__global__ void __launch_bounds__(1024, 1) k(uint32_t* out, float fb, float fc, uint32_t ub, uint32_t uc, long long* cycles) {
+__global__ void __launch_bounds__(1024, 1) k(uint32_t* out, float fb, float fc, uint32_t ub, uint32_t uc,
+                                              unsigned long long* t_first, unsigned long long* t_last) {
     __shared__ uint32_t sm[4096];
     for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = 0;
     __syncthreads();
@@ -31,7 +33,8 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, float fb, float fc, 
     }
     const unsigned long long wb = ((unsigned long long)__float_as_uint(fb) << 32) | __float_as_uint(fb);
     const unsigned long long wc = ((unsigned long long)__float_as_uint(fc) << 32) | __float_as_uint(fc);
-    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sm) + 4u * ((threadIdx.x * 33u) & 4095u);
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sm) + 4u * ((threadIdx.x * 33u) & 2047u);   // + 128 * i stays inside
+    __syncthreads();
     const long long t0 = clock64();
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
@@ -90,22 +93,32 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, float fb, float fc, 
     for (int i = 0; i < NCH; ++i) s += u[i] + __float_as_uint(a[i]) + (uint32_t)(w[i] >> 32) + (uint32_t)w[i];
     __syncthreads();
     out[blockIdx.x * blockDim.x + threadIdx.x] = s + sm[threadIdx.x];
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+    // the CTA's span: first warp to start .. last warp to finish (a single warp's clock favours whichever
+    // warp the scheduler prefers)
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+        atomicMin(t_first, (unsigned long long)t0);
+        atomicMax(t_last, (unsigned long long)t1);
+    }
 }
 
 template <int OP>
 void run(const char* name, int instr_per_chain_step) {
     uint32_t* out;
-    long long *cyc, h;
+    unsigned long long *cyc, hv[2];
+    long long h = 0;
     int sms;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     cudaMalloc(&out, (size_t)sms * 1024 * 4);
-    cudaMalloc(&cyc, 8);
+    cudaMalloc(&cyc, 16);
     for (int rep = 0; rep < 2; ++rep) {
-        k<OP><<<sms, 1024>>>(out, 1.0000001f, 1e-9f, 0x9e3779b9u, 0x7f4a7c15u, cyc);
-        cudaDeviceSynchronize();
+        hv[0] = ~0ull; hv[1] = 0ull;
+        cudaMemcpy(cyc, hv, 16, cudaMemcpyHostToDevice);
+        k<OP><<<sms, 1024>>>(out, 1.0000001f, 1e-9f, 0x9e3779b9u, 0x7f4a7c15u, cyc, cyc + 1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("%-28s FAILED: %s\n", name, cudaGetErrorString(e)); exit(1); }
+        cudaMemcpy(hv, cyc, 16, cudaMemcpyDeviceToHost);
+        h = (long long)(hv[1] - hv[0]);
     }
-    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
     const double winstr_per_smsp = 8.0 * ITERS * NCH * instr_per_chain_step;     // 8 warps per scheduler
     printf("%-28s %2d instr/step  %10lld cycles  -> %6.3f cycles per warp-instr per SMSP  (%5.1f lane-instr/clk/SM)\n", name,
            instr_per_chain_step, h, (double)h / winstr_per_smsp, 128.0 * winstr_per_smsp / (double)h);
