@@ -231,7 +231,6 @@ __global__ void __launch_bounds__(256) k_mask_meta(const uint32_t* __restrict__ 
     if (threadIdx.x == 0) stat_store(red, popc + m, bbox + 4 * m);
 }
 
-constexpr int kProjPXc = 8;                         // points per k_project item (rows of the cloud are padded to it)
 constexpr int kHF = 12;                              // floats per candidate: H (9, recentred), E_cand, exact-only flag, pad
 
 // fp64 set-up of one candidate's homography; m = its 12 floats (R row-major, t), (x0, y0) the centre the
@@ -319,15 +318,11 @@ __device__ __forceinline__ void make_homography(const Cam& cam, const a3d_job_t&
 
 // ---------------------------------------------------------------------------
 // unproject: source mask -> compacted fp32 point cloud (get_pcd, vis.py:86-102).
-// CTAs per job (one, or several when there are few jobs).  Phase 1: per-row point counts of the source
-// bounding box, each padded to a multiple of 8, and their exclusive prefix: every source ROW starts at an
-// 8-point boundary of the cloud, so the 8-point items k_project deals to its threads never straddle rows
-// (the row coordinate is an item constant: one FMA per homography row instead of two per point).  The pad
-// slots repeat the row's last point — duplicates are idempotent under the OR splat.  Phase 2: one warp per
-// row, word by word, one lane per pixel: float64 ray/plane intersection, one rounding to fp32, store at
-// row base + rank (row-major = the reference's nonzero() order, up to the pads).  Output slice of job j:
-// X | Y | Z | packed pixel | bound coefficient planes of pcd_cap floats each, starting at
-// A3D_PCD_PLANES * pcd_begin; pcd_cap >= popcount + 7 * rows of the source box.
+// One CTA per job.  Phase 1: exclusive prefix of the per-word popcounts of the
+// source bounding box (row-major = the reference's nonzero() order).  Phase 2:
+// one warp per word, one lane per pixel: float64 ray/plane intersection, one
+// rounding to fp32, store at prefix + rank.  Output slice of job j:
+// X | Y | Z planes of pcd_cap floats each, starting at 3 * pcd_begin.
 // ---------------------------------------------------------------------------
 constexpr int kUnprojThreads = 256;
 
@@ -336,7 +331,7 @@ __global__ void __launch_bounds__(kUnprojThreads)
 k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* __restrict__ src_bits,
             const int32_t* __restrict__ src_bbox, const float* __restrict__ xform, float* __restrict__ pcd,
             int32_t* __restrict__ pcd_count, float* __restrict__ hom) {
-    extern __shared__ uint32_t rowbase[];           // one entry per row of the source box
+    extern __shared__ uint32_t prefix[];            // one entry per word of the source box
     __shared__ uint32_t warp_sum[kUnprojThreads / 32];
     __shared__ uint32_t total_s;
     __shared__ int tmax_s;
@@ -352,9 +347,8 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
         return;
     }
     const uint32_t* src = src_bits + (size_t)job.src_mask * cam.H * pitch;
-    const int ncols = w1 - w0 + 1, nrows = r1 - r0 + 1;
+    const int ncols = w1 - w0 + 1, nwords = (r1 - r0 + 1) * ncols;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kWarps = kUnprojThreads / 32;
 
     // homographies of the job's candidates for the filtered projection, one candidate per thread; source
     // coordinates are taken from the centre of the source box (smaller terms, tighter bound)
@@ -369,19 +363,14 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
         }
     }
 
-    // phase 1a: padded point count of every row
-    for (int rr = warp; rr < nrows; rr += kWarps) {
-        uint32_t c = 0;
-        for (int j = lane; j < ncols; j += 32) c += __popc(src[(r0 + rr) * pitch + w0 + j]);
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0) rowbase[rr] = (c + (kProjPXc - 1)) & ~(uint32_t)(kProjPXc - 1);
-    }
-    __syncthreads();
-    // phase 1b: block-wide exclusive scan, each thread owns a contiguous chunk of rows
-    const int chunk = (nrows + kUnprojThreads - 1) / kUnprojThreads;
-    const int rb = min(nrows, (int)threadIdx.x * chunk), re = min(nrows, rb + chunk);
+    // phase 1: block-wide exclusive scan, each thread owns a contiguous chunk of words
+    const int chunk = (nwords + kUnprojThreads - 1) / kUnprojThreads;
+    const int wb = min(nwords, (int)threadIdx.x * chunk), we = min(nwords, wb + chunk);
     uint32_t mine = 0;
-    for (int r = rb; r < re; ++r) mine += rowbase[r];
+    for (int w = wb; w < we; ++w) {
+        const int rr = w / ncols;
+        mine += __popc(src[(r0 + rr) * pitch + w0 + (w - rr * ncols)]);
+    }
     uint32_t incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -393,11 +382,12 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
     uint32_t base = incl - mine;
     for (int i = 0; i < warp; ++i) base += warp_sum[i];
     if (threadIdx.x == kUnprojThreads - 1) total_s = base + mine;
-    for (int r = rb; r < re; ++r) {
-        const uint32_t v = rowbase[r];
-        rowbase[r] = base;
-        base += v;
+    for (int w = wb; w < we; ++w) {
+        const int rr = w / ncols;
+        prefix[w] = base;
+        base += __popc(src[(r0 + rr) * pitch + w0 + (w - rr * ncols)]);
     }
+    __syncthreads();
 
     // phase 2
     const int cap = job.pcd_cap;
@@ -422,94 +412,62 @@ k_unproject(const Cam cam, const a3d_job_t* __restrict__ jobs, const uint32_t* _
         m = __reduce_max_sync(0xffffffffu, m);
         if (lane == 0 && m) atomicMax(&tmax_s, m);
     }
-    __syncthreads();                                             // rowbase, total_s, tmax_s
+    __syncthreads();
     const double tmax = (double)__int_as_float(tmax_s);
     const double a0 = (double)job.pivot[0], a1 = (double)job.pivot[1], a2 = (double)job.pivot[2];
     const double amax = fmax(fabs(a0), fmax(fabs(a1), fabs(a2)));
     const double K1 = (double)cam.f + fmax(fabs((double)cam.cx), fabs((double)cam.cy));
     const double Dm = (double)max(cam.W, cam.H);
-    // the rows of the box are dealt round-robin to the warps of the gridDim.y CTAs of this job
-    const int rstride = kWarps * gridDim.y;
-    for (int rr = blockIdx.y * kWarps + warp; rr < nrows; rr += rstride) {
-        const int row = r0 + rr;
-        const double yd = (double)row;
-        const uint32_t row_begin = rowbase[rr];
-        uint32_t run = row_begin;                                // next free slot of the row
-        float lx = 0.f, ly = 0.f, lz = 0.f, lc = 0.f;            // this lane's latest point
-        uint32_t lxy = 0;
-        int last_lane = -1;
-        for (int j0 = 0; j0 < ncols; j0 += 32) {
-            const uint32_t myw = (j0 + lane < ncols) ? src[row * pitch + w0 + j0 + lane] : 0u;
-            uint32_t nzm = __ballot_sync(0xffffffffu, myw != 0u);
-            while (nzm) {
-                const int j = __ffs(nzm) - 1;
-                nzm &= nzm - 1;
-                const uint32_t bits = __shfl_sync(0xffffffffu, myw, j);
-                const int wc = w0 + j0 + j;
-                if ((bits >> lane) & 1u) {
-                    const int pos = (int)run + __popc(bits & ((1u << lane) - 1u));
-                    const double xd = (double)(wc * 32 + lane);
-                    double rx, ry, rz;
-                    if (kSparseK) {
-                        rx = __dadd_rn(__dmul_rn(cam.k[0], xd), cam.k[2]);
-                        ry = __dadd_rn(__dmul_rn(cam.k[4], yd), cam.k[5]);
-                        rz = 1.0;
-                    } else {
-                        rx = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[0], xd), __dmul_rn(cam.k[1], yd)), cam.k[2]);
-                        ry = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[3], xd), __dmul_rn(cam.k[4], yd)), cam.k[5]);
-                        rz = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[6], xd), __dmul_rn(cam.k[7], yd)), cam.k[8]);
-                    }
-                    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(n0, rx), __dmul_rn(n1, ry)), __dmul_rn(n2, rz));
-                    const double depth = __ddiv_rn(off, dot);
-                    float x = __double2float_rn(__dmul_rn(depth, rx));
-                    float y = __double2float_rn(__dmul_rn(depth, ry));
-                    float z = __double2float_rn(__dmul_rn(depth, rz));
-                    // a point with any non-finite coordinate leaves the first homogeneous transform
-                    // all-NaN (every output mixes 0*coordinate terms)
-                    const bool finite = fabsf(x) <= 3.402823466e38f && fabsf(y) <= 3.402823466e38f && fabsf(z) <= 3.402823466e38f;
-                    if (!finite) {
-                        x = NaNf; y = NaNf; z = NaNf;
-                    }
-                    // coefficient C of the point: |q_exact - q_true| <= C * |1/W_h| + c0 for every candidate, W_h the
-                    // homogeneous w of the plane-induced homography (scaled by n.ray, hence the |dot| factor)
-                    const double p1 = fabs((double)x) + fabs((double)y) + fabs((double)z);
-                    double Sig, M;
-                    if (job.mode == A3D_MODE_SEQ) {
-                        const double pp1 = fabs((double)x - a0) + fabs((double)y - a1) + fabs((double)z - a2);
-                        Sig = 1.001 * (1.01 * p1 + 5.0 * pp1) + amax;
-                        M = 1.001 * pp1 + amax;
-                    } else {
-                        Sig = 1.001 * 5.01 * p1 + tmax;
-                        M = 1.001 * p1 + tmax;
-                    }
-                    const double coef = 5.9604644775390625e-8 * 1.25 * fabs(dot) * (K1 * (Sig + 2.0 * M) + Dm * Sig);
-                    float cf = __double2float_ru(coef * 1.000001);
-                    const double dmag = fabs(n0 * rx) + fabs(n1 * ry) + fabs(n2 * rz);
-                    if (!finite || !(fabs(dot) >= 1e-6 * dmag) || !(cf <= 3.402823466e38f)) cf = INFf;
-                    lx = x; ly = y; lz = z; lc = cf;
-                    lxy = ((uint32_t)row << 16) | (uint32_t)(wc * 32 + lane);
-                    if (pos < cap) {
-                        Xp[pos] = x; Yp[pos] = y; Zp[pos] = z;
-                        XYp[pos] = lxy;
-                        Cp[pos] = cf;
-                    }
-                }
-                run += __popc(bits);
-                last_lane = 31 - __clz(bits);
-            }
+    // the words of the box are dealt round-robin to the warps of the gridDim.y CTAs of this job
+    const int wstride = (kUnprojThreads / 32) * gridDim.y;
+    for (int w = blockIdx.y * (kUnprojThreads / 32) + warp; w < nwords; w += wstride) {
+        const int rr = w / ncols;
+        const int row = r0 + rr, wc = w0 + (w - rr * ncols);
+        const uint32_t bits = src[row * pitch + wc];
+        if (!((bits >> lane) & 1u)) continue;
+        const int pos = (int)prefix[w] + __popc(bits & ((1u << lane) - 1u));
+        if (pos >= cap) continue;
+        const double xd = (double)(wc * 32 + lane), yd = (double)row;
+        double rx, ry, rz;
+        if (kSparseK) {
+            rx = __dadd_rn(__dmul_rn(cam.k[0], xd), cam.k[2]);
+            ry = __dadd_rn(__dmul_rn(cam.k[4], yd), cam.k[5]);
+            rz = 1.0;
+        } else {
+            rx = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[0], xd), __dmul_rn(cam.k[1], yd)), cam.k[2]);
+            ry = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[3], xd), __dmul_rn(cam.k[4], yd)), cam.k[5]);
+            rz = __dadd_rn(__dadd_rn(__dmul_rn(cam.k[6], xd), __dmul_rn(cam.k[7], yd)), cam.k[8]);
         }
-        if (last_lane >= 0) {                                    // pad slots: copies of the row's last point
-            const float px = __shfl_sync(0xffffffffu, lx, last_lane), py = __shfl_sync(0xffffffffu, ly, last_lane);
-            const float pz = __shfl_sync(0xffffffffu, lz, last_lane), pc = __shfl_sync(0xffffffffu, lc, last_lane);
-            const uint32_t pxy = __shfl_sync(0xffffffffu, lxy, last_lane);
-            const uint32_t row_end = row_begin + ((run - row_begin + (kProjPXc - 1)) & ~(uint32_t)(kProjPXc - 1));
-            const uint32_t slot = run + lane;
-            if (slot < row_end && (int)slot < cap) {
-                Xp[slot] = px; Yp[slot] = py; Zp[slot] = pz;
-                XYp[slot] = pxy;
-                Cp[slot] = pc;
-            }
+        const double dot = __dadd_rn(__dadd_rn(__dmul_rn(n0, rx), __dmul_rn(n1, ry)), __dmul_rn(n2, rz));
+        const double depth = __ddiv_rn(off, dot);
+        float x = __double2float_rn(__dmul_rn(depth, rx));
+        float y = __double2float_rn(__dmul_rn(depth, ry));
+        float z = __double2float_rn(__dmul_rn(depth, rz));
+        // a point with any non-finite coordinate leaves the first homogeneous transform
+        // all-NaN (every output mixes 0*coordinate terms)
+        const bool finite = fabsf(x) <= 3.402823466e38f && fabsf(y) <= 3.402823466e38f && fabsf(z) <= 3.402823466e38f;
+        if (!finite) {
+            x = NaNf; y = NaNf; z = NaNf;
         }
+        Xp[pos] = x; Yp[pos] = y; Zp[pos] = z;
+        // coefficient C of the point: |q_exact - q_true| <= C * |1/W_h| + c0 for every candidate, W_h the
+        // homogeneous w of the plane-induced homography (scaled by n.ray, hence the |dot| factor)
+        const double p1 = fabs((double)x) + fabs((double)y) + fabs((double)z);
+        double Sig, M;
+        if (job.mode == A3D_MODE_SEQ) {
+            const double pp1 = fabs((double)x - a0) + fabs((double)y - a1) + fabs((double)z - a2);
+            Sig = 1.001 * (1.01 * p1 + 5.0 * pp1) + amax;
+            M = 1.001 * pp1 + amax;
+        } else {
+            Sig = 1.001 * 5.01 * p1 + tmax;
+            M = 1.001 * p1 + tmax;
+        }
+        const double coef = 5.9604644775390625e-8 * 1.25 * fabs(dot) * (K1 * (Sig + 2.0 * M) + Dm * Sig);
+        float cf = __double2float_ru(coef * 1.000001);
+        const double dmag = fabs(n0 * rx) + fabs(n1 * ry) + fabs(n2 * rz);
+        if (!finite || !(fabs(dot) >= 1e-6 * dmag) || !(cf <= 3.402823466e38f)) cf = INFf;
+        XYp[pos] = ((uint32_t)row << 16) | (uint32_t)(wc * 32 + lane);
+        Cp[pos] = cf;
     }
     if (threadIdx.x == 0 && blockIdx.y == 0) pcd_count[blockIdx.x] = min((int)total_s, cap);
 }
@@ -539,7 +497,7 @@ constexpr int kProjCtasPerSm = 1024 / kProjThreads;
 #ifndef A3D_PROJECT_PERSISTENT_DEFAULT
 #define A3D_PROJECT_PERSISTENT_DEFAULT false
 #endif
-constexpr int kProjPX = kProjPXc;
+constexpr int kProjPX = 8;
 
 // The reference's fp32 chain for one point and one candidate (kMode is a compile-time constant so the
 // code is straight-line): transform, project2D, `.long()`, clamp.  For SEQ the point is already in the
@@ -695,7 +653,7 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
 // [2] of those, pairs of exact-only candidates, [3] warp-iterations of the exact loop
 __device__ unsigned long long g_filter_stats[4];
 #endif
-// kMagic = 12582912.f = 1.5 * 2^23 (0f4B400000 in the PTX below): x + kMagic holds rint(x) in its low mantissa bits
+constexpr float kMagic = 12582912.f;                 // 1.5 * 2^23: x + kMagic holds rint(x) in its low mantissa bits
 // Phase A of one (item, candidate): the cheap pixel of up to 8 points; proven ones are splatted, the
 // others come back as a bit mask (bit k = point k needs the exact chain).
 // The integer-pipe instructions (min/max, select, logic, compares; half rate) bound this loop, so the work
@@ -705,91 +663,48 @@ __device__ unsigned long long g_filter_stats[4];
 // all-zero operand when it is unproven.
 struct FilterConst {
     float wmax, hmax, chx, chy, c0h;                  // chx = -0.5 / wmax; c0h = c0 - 0.5 (rounded up)
-    uint32_t p32;                                     // bits per packed row (pitch * 32)
-    uint32_t kfold;                                   // 4 * ((kMagicBits * (p32 + 1)) >> 5): the magic-number bits folded out of the word address
+    int pitch4;
 };
-constexpr uint32_t kMagicBits = 0x4B400000u;          // bit pattern of kMagic
 
-// One point of phase A, all in one PTX block so that the instruction selection is fixed: 13 FMA-pipe
-// operations (the caller's three FFMA of the homography rows included), 1 MUFU, 2 FSETP, the word address
-// as IMAD / SHF / IMAD on the bits of the two magic-number sums (bit index of the pixel in the mask =
-// row * p32 + col; both sums carry the constant kMagicBits, whose contribution is a multiple of 32 and is
-// folded into `basec`), one ATOMS whose operand is zero for an unproven point (ptxas turns a predicated
-// ATOMS plus its address arithmetic into a branch region: 3 instructions more) and one predicated OR that
-// records the unproven point.
-#define A3D_FILTER_POINT(U, V, W, KBIT)                                                                          \
-    asm volatile(                                                                                                \
-        "{\n\t.reg .pred p;\n\t.reg .f32 r, ar, sx, sy, tx, ty, nx, ny, dx, dy, adx, ady, nthr;\n\t"             \
-        ".reg .b32 bi, wi, ad, bt, one;\n\t"                                                                          \
-        "rcp.approx.ftz.f32 r, %3;\n\t"                                                                          \
-        "fma.rn.sat.f32 sx, %1, r, %4;\n\t"                                                                      \
-        "fma.rn.sat.f32 sy, %2, r, %5;\n\t"                                                                      \
-        "fma.rn.f32 tx, sx, %6, 0f4B400000;\n\t"                                                                 \
-        "fma.rn.f32 ty, sy, %7, 0f4B400000;\n\t"                                                                 \
-        "sub.rn.f32 nx, 0f4B400000, tx;\n\t"                                                                     \
-        "sub.rn.f32 ny, 0f4B400000, ty;\n\t"                                                                     \
-        "fma.rn.f32 dx, sx, %6, nx;\n\t"                                                                         \
-        "fma.rn.f32 dy, sy, %7, ny;\n\t"                                                                         \
-        "abs.f32 ar, r;\n\t"                                                                                     \
-        "fma.rn.f32 nthr, %8, ar, %9;\n\t"                                                                       \
-        "neg.f32 nthr, nthr;\n\t"                                                                                \
-        "abs.f32 adx, dx;\n\t"                                                                                   \
-        "abs.f32 ady, dy;\n\t"                                                                                   \
-        "setp.le.f32 p, adx, nthr;\n\t"                                                                          \
-        "setp.le.and.f32 p, ady, nthr, p;\n\t"                                                                   \
-        "mov.b32 bi, tx;\n\t"                                                                                    \
-        "mov.b32 wi, ty;\n\t"                                                                                    \
-        "mad.lo.u32 bi, wi, %10, bi;\n\t"                                                                        \
-        "shr.u32 wi, bi, 5;\n\t"                                                                                 \
-        "mad.lo.u32 ad, wi, 4, %11;\n\t"                                                                         \
-        "selp.b32 one, 1, 0, p;\n\t"                                                                             \
-        "shf.l.wrap.b32 bt, 0, one, bi;\n\t"                                                                     \
-        "red.shared.or.b32 [ad], bt;\n\t"                                                                        \
-        "@!p or.b32 %0, %0, " #KBIT ";\n\t}"                                                                     \
-        : "+r"(unproven)                                                                                         \
-        : "f"(U), "f"(V), "f"(W), "f"(fc.chx), "f"(fc.chy), "f"(fc.wmax), "f"(fc.hmax), "f"(ce), "f"(fc.c0h),    \
-          "r"(fc.p32), "r"(basec)                                                                                \
-        : "memory")
-
-// Phase A of one (item, candidate): the 8 points of an item share their source row, so the row terms of
-// the three homography rows are item constants.  Returns the unproven points as a bit mask.
-__device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjPX], const float y, const float C,
-                                                        const float* __restrict__ h, const FilterConst& fc,
-                                                        uint32_t cm) {
+template <bool kFull>
+__device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjPX], const float (&ys)[kProjPX],
+                                                        const float C, int nvalid, const float* __restrict__ h,
+                                                        const FilterConst& fc, uint32_t cm) {
 #ifdef A3D_FILTER_STATS
-    atomicAdd(&g_filter_stats[0], 8ull);
+    atomicAdd(&g_filter_stats[0], (unsigned long long)(kFull ? 8 : nvalid));
     if (h[10] != 0.f) {
-        atomicAdd(&g_filter_stats[1], 8ull);
-        atomicAdd(&g_filter_stats[2], 8ull);
+        atomicAdd(&g_filter_stats[1], (unsigned long long)(kFull ? 8 : nvalid));
+        atomicAdd(&g_filter_stats[2], (unsigned long long)(kFull ? 8 : nvalid));
     }
 #endif
-    const float4 ha = reinterpret_cast<const float4*>(h)[0], hb = reinterpret_cast<const float4*>(h)[1],
-                 hc = reinterpret_cast<const float4*>(h)[2];
-    if (hc.z != 0.f) return 0u;                        // exact-only candidate: handled by the straight-line chain
-    const float h0 = ha.x, h3 = ha.w, h6 = hb.z;
-    const float uy = fmaf(ha.y, y, ha.z), vy = fmaf(hb.x, y, hb.y), wy = fmaf(hb.w, y, hc.x);
-    const float ce = __fadd_ru(C, hc.y);
-    const uint32_t basec = cm - fc.kfold;
-    uint32_t unproven = 0;
-    {
-        const float U0 = fmaf(h0, xs[0], uy), V0 = fmaf(h3, xs[0], vy), W0 = fmaf(h6, xs[0], wy);
-        A3D_FILTER_POINT(U0, V0, W0, 1);
-        const float U1 = fmaf(h0, xs[1], uy), V1 = fmaf(h3, xs[1], vy), W1 = fmaf(h6, xs[1], wy);
-        A3D_FILTER_POINT(U1, V1, W1, 2);
-        const float U2 = fmaf(h0, xs[2], uy), V2 = fmaf(h3, xs[2], vy), W2 = fmaf(h6, xs[2], wy);
-        A3D_FILTER_POINT(U2, V2, W2, 4);
-        const float U3 = fmaf(h0, xs[3], uy), V3 = fmaf(h3, xs[3], vy), W3 = fmaf(h6, xs[3], wy);
-        A3D_FILTER_POINT(U3, V3, W3, 8);
-        const float U4 = fmaf(h0, xs[4], uy), V4 = fmaf(h3, xs[4], vy), W4 = fmaf(h6, xs[4], wy);
-        A3D_FILTER_POINT(U4, V4, W4, 16);
-        const float U5 = fmaf(h0, xs[5], uy), V5 = fmaf(h3, xs[5], vy), W5 = fmaf(h6, xs[5], wy);
-        A3D_FILTER_POINT(U5, V5, W5, 32);
-        const float U6 = fmaf(h0, xs[6], uy), V6 = fmaf(h3, xs[6], vy), W6 = fmaf(h6, xs[6], wy);
-        A3D_FILTER_POINT(U6, V6, W6, 64);
-        const float U7 = fmaf(h0, xs[7], uy), V7 = fmaf(h3, xs[7], vy), W7 = fmaf(h6, xs[7], wy);
-        A3D_FILTER_POINT(U7, V7, W7, 128);
+    if (h[10] != 0.f) return 0u;                       // exact-only candidate: handled by the straight-line chain
+    const float h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3], h4 = h[4], h5 = h[5], h6 = h[6], h7 = h[7], h8 = h[8];
+    const float ce = __fadd_ru(C, h[9]);
+    // bits of (kMagic + n) = 0x4B400000 + n: fold the constant out of  row * pitch4 + (col >> 5) * 4
+    const uint32_t cmk = cm - 0x4B400000u * (uint32_t)fc.pitch4 - ((0x4B400000u >> 5) << 2);
+    uint32_t proven = 0;
+#pragma unroll
+    for (int k = 0; k < kProjPX; ++k) {
+        if (!kFull && k >= nvalid) break;
+        const float Uq = fmaf(h0, xs[k], fmaf(h1, ys[k], h2));
+        const float Vq = fmaf(h3, xs[k], fmaf(h4, ys[k], h5));
+        const float Wq = fmaf(h6, xs[k], fmaf(h7, ys[k], h8));
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(Wq));
+        float sx, sy;                                   // clamp((u/w - 0.5) / (W-1), 0, 1); NaN -> 0
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(sx) : "f"(Uq), "f"(r), "f"(fc.chx));
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(sy) : "f"(Vq), "f"(r), "f"(fc.chy));
+        const float tx = fmaf(sx, fc.wmax, kMagic), ty = fmaf(sy, fc.hmax, kMagic);
+        const float dx = fmaf(sx, fc.wmax, -__fsub_rn(tx, kMagic)), dy = fmaf(sy, fc.hmax, -__fsub_rn(ty, kMagic));
+        const float neg_thr = fmaf(ce, fabsf(r), fc.c0h);         // eps - 0.5
+        // proven only if both fractional parts keep more than eps from the integer boundaries (a NaN or
+        // infinite eps fails the comparison)
+        const uint32_t one = (fabsf(dx) <= -neg_thr && fabsf(dy) <= -neg_thr) ? 1u : 0u;
+        const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
+        red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
+        proven += one << k;
     }
-    return unproven;
+    return ~proven & (kFull ? 0xffu : ((1u << nvalid) - 1u));
 }
 
 // Phase B: the exact chain for the (candidate, point) pairs of one item that phase A could not prove.
@@ -831,38 +746,41 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
     const float Dm = (float)max(cam.W, cam.H);
     const int pitch4 = cam.pitch * 4, words4 = words * 4;
     FilterConst fc;
-    fc.wmax = wmax; fc.hmax = hmax;
-    fc.p32 = (uint32_t)cam.pitch * 32u;
-    fc.kfold = 4u * ((kMagicBits * (fc.p32 + 1u)) >> 5);
+    fc.wmax = wmax; fc.hmax = hmax; fc.pitch4 = pitch4;
     fc.chx = -0.5f / wmax; fc.chy = -0.5f / hmax;
     // (Dm + 1) (2^-22 + 6 * 2^-24) + 2^-24 Dm, rounded up: reciprocal, scaled clamp and division terms
     fc.c0h = __fadd_ru(__fmul_ru(__fadd_ru(__fmul_ru(__fadd_ru(Dm, 1.f), 5.9604645e-7f), __fmul_ru(Dm, 5.9604645e-8f)), 1.0001f), -0.5f);
     const uint32_t masks_s = (uint32_t)__cvta_generic_to_shared(masks);
-    const int nitems = npts / kProjPX;                // k_unproject pads every source row to whole items
-    // y: the item's source row; C: the largest coefficient of the item's points (neighbouring pixels: nearly equal)
-    auto load_item = [&](int item, float (&xs)[kProjPX], float& y, float& C) {
+    const int nitems = (npts + kProjPX - 1) / kProjPX;
+    // C: the largest coefficient of the item's points (neighbouring pixels: nearly equal); unwritten slots of
+    // the last item are ignored
+    auto load_item = [&](int item, float (&xs)[kProjPX], float (&ys)[kProjPX], float& C, int nvalid) {
         const uint4 a = __ldg(XY4 + 2 * item), b = __ldg(XY4 + 2 * item + 1);
         const uint32_t xy[kProjPX] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int k = 0; k < kProjPX; ++k) xs[k] = (float)((int)(xy[k] & 0xffffu) - x0);
-        y = (float)((int)(xy[0] >> 16) - y0);
+        for (int k = 0; k < kProjPX; ++k) {
+            xs[k] = (float)((int)(xy[k] & 0xffffu) - x0);
+            ys[k] = (float)((int)(xy[k] >> 16) - y0);
+        }
         const float4 c = __ldg(C4 + 2 * item), d = __ldg(C4 + 2 * item + 1);
         const float cc[kProjPX] = {c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
         C = 0.f;
 #pragma unroll
-        for (int k = 0; k < kProjPX; ++k) C = (cc[k] >= C) ? cc[k] : C;     // +inf propagates (a written C is never NaN)
+        for (int k = 0; k < kProjPX; ++k)
+            if (k < nvalid) C = (cc[k] >= C) ? cc[k] : C;         // +inf propagates (a written C is never NaN)
     };
     // full rounds: every thread owns one 8-point item and applies the candidates of the tile to it, 8 at a
     // time (the unproven pairs of 8 candidates x 8 points fit one 64-bit mask)
     const int nfull = (nitems / kStride) * kStride;
     for (int item = tid; item < nfull; item += kStride) {
-        float xs[kProjPX], y, C;
-        load_item(item, xs, y, C);
+        float xs[kProjPX], ys[kProjPX], C;
+        load_item(item, xs, ys, C, kProjPX);
         for (int cb = 0; cb < nc; cb += 8) {
             unsigned long long todo = 0;
             const int ce = min(nc, cb + 8);
             for (int c = cb; c < ce; ++c) {
-                const uint32_t unc = splat_points_filter(xs, y, C, hf + kHF * c, fc, masks_s + (uint32_t)(c * words4));
+                const uint32_t unc = splat_points_filter<true>(xs, ys, C, kProjPX, hf + kHF * c, fc,
+                                                               masks_s + (uint32_t)(c * words4));
                 todo |= (unsigned long long)unc << (8 * (c - cb));
             }
             splat_exact_list<kMode>(todo, cb, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy,
@@ -883,11 +801,13 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
         for (int u = tid; u < tail * ngroups; u += kStride) {
             const int grp = u / tail, item = nfull + (u - grp * tail);
             const int cb = grp * g, ce = min(nc, cb + g);
-            float xs[kProjPX], y, C;
-            load_item(item, xs, y, C);
+            float xs[kProjPX], ys[kProjPX], C;
+            const int nvalid = min(kProjPX, npts - item * kProjPX);
+            load_item(item, xs, ys, C, nvalid);
             unsigned long long todo = 0;
             for (int c = cb; c < ce; ++c) {
-                const uint32_t unc = splat_points_filter(xs, y, C, hf + kHF * c, fc, masks_s + (uint32_t)(c * words4));
+                const uint32_t unc = splat_points_filter<false>(xs, ys, C, nvalid, hf + kHF * c, fc,
+                                                                masks_s + (uint32_t)(c * words4));
                 todo |= (unsigned long long)unc << (8 * (c - cb));
             }
             splat_exact_list<kMode>(todo, cb, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy,
@@ -1021,6 +941,59 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
     }
     worker_sync<kStride>(bar);
 
+    if (!rows_only) {
+        // ---- stream the tile out, with popcount + bounding box per candidate ----------
+        // (row, uint4 column) of a thread's elements advance by constants: no division in the loop; the
+        // occupied word columns are collected as a bit mask (pitch <= 32 words)
+        const int p4 = pitch >> 2, n4 = H * p4;
+        const int row0 = tid / p4, col0 = tid - row0 * p4;
+        const int drow = kStride / p4, dcol = kStride - drow * p4;
+        for (int c = 0; c < nc; ++c) {
+            if (gid[c] < 0) continue;
+            const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
+            uint4* d4 = reinterpret_cast<uint4*>(proj_bits + (size_t)(job.cand_begin + gid[c]) * words);
+            MaskStat s = stat_identity();
+            if (pitch <= 32) {
+                uint32_t colmask = 0;
+                int row = row0, col = col0;
+                for (int i = tid; i < n4; i += kStride) {
+                    const uint4 v = s4[i];
+                    d4[i] = v;
+                    if (v.x | v.y | v.z | v.w) {
+                        s.popc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+                        s.rmin = min(s.rmin, row);
+                        s.rmax = max(s.rmax, row);
+                        const uint32_t nz = (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
+                        colmask |= nz << (4 * col);
+                    }
+                    row += drow; col += dcol;
+                    if (col >= p4) { col -= p4; ++row; }
+                }
+                colmask = __reduce_or_sync(0xffffffffu, colmask);
+                if (colmask) { s.cmin = __ffs(colmask) - 1; s.cmax = 31 - __clz(colmask); }
+            } else {
+                for (int i = tid; i < n4; i += kStride) {
+                    const uint4 v = s4[i];
+                    d4[i] = v;
+                    if (v.x | v.y | v.z | v.w) {
+                        const int row = i / p4, cc = (i - row * p4) << 2;
+                        stat_add_word(s, v.x, row, cc);
+                        stat_add_word(s, v.y, row, cc + 1);
+                        stat_add_word(s, v.z, row, cc + 2);
+                        stat_add_word(s, v.w, row, cc + 3);
+                    }
+                }
+            }
+            stat_block_accumulate(red + 5 * c, s);
+        }
+        worker_sync<kStride>(bar);
+        for (int c = tid; c < nc; c += kStride) {
+            if (gid[c] < 0) continue;
+            const size_t g = (size_t)job.cand_begin + gid[c];
+            stat_store(red + 5 * c, proj_popc + g, proj_bbox + 4 * g);
+        }
+        return;
+    }
     // ---- statistics of the tile's masks (popcount + bounding box per candidate), then the write-out ------
     // (row, uint4 column) of a thread's elements advance by constants: no division in the loop; the
     // occupied word columns are collected as a bit mask (pitch <= 32 words)
@@ -1063,21 +1036,22 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
         stat_block_accumulate(red + 5 * c, s);
     }
     worker_sync<kStride>(bar);
-    // A3D_OUT_FULL: every word of every mask.  A3D_OUT_BBOX_ROWS: only rows row_min..row_max of each mask —
-    // the scoring kernels, k_finalize and a3d_gather_masks read nothing else (a door-sized mask occupies an
-    // eighth of the frame's rows; the zeros around it were 85 % of the pass's DRAM writes)
+    // A3D_OUT_BBOX_ROWS: the slot's image in proj_bits is zero outside the rows of proj_bbox[slot] (the
+    // caller's promise on entry, this kernel's on exit), so only the rows of the old box and of the new one
+    // are written — zeros included, from the complete mask in shared memory.  A door-sized mask occupies an
+    // eighth of the frame's rows; the zeros around it were 85 % of the pass's DRAM writes.
     for (int c = 0; c < nc; ++c) {
         if (gid[c] < 0) continue;
+        const size_t g = (size_t)job.cand_begin + gid[c];
         const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
-        uint4* d4 = reinterpret_cast<uint4*>(proj_bits + (size_t)(job.cand_begin + gid[c]) * words);
-        int lo = 0, hi = n4;
-        if (rows_only) {
-            const int rmin = red[5 * c + 1], rmax = red[5 * c + 2];
-            lo = rmax < 0 ? 0 : rmin * p4;
-            hi = rmax < 0 ? 0 : (rmax + 1) * p4;
-        }
+        uint4* d4 = reinterpret_cast<uint4*>(proj_bits + g * words);
+        int rmin = red[5 * c + 1], rmax = red[5 * c + 2];            // new box (0x7fffffff, -1 when empty)
+        const int omin = proj_bbox[4 * g], omax = proj_bbox[4 * g + 1];
+        if (omax >= omin) { rmin = min(rmin, max(omin, 0)); rmax = max(rmax, min(omax, H - 1)); }
+        const int lo = rmax < 0 ? 0 : rmin * p4, hi = rmax < 0 ? 0 : (rmax + 1) * p4;
         for (int i = lo + tid; i < hi; i += kStride) d4[i] = s4[i];
     }
+    worker_sync<kStride>(bar);                                       // the old boxes are read before they are replaced
     for (int c = tid; c < nc; c += kStride) {
         if (gid[c] < 0) continue;
         const size_t g = (size_t)job.cand_begin + gid[c];
@@ -1118,9 +1092,9 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
     ProjSmem sm;
     sm.masks = smem;
     sm.xf = reinterpret_cast<float*>(smem + (size_t)tile_cand * words);
-    sm.hf = sm.xf + tile_cand * 12;                  // 16-byte aligned: read as three float4 per candidate
-    sm.red = reinterpret_cast<int*>(sm.hf + tile_cand * kHF);
-    sm.gid = sm.red + tile_cand * 5;
+    sm.red = reinterpret_cast<int*>(sm.xf + tile_cand * 12);
+    sm.hf = reinterpret_cast<float*>(sm.red + tile_cand * 5);
+    sm.gid = reinterpret_cast<int*>(sm.hf + tile_cand * kHF);
     sm.ctl = ctl;
     project_tile<kFilter, kProjThreads>(cam, job, jid, c0, want, extra, tile_cand, xform, src_bbox, pcd, pcd_count, hom,
                                         proj_bits, proj_popc, proj_bbox, sm, threadIdx.x, 0, true, rows_only);
@@ -1148,9 +1122,9 @@ k_project_p(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, in
     ProjSmem sm;
     sm.masks = base;
     sm.xf = reinterpret_cast<float*>(base + (size_t)tile_cand * words);
-    sm.hf = sm.xf + tile_cand * 12;                  // 16-byte aligned: read as three float4 per candidate
-    sm.red = reinterpret_cast<int*>(sm.hf + tile_cand * kHF);
-    sm.gid = sm.red + tile_cand * 5;
+    sm.red = reinterpret_cast<int*>(sm.xf + tile_cand * 12);
+    sm.hf = reinterpret_cast<float*>(sm.red + tile_cand * 5);
+    sm.gid = reinterpret_cast<int*>(sm.hf + tile_cand * kHF);
     sm.ctl = ctl[g];
     const int bar = 1 + g;
     pdl_wait();                       // the work counter and the point clouds of k_unproject
@@ -2072,25 +2046,6 @@ k_emit(const uint32_t* __restrict__ bits, const int32_t* __restrict__ index, int
     }
 }
 
-// out[i] = bits[index[i]] restricted to the rows of its bounding box (all other rows zero): the defined
-// part of a mask a3d_project wrote in A3D_OUT_BBOX_ROWS mode.  One CTA per mask, uint4 words.
-__global__ void __launch_bounds__(256)
-k_gather_masks(const uint32_t* __restrict__ bits, const int32_t* __restrict__ bbox, const int32_t* __restrict__ index,
-               int H, int pitch, uint32_t* __restrict__ out) {
-    const int64_t i = blockIdx.x;
-    const int64_t m = index ? index[i] : i;
-    const int p4 = pitch >> 2, n4 = H * p4;
-    const uint4* s4 = reinterpret_cast<const uint4*>(bits + m * (int64_t)H * pitch);
-    uint4* d4 = reinterpret_cast<uint4*>(out + i * (int64_t)H * pitch);
-    int lo = 0, hi = n4;
-    if (bbox) {
-        const int rmin = bbox[4 * m], rmax = bbox[4 * m + 1];
-        lo = rmax < rmin ? 0 : rmin * p4;
-        hi = rmax < rmin ? 0 : (rmax + 1) * p4;
-    }
-    for (int k = threadIdx.x; k < n4; k += blockDim.x) d4[k] = (k >= lo && k < hi) ? s4[k] : make_uint4(0, 0, 0, 0);
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -2393,9 +2348,7 @@ static int project_impl(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jo
     const char* env_proj = getenv("A3D_PROJECT_KERNEL");
     const bool force_filter = env_proj && !strcmp(env_proj, "filter"), force_exact = env_proj && !strcmp(env_proj, "exact");
     if (force_filter && !hom_ws) return fail(A3D_EINVAL, "a3d_project: A3D_PROJECT_KERNEL=filter needs hom_ws");
-    // (the filter folds its magic-number bits out of a 32-bit pixel index: H * pitch * 32 <= 2^22)
-    bool filter = !force_exact && cam->H <= 32768 && cam->W <= 32768 && hom_ws &&
-                  (long long)cam->H * pitch_words(cam->W) * 32 <= (1LL << 22);
+    bool filter = !force_exact && cam->H <= 32768 && cam->W <= 32768 && hom_ws;
     if (filter && !force_filter) {
         const int mt = a3d_project_max_tile(cam->H, cam->W);
         const int t = tile_cand > 0 ? tile_cand : (mt > 0 ? mt : 1);
@@ -2417,7 +2370,7 @@ static int project_impl(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jo
     cudaStream_t s = (cudaStream_t)stream;
 
     // 1. source pixels -> compacted point clouds
-    const size_t usmem = (size_t)c.H * sizeof(uint32_t);             // one prefix entry per row of the source box
+    const size_t usmem = (size_t)c.H * c.pitch * sizeof(uint32_t);
     if (usmem > (size_t)device_smem_optin())
         return fail(A3D_ELIMIT, "a3d_project: %dx%d mask does not fit shared memory", c.H, c.W);
     // few jobs: spread each job's phase 2 over several CTAs so all SMs have work
@@ -2623,17 +2576,6 @@ int a3d_emit_masks(const uint32_t* bits, const int32_t* index, int64_t n, int H,
         k_emit<unsigned char><<<grid, 256, 0, s>>>(bits, index, H, W, pitch, (unsigned char*)out);
     else
         return fail(A3D_EINVAL, "a3d_emit_masks: unknown dtype %d", out_dtype);
-    A3D_CUDA_TRY(cudaGetLastError());
-    return A3D_OK;
-}
-
-int a3d_gather_masks(const uint32_t* bits, const int32_t* bbox, const int32_t* index, int64_t n, int H, int W,
-                     uint32_t* out, void* stream) {
-    if (n < 0 || H <= 0 || W <= 0) return fail(A3D_EINVAL, "a3d_gather_masks: bad shape");
-    if (n == 0) return A3D_OK;
-    if (!bits || !out) return fail(A3D_EINVAL, "a3d_gather_masks: null pointer");
-    if (n > 0x7fffffff) return fail(A3D_ELIMIT, "a3d_gather_masks: n too large");
-    k_gather_masks<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>(bits, bbox, index, H, pitch_words(W), out);
     A3D_CUDA_TRY(cudaGetLastError());
     return A3D_OK;
 }

@@ -41,30 +41,9 @@ def camera_struct(cfg: OptConfig) -> _lib.Camera:
     return cam
 
 
-POINTS_PER_ITEM = 8          # k_project item size: k_unproject pads every source row to a multiple of it
-
-
-class SourcePoints(np.ndarray):
-    """Per-mask source pixel counts (what ``MaskPool.source_points`` returns) with the capacities of the
-    row-padded point clouds riding along: ``caps[i]`` = points + 7 per row of the source box, rounded up to
-    32 (``a3d_job_t.pcd_cap``)."""
-    caps = None
-
-    @classmethod
-    def make(cls, points, rows=None):
-        pts = np.asarray(points, dtype=np.int64)
-        # without the box heights: every row holds at least one point
-        rows = pts if rows is None else np.minimum(np.asarray(rows, dtype=np.int64), pts)
-        out = pts.view(cls)
-        out.caps = (pts + (POINTS_PER_ITEM - 1) * rows + 31) & ~31
-        return out
-
-
 def point_caps(src_points) -> np.ndarray:
-    """Point-cloud capacities for ``a3d_job_t.pcd_cap`` from a ``MaskPool.source_points`` array (or, for a
-    plain array of pixel counts, the worst case of one point per row)."""
-    caps = getattr(src_points, "caps", None)
-    return caps if caps is not None else SourcePoints.make(src_points).caps
+    """Point-cloud capacities (``a3d_job_t.pcd_cap``) of the pool's masks: source pixels rounded up to 32."""
+    return (np.asarray(src_points, dtype=np.int64) + 31) & ~31
 
 
 @dataclass
@@ -86,26 +65,19 @@ class MaskPool:
 
     def _resolve(self):
         """First host-side use of the pool: ONE D2H of the count vectors (the host needs the
-        source-pixel counts and the rows of the source boxes to size the point-cloud workspace).  Binary
-        masks (the contract) give identical ``> thresh`` and ``!= 0`` counts and the second bitmap is
-        dropped.  Deferred to here so that the upload and packing stay asynchronous behind the host's
-        geometry work."""
-        def rows_of(bbox):
-            return (bbox[:, 1] - bbox[:, 0] + 1).clamp_(min=0)
+        source-pixel counts to size the point-cloud workspace).  Binary masks (the contract) give
+        identical ``> thresh`` and ``!= 0`` counts and the second bitmap is dropped.  Deferred to here
+        so that the upload and packing stay asynchronous behind the host's geometry work."""
         if self._nz_pending is not None:
             nz, bbox_nz, popc_nz = self._nz_pending
             self._nz_pending = None
-            both = torch.stack((self.popc, popc_nz, rows_of(self.bbox), rows_of(bbox_nz))).cpu().numpy()
+            both = torch.stack((self.popc, popc_nz)).cpu().numpy()
             if not np.array_equal(both[0], both[1]):
                 self.bits_nz, self.bbox_nz, self.popc_nz = nz, bbox_nz, popc_nz
-            pts, rows = both[1].astype(np.int64), both[3].astype(np.int64)
+            self._src_points = both[1].astype(np.int64)
         elif self._src_points is None:
-            t, bb = (self.popc, self.bbox) if self.popc_nz is None else (self.popc_nz, self.bbox_nz)
-            both = torch.stack((t, rows_of(bb))).cpu().numpy()
-            pts, rows = both[0].astype(np.int64), both[1].astype(np.int64)
-        else:
-            return
-        self._src_points = SourcePoints.make(pts, rows)
+            t = self.popc if self.popc_nz is None else self.popc_nz
+            self._src_points = t.cpu().numpy().astype(np.int64)
 
     @property
     def source_points(self) -> np.ndarray:
@@ -405,12 +377,11 @@ class PassResult:
     proj_bbox: torch.Tensor       # (n_cand_total, 4) int32
     inter_tab: torch.Tensor | None
     block: torch.Tensor | None = None     # (4, n_tgt_total) int32: the four best_* rows, contiguous
-    rows_only: bool = False               # proj_bits holds only the rows of each mask's proj_bbox (A3D_OUT_BBOX_ROWS)
+    rows_only: bool = False               # written with A3D_OUT_BBOX_ROWS (proj_bits is fully defined either way)
 
     def masks(self, index: torch.Tensor | None = None) -> torch.Tensor:
-        """Projected masks ``index`` (global candidate slots; None = all) as fully defined packed images,
-        copied out of the pass workspace."""
-        return gather_masks(self.proj_bits, self.proj_bbox if self.rows_only else None, index)
+        """Projected masks ``index`` (global candidate slots; None = all), copied out of the pass workspace."""
+        return self.proj_bits.clone() if index is None else self.proj_bits.index_select(0, index.long())
 
 
 class DeviceBatch:
@@ -509,6 +480,24 @@ class Workspace:
             self._bufs[name] = buf
         return buf[:n].view(*shape)
 
+    def get_proj(self, nc: int, H: int, pitch: int):
+        """(proj_bits, proj_popc, proj_bbox) for ``nc`` candidate slots, kept in the state A3D_OUT_BBOX_ROWS
+        asks for: masks zero outside the rows of their boxes.  A fresh (or re-shaped) pair is all-zero masks
+        with empty boxes; afterwards every pass of this workspace maintains the invariant slot by slot."""
+        key = (H, pitch)
+        cur = self._bufs.get("_proj")
+        if cur is None or cur[0] != key or cur[1].shape[0] < nc:
+            cap = max(nc, 1) if cur is None or cur[0] != key else max(nc, 2 * cur[1].shape[0])
+            self._bufs.pop("_proj", None)                # release the old pair before allocating the new one
+            cur = None
+            bits = torch.zeros(cap, H, pitch, dtype=torch.int32, device=self.device)
+            bbox = torch.zeros(cap, 4, dtype=torch.int32, device=self.device)
+            bbox[:, 1] = -1
+            bbox[:, 3] = -1
+            popc = torch.zeros(cap, dtype=torch.int32, device=self.device)
+            cur = self._bufs["_proj"] = (key, bits, popc, bbox)
+        return cur[1][:nc], cur[2][:nc], cur[3][:nc]
+
 
 _cam_cache: dict = {}
 _tile_cache: dict = {}
@@ -550,25 +539,10 @@ def choose_tile(cfg: OptConfig, n_cand_total: int, n_jobs: int = 1, sm_count: in
 
 
 def default_out_mode() -> int:
-    """Projected masks are written as the rows of their bounding boxes only (everything the scoring reads);
-    ``A3D_PROJ_OUT=full`` writes every word, as ``a3d_project`` called directly with A3D_OUT_FULL does."""
+    """The engine keeps the projected-mask buffers of a ``Workspace`` between passes, zero outside each slot's
+    box, so a pass writes only the rows of the old and the new box of every slot (A3D_OUT_BBOX_ROWS);
+    ``A3D_PROJ_OUT=full`` writes every word of every mask instead."""
     return _lib.OUT_FULL if os.environ.get("A3D_PROJ_OUT") == "full" else _lib.OUT_BBOX_ROWS
-
-
-def gather_masks(bits: torch.Tensor, bbox: torch.Tensor | None, index: torch.Tensor | None) -> torch.Tensor:
-    """``bits[index]`` (n, H, pitch) with the rows outside each mask's ``bbox`` zeroed (a3d_gather_masks)."""
-    lib = _lib.load()
-    _require_cuda(bits, "bits")
-    H, pitch = int(bits.shape[1]), int(bits.shape[2])
-    n = int(index.numel()) if index is not None else int(bits.shape[0])
-    out = torch.empty(n, H, pitch, dtype=torch.int32, device=bits.device)
-    if index is not None:
-        index = index.to(torch.int32).contiguous()
-    with torch.cuda.device(bits.device):
-        _lib.check(lib.a3d_gather_masks(bits.data_ptr(), bbox.data_ptr() if bbox is not None else None,
-                                        index.data_ptr() if index is not None else None, n, H, pitch * 32,
-                                        out.data_ptr(), _stream_ptr()), "a3d_gather_masks")
-    return out
 
 
 def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace | None = None,
@@ -585,9 +559,7 @@ def run_pass(cfg: OptConfig, pool: MaskPool, dbatch: DeviceBatch, ws: Workspace 
     pitch = _lib.pitch_words(W)
     nc, nt = dbatch.n_cand_total, dbatch.n_tgt_total
     with torch.cuda.device(dev):
-        proj_bits = ws.get("proj_bits", (nc, H, pitch), torch.int32)
-        proj_popc = ws.get("proj_popc", (nc,), torch.int32)
-        proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
+        proj_bits, proj_popc, proj_bbox = ws.get_proj(nc, H, pitch)
         pcd_ws = ws.get("pcd_ws", (max(_lib.PCD_PLANES * dbatch.pcd_total, 32),), torch.float32)
         pcd_count = ws.get("pcd_count", (dbatch.n_jobs + 1,), torch.int32)
         hom_ws = ws.get("hom_ws", (max(nc, 1), _lib.HOM_FLOATS), torch.float32)

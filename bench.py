@@ -458,9 +458,7 @@ def _run_split(engine, inp, ws, evs):
     H, W = cfg.height, cfg.width
     pitch = _lib.pitch_words(W)
     nc, nt = db.n_cand_total, db.n_tgt_total
-    proj_bits = ws.get("proj_bits", (nc, H, pitch), torch.int32)
-    proj_popc = ws.get("proj_popc", (nc,), torch.int32)
-    proj_bbox = ws.get("proj_bbox", (nc, 4), torch.int32)
+    proj_bits, proj_popc, proj_bbox = ws.get_proj(nc, H, pitch)
     pcd_ws = ws.get("pcd_ws", (max(_lib.PCD_PLANES * db.pcd_total, 32),), torch.float32)
     pcd_count = ws.get("pcd_count", (db.n_jobs + 1,), torch.int32)
     hom_ws = ws.get("hom_ws", (max(nc, 1), _lib.HOM_FLOATS), torch.float32)

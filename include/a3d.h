@@ -82,9 +82,7 @@ typedef struct {
     float   offset;          /* plane offset                      (opt_utils.py:411)    */
     float   pivot[3];        /* fp32 axis point a = Translate(verts_axis_3d[0]) (:420)  */
     int32_t pcd_cap;         /* capacity (points, multiple of 32) of this job's slice of
-                                the point-cloud workspace; >= popcount of the source
-                                + 7 per row of its bounding box (every source row is
-                                padded to whole 8-point items, a3d_project)             */
+                                the point-cloud workspace; >= popcount of the source    */
     int64_t tab_begin;       /* first element of this job's [n_tgt][n_cand] table       */
     int64_t pcd_begin;       /* first point of this job's slice (multiple of 32)        */
 } a3d_job_t;                 /* 72 bytes */
@@ -138,7 +136,7 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W,
  *   xform      [n_cand_total][12] fp32: rows 0-2 of R (row-vector convention,
  *              p' = p*R), then t
  *   pcd_ws     workspace, A3D_PCD_PLANES * sum(pcd_cap) floats (planes of pcd_cap floats per job slice)
- *   pcd_count  workspace, [n_jobs + 1] int32 (points actually produced per job, pad copies included; the last entry is the
+ *   pcd_count  workspace, [n_jobs + 1] int32 (points actually produced per job; the last entry is the
  *              work counter of the persistent projection kernel)
  *   hom_ws     workspace, [n_cand_total][A3D_HOM_FLOATS] floats: per candidate the plane-induced
  *              homography source pixel -> projected pixel and its error bound, from which the
@@ -154,11 +152,13 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W,
  *              grid of about one wave are the case for it (see engine.plan_tiles).
  *   proj_bits  [n_cand_total][H][pitch]; proj_popc [n_cand_total];
  *   proj_bbox  [n_cand_total][4]
- *   out_mode   A3D_OUT_FULL: every word of every projected mask is written.  A3D_OUT_BBOX_ROWS: only the
- *              rows row_min..row_max of each mask (whole rows); the other rows of proj_bits are left
- *              untouched.  a3d_score reads nothing outside the boxes; a3d_gather_masks copies such a
- *              mask out with the other rows zeroed.  (The zeros around a door-sized mask are 85 % of the
- *              projection's DRAM writes.)                                          */
+ *   out_mode   A3D_OUT_FULL: every word of every projected mask is written.
+ *              A3D_OUT_BBOX_ROWS: for callers that keep proj_bits / proj_bbox between calls.  On entry the
+ *              image of every slot must be zero outside the rows row_min..row_max of proj_bbox[slot] — true
+ *              for a pair initialised to {proj_bits = 0, proj_bbox = {0,-1,0,-1}} and after every call in
+ *              this mode; the call then writes only the rows of the slot's old box and of its new one
+ *              (zeros included) and leaves the same invariant.  proj_bits is fully defined either way.
+ *              (The zeros around a door-sized mask are 85 % of the projection's DRAM writes.)         */
 int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
                 int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,
                 const float* xform, float* pcd_ws, int32_t* pcd_count, float* hom_ws,
@@ -198,14 +198,6 @@ int a3d_pass(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max
              uint64_t* key_ws, int32_t* inter_tab,
              int32_t* best_cand, int32_t* best_inter, int32_t* best_union, float* best_iou,
              int out_mode, void* stream);
-
-/* Copies selected packed masks: out[i] = bits[index[i]] (index NULL = identity), keeping only the rows
- * of the mask's bounding box when bbox ([..][4], a3d_project's proj_bbox) is given and zeroing the
- * others — the way to take masks out of a proj_bits array written in A3D_OUT_BBOX_ROWS mode
- * (the winning masks of the final assignment, opt_utils.py:614, 906).
- *   out  [n][H][pitch]                                                           */
-int a3d_gather_masks(const uint32_t* bits, const int32_t* bbox, const int32_t* index, int64_t n, int H, int W,
-                     uint32_t* out, void* stream);
 
 /* (a11) materialise selected packed masks as dense images: out[i] =
  * unpack(bits[index[i]]) as A3D_F32 (0.0/1.0) or A3D_U8 (0/1).  Replaces

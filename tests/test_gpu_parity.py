@@ -22,8 +22,7 @@ def projection_kernel(request, monkeypatch):
     """Every test of this module runs with both projection kernels (the library's default picks one from
     the grid size): the reference chain for every point, and the homography filter with proven truncation."""
     monkeypatch.setenv("A3D_PROJECT_KERNEL", request.param)
-    # fresh pass buffers hold 0xAB bytes: projected masks are written as the rows of their boxes only
-    # (A3D_OUT_BBOX_ROWS), and no kernel may read a word outside them
+    # fresh pass buffers hold 0xAB bytes: nothing may depend on what a workspace buffer held before
     monkeypatch.setenv("A3D_WS_POISON", "1")
     return request.param
 
@@ -677,30 +676,33 @@ def test_filter_kernel_adversarial_geometry(seed, monkeypatch):
 
 
 def test_bbox_rows_output_equals_full_output(monkeypatch):
-    """A3D_OUT_BBOX_ROWS (the pass default: only the rows of each projected mask's box are written) against
-    A3D_OUT_FULL: identical statistics, scores, and — through a3d_gather_masks — identical masks; outside the
-    boxes the rows-only buffer still holds the poison bytes it was allocated with."""
+    """A3D_OUT_BBOX_ROWS (the engine's default: a workspace keeps its projected-mask buffers zero outside each
+    slot's box, and a pass writes only the rows of the slot's old and new box) against A3D_OUT_FULL on fresh
+    buffers: identical masks — every word — statistics and scores, also when the same workspace serves passes
+    of different geometry, of fewer and then of more candidate slots one after the other."""
     from articulation3d_b200 import workloads
-    wl = workloads.Workload("probe", "3 videos x 3 tracks x 14 frames, 40 candidates", 3, 3, 14, 40)
-    inp = workloads.build_pass(wl, 77, DEV)
-    full = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, engine.Workspace(DEV), want_table=True, out_mode=_lib.OUT_FULL)
-    rows = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, engine.Workspace(DEV), want_table=True,
-                           out_mode=_lib.OUT_BBOX_ROWS)
-    torch.cuda.synchronize()
-    assert rows.rows_only and not full.rows_only
-    for name in ("proj_popc", "proj_bbox", "inter_tab", "best_cand", "best_inter", "best_union"):
-        assert torch.equal(getattr(full, name), getattr(rows, name)), name
-    assert torch.equal(full.best_iou.view(torch.int32), rows.best_iou.view(torch.int32))
-    assert torch.equal(full.proj_bits, rows.masks()) and torch.equal(full.proj_bits, full.masks())
-    idx = torch.tensor([5, 0, 17, 5], device=DEV)
-    assert torch.equal(rows.masks(idx), full.proj_bits[idx])
-    raw = rows.proj_bits.cpu().numpy().view(np.uint32)
-    bb = rows.proj_bbox.cpu().numpy()
-    k = int(np.argmax(bb[:, 1] - bb[:, 0]))                      # a non-empty mask
-    assert bb[k, 0] > 0 or bb[k, 1] < inp.cfg.height - 1
-    outside = np.ones(inp.cfg.height, bool)
-    outside[bb[k, 0]: bb[k, 1] + 1] = False
-    assert (raw[k][outside] == 0xABABABAB).all()
+    ws = engine.Workspace(DEV)
+    shapes = [(3, 3, 14, 40, 77, _lib.MODE_SEQ), (3, 3, 14, 40, 78, _lib.MODE_COMPOSED), (1, 2, 12, 16, 79, _lib.MODE_SEQ),
+              (4, 3, 10, 56, 80, _lib.MODE_TRANSLATE), (3, 3, 14, 40, 77, _lib.MODE_SEQ)]
+    for videos, tracks, frames, cand, seed, mode in shapes:
+        wl = workloads.Workload("probe", "probe", videos, tracks, frames, cand)
+        inp = workloads.build_pass(wl, seed, DEV, mode=mode)
+        full = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, engine.Workspace(DEV), want_table=True, out_mode=_lib.OUT_FULL)
+        rows = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, ws, want_table=True, out_mode=_lib.OUT_BBOX_ROWS)
+        torch.cuda.synchronize()
+        assert rows.rows_only and not full.rows_only
+        for name in ("proj_bits", "proj_popc", "proj_bbox", "inter_tab", "best_cand", "best_inter", "best_union"):
+            assert torch.equal(getattr(full, name), getattr(rows, name)), (name, seed)
+        assert torch.equal(full.best_iou.view(torch.int32), rows.best_iou.view(torch.int32))
+        assert int(full.proj_popc.sum()) > 0
+    # slots beyond the last pass still hold masks that are zero outside their boxes
+    key, bits, popc, bbox = ws._bufs["_proj"]
+    b, bb = bits.cpu().numpy(), bbox.cpu().numpy()
+    for k in range(len(bb)):
+        inside = np.zeros(b.shape[1], bool)
+        if bb[k, 1] >= bb[k, 0]:
+            inside[bb[k, 0]: bb[k, 1] + 1] = True
+        assert not b[k][~inside].any(), k
 
 
 @pytest.mark.parametrize("name,videos,tracks,frames,cand,W,H,mode", [

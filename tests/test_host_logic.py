@@ -126,21 +126,15 @@ def test_build_batch_layout():
     xf = [np.zeros((3, 12), np.float32), np.ones((5, 12), np.float32)]
     pts = np.zeros(10, np.int64)
     pts[7], pts[9] = 33, 64
-    rows = np.zeros(10, np.int64)
-    rows[7], rows[9] = 3, 8
-    # capacities of the row-padded clouds: points + 7 per row of the source box, rounded up to 32
-    assert engine.point_caps(pts)[[7, 9]].tolist() == [288, 512]              # no box heights: one point per row
-    pts = engine.SourcePoints.make(pts, rows)
-    assert pts.caps[[7, 9]].tolist() == [64, 128] and pts[7] == 33
     b = engine.build_batch([7, 9], [0, 2], [np.arange(3), np.ones(3)], [1.5, 2.5],
                            [np.zeros(3), np.ones(3)], xf, [[1, 2], [3, 4, 5, 6]], pts)
     assert b.jobs.dtype.itemsize == 72 and b.jobs.tobytes().__len__() == 144
-    assert list(b.jobs["pcd_cap"]) == [64, 128] and list(b.jobs["pcd_begin"]) == [0, 64]
+    assert list(b.jobs["pcd_cap"]) == [64, 64] and list(b.jobs["pcd_begin"]) == [0, 64]
     assert list(b.jobs["cand_begin"]) == [0, 3] and list(b.jobs["tgt_begin"]) == [0, 2]
     assert list(b.jobs["tab_begin"]) == [0, 6] and b.units == 3 * 2 + 5 * 4
     assert b.xform.shape == (8, 12) and b.tgt_index.tolist() == [1, 2, 3, 4, 5, 6]
     raw = np.frombuffer(b.jobs.tobytes(), dtype=np.int32).reshape(2, 18)
-    assert raw[1, 0] == 9 and raw[1, 1] == 2 and raw[1, 3] == 5 and raw[1, 5] == 4 and raw[1, 13] == 128
+    assert raw[1, 0] == 9 and raw[1, 1] == 2 and raw[1, 3] == 5 and raw[1, 5] == 4 and raw[1, 13] == 64
     assert np.frombuffer(b.jobs.tobytes(), dtype=np.float32).reshape(2, 18)[1, 9] == 2.5
     assert np.frombuffer(b.jobs.tobytes(), dtype=np.int64).reshape(2, 9)[1, 8] == 64
 
