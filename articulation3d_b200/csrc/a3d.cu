@@ -653,6 +653,9 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
 // [2] of those, pairs of exact-only candidates, [3] warp-iterations of the exact loop
 __device__ unsigned long long g_filter_stats[4];
 #endif
+#ifndef A3D_EXP
+#define A3D_EXP 0
+#endif
 constexpr float kMagic = 12582912.f;                 // 1.5 * 2^23: x + kMagic holds rint(x) in its low mantissa bits
 // Phase A of one (item, candidate): the cheap pixel of up to 8 points; proven ones are splatted, the
 // others come back as a bit mask (bit k = point k needs the exact chain).
@@ -699,10 +702,21 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
         const float neg_thr = fmaf(ce, fabsf(r), fc.c0h);         // eps - 0.5
         // proven only if both fractional parts keep more than eps from the integer boundaries (a NaN or
         // infinite eps fails the comparison)
+#if A3D_EXP
+        // dx, dy are finite (sx, sy lie in [0, 1]), so the larger magnitude decides both tests with one compare;
+        // the proven bit is a predicated OR instead of a select + add
+        const float dm = fmaxf(fabsf(dx), fabsf(dy));
+        uint32_t one;
+        asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t@p or.b32 %1, %1, %4;\n\t}"
+            : "=r"(one), "+r"(proven) : "f"(dm), "f"(-neg_thr), "r"(1u << k));
+        const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
+        red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
+#else
         const uint32_t one = (fabsf(dx) <= -neg_thr && fabsf(dy) <= -neg_thr) ? 1u : 0u;
         const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
         red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
         proven += one << k;
+#endif
     }
     return ~proven & (kFull ? 0xffu : ((1u << nvalid) - 1u));
 }
@@ -941,75 +955,34 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
     }
     worker_sync<kStride>(bar);
 
-    if (!rows_only) {
-        // ---- stream the tile out, with popcount + bounding box per candidate ----------
-        // (row, uint4 column) of a thread's elements advance by constants: no division in the loop; the
-        // occupied word columns are collected as a bit mask (pitch <= 32 words)
-        const int p4 = pitch >> 2, n4 = H * p4;
-        const int row0 = tid / p4, col0 = tid - row0 * p4;
-        const int drow = kStride / p4, dcol = kStride - drow * p4;
-        for (int c = 0; c < nc; ++c) {
-            if (gid[c] < 0) continue;
-            const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
-            uint4* d4 = reinterpret_cast<uint4*>(proj_bits + (size_t)(job.cand_begin + gid[c]) * words);
-            MaskStat s = stat_identity();
-            if (pitch <= 32) {
-                uint32_t colmask = 0;
-                int row = row0, col = col0;
-                for (int i = tid; i < n4; i += kStride) {
-                    const uint4 v = s4[i];
-                    d4[i] = v;
-                    if (v.x | v.y | v.z | v.w) {
-                        s.popc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-                        s.rmin = min(s.rmin, row);
-                        s.rmax = max(s.rmax, row);
-                        const uint32_t nz = (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
-                        colmask |= nz << (4 * col);
-                    }
-                    row += drow; col += dcol;
-                    if (col >= p4) { col -= p4; ++row; }
-                }
-                colmask = __reduce_or_sync(0xffffffffu, colmask);
-                if (colmask) { s.cmin = __ffs(colmask) - 1; s.cmax = 31 - __clz(colmask); }
-            } else {
-                for (int i = tid; i < n4; i += kStride) {
-                    const uint4 v = s4[i];
-                    d4[i] = v;
-                    if (v.x | v.y | v.z | v.w) {
-                        const int row = i / p4, cc = (i - row * p4) << 2;
-                        stat_add_word(s, v.x, row, cc);
-                        stat_add_word(s, v.y, row, cc + 1);
-                        stat_add_word(s, v.z, row, cc + 2);
-                        stat_add_word(s, v.w, row, cc + 3);
-                    }
-                }
-            }
-            stat_block_accumulate(red + 5 * c, s);
-        }
-        worker_sync<kStride>(bar);
-        for (int c = tid; c < nc; c += kStride) {
-            if (gid[c] < 0) continue;
-            const size_t g = (size_t)job.cand_begin + gid[c];
-            stat_store(red + 5 * c, proj_popc + g, proj_bbox + 4 * g);
-        }
-        return;
-    }
-    // ---- statistics of the tile's masks (popcount + bounding box per candidate), then the write-out ------
+    // ---- stream the tile out, with popcount + bounding box per candidate ----------
     // (row, uint4 column) of a thread's elements advance by constants: no division in the loop; the
-    // occupied word columns are collected as a bit mask (pitch <= 32 words)
+    // occupied word columns are collected as a bit mask (pitch <= 32 words).
+    // A3D_OUT_FULL: every word is written.  A3D_OUT_BBOX_ROWS: the slot's image in proj_bits is zero outside
+    // the rows of proj_bbox[slot] (the caller's promise on entry, this kernel's on exit), so a 16-byte piece
+    // is written only if it lies in a row of the slot's OLD box (whatever it holds now, zeros included) or is
+    // non-zero — one pass, no box needed in advance.  A door-sized mask occupies an eighth of the frame's rows;
+    // the zeros around it were 85 % of the pass's DRAM writes.
     const int p4 = pitch >> 2, n4 = H * p4;
     const int row0 = tid / p4, col0 = tid - row0 * p4;
     const int drow = kStride / p4, dcol = kStride - drow * p4;
     for (int c = 0; c < nc; ++c) {
         if (gid[c] < 0) continue;
+        const size_t g = (size_t)job.cand_begin + gid[c];
         const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
+        uint4* d4 = reinterpret_cast<uint4*>(proj_bits + g * words);
+        // rows that are always written: all of them, or those of the old box
+        int wlo = 0, whi = H - 1;
+        if (rows_only) { wlo = proj_bbox[4 * g]; whi = proj_bbox[4 * g + 1]; }
         MaskStat s = stat_identity();
         if (pitch <= 32) {
             uint32_t colmask = 0;
             int row = row0, col = col0;
             for (int i = tid; i < n4; i += kStride) {
                 const uint4 v = s4[i];
-                if (v.x | v.y | v.z | v.w) {
+                const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
+                if (nzv || (row >= wlo && row <= whi)) d4[i] = v;
+                if (nzv) {
                     s.popc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
                     s.rmin = min(s.rmin, row);
                     s.rmax = max(s.rmax, row);
@@ -1024,8 +997,11 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
         } else {
             for (int i = tid; i < n4; i += kStride) {
                 const uint4 v = s4[i];
-                if (v.x | v.y | v.z | v.w) {
-                    const int row = i / p4, cc = (i - row * p4) << 2;
+                const int row = i / p4;
+                const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
+                if (nzv || (row >= wlo && row <= whi)) d4[i] = v;
+                if (nzv) {
+                    const int cc = (i - row * p4) << 2;
                     stat_add_word(s, v.x, row, cc);
                     stat_add_word(s, v.y, row, cc + 1);
                     stat_add_word(s, v.z, row, cc + 2);
@@ -1035,23 +1011,7 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
         }
         stat_block_accumulate(red + 5 * c, s);
     }
-    worker_sync<kStride>(bar);
-    // A3D_OUT_BBOX_ROWS: the slot's image in proj_bits is zero outside the rows of proj_bbox[slot] (the
-    // caller's promise on entry, this kernel's on exit), so only the rows of the old box and of the new one
-    // are written — zeros included, from the complete mask in shared memory.  A door-sized mask occupies an
-    // eighth of the frame's rows; the zeros around it were 85 % of the pass's DRAM writes.
-    for (int c = 0; c < nc; ++c) {
-        if (gid[c] < 0) continue;
-        const size_t g = (size_t)job.cand_begin + gid[c];
-        const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
-        uint4* d4 = reinterpret_cast<uint4*>(proj_bits + g * words);
-        int rmin = red[5 * c + 1], rmax = red[5 * c + 2];            // new box (0x7fffffff, -1 when empty)
-        const int omin = proj_bbox[4 * g], omax = proj_bbox[4 * g + 1];
-        if (omax >= omin) { rmin = min(rmin, max(omin, 0)); rmax = max(rmax, min(omax, H - 1)); }
-        const int lo = rmax < 0 ? 0 : rmin * p4, hi = rmax < 0 ? 0 : (rmax + 1) * p4;
-        for (int i = lo + tid; i < hi; i += kStride) d4[i] = s4[i];
-    }
-    worker_sync<kStride>(bar);                                       // the old boxes are read before they are replaced
+    worker_sync<kStride>(bar);                     // (the old boxes are all read before any is replaced)
     for (int c = tid; c < nc; c += kStride) {
         if (gid[c] < 0) continue;
         const size_t g = (size_t)job.cand_begin + gid[c];

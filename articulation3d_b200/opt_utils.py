@@ -527,16 +527,34 @@ def _write_back(preds, planes, cfg: OptConfig, kind: str):
 # ---------------------------------------------------------------------------
 _UPLOAD_CHUNK_BYTES = 1 << 29      # dense masks staged on the device per pack call
 _PROJ_BUDGET_BYTES = 6 << 30       # projected-mask workspace of one device pass
+_uploader = None                   # ONE helper thread: uploads of successive sessions queue up instead of sharing PCIe
+_upload_streams: dict = {}         # device -> the stream all uploads of that device run on
+
+
+def _upload_executor():
+    global _uploader
+    if _uploader is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _uploader = ThreadPoolExecutor(max_workers=1, thread_name_prefix="a3d-upload")
+    return _uploader
+
+
+def _upload_stream(device) -> "torch.cuda.Stream":
+    key = str(device)
+    st = _upload_streams.get(key)
+    if st is None:
+        st = _upload_streams[key] = torch.cuda.Stream(device=device)
+    return st
 
 
 class _Session:
     """Packed masks of every tracked box of a set of videos, resident on one GPU."""
 
-    def __init__(self, videos, cfg: OptConfig, device):
+    def __init__(self, videos, cfg: OptConfig, device, ws=None, staging=None):
         self.cfg = cfg
         self.device = torch.device(device)
-        self.ws = engine.Workspace(self.device)
-        self.staging = engine.Staging(self.device)
+        self.ws = ws if ws is not None else engine.Workspace(self.device)        # shared by the sessions of a pipeline
+        self.staging = staging if staging is not None else engine.Staging(self.device)
         self.videos = videos
         self.pool_of = []                   # per video: {(frame, box_id): pool index}
         self._rows = {}
@@ -565,7 +583,7 @@ class _Session:
         self.h2d_bytes = 0
         self.n_masks = n
         self._pool = None
-        self._uploader = self._upload_error = self._upload_done = None
+        self._upload_future = self._upload_done = None
         if n == 0:
             return
         if rles:
@@ -577,34 +595,33 @@ class _Session:
         self.h2d_bytes += sum(c.numel() * c.element_size() for c in chunks if not c.is_cuda)
         # The upload runs on its own stream from a helper thread, so the host-side preparation of the first
         # pass (source geometry, candidate transforms) and — with several videos — the device passes of the
-        # previous video overlap the H2D copies, also when the driver makes the copy calls block.
-        self._upload_stream = torch.cuda.Stream(device=self.device)
-        self._uploader = threading.Thread(target=self._upload_worker, args=(chunks, n), daemon=True)
-        self._uploader.start()
+        # previous video overlap the H2D copies, also when the driver makes the copy calls block.  One thread
+        # and one stream for all sessions: the uploads of a pipeline of videos run one after the other at full
+        # PCIe rate (two at once would both finish late).
+        self._upload_stream = _upload_stream(self.device)
+        self._upload_future = _upload_executor().submit(self._upload_worker, chunks, n)
 
     @property
     def pool(self):
         """The packed mask pool; the first access waits for the upload thread and orders the current
         stream after the upload stream."""
-        if self._uploader is not None:
-            self._uploader.join()
-            self._uploader = None
-            if self._upload_error is not None:
-                raise self._upload_error
+        if self._upload_future is not None:
+            fut, self._upload_future = self._upload_future, None
+            fut.result()                                   # re-raises what the upload thread raised
             torch.cuda.current_stream(self.device).wait_event(self._upload_done)
             for t in (self._pool.bits, self._pool.popc, self._pool.bbox) + tuple(self._pool._nz_pending or ()):
                 t.record_stream(torch.cuda.current_stream(self.device))
         return self._pool
 
     def _upload_worker(self, chunks, n):
-        try:
-            torch.cuda.set_device(self.device)
-            with torch.cuda.stream(self._upload_stream):
-                self._pool = self._upload(chunks, n)
-                self._upload_done = torch.cuda.Event()
-                self._upload_done.record()
-        except BaseException as e:                     # re-raised by the thread that asks for the pool
-            self._upload_error = e
+        torch.cuda.set_device(self.device)
+        with torch.cuda.stream(self._upload_stream):
+            self._pool = self._upload(chunks, n)
+            self._upload_done = torch.cuda.Event()
+            self._upload_done.record()
+            # the next session's copies must not start before this one's are through (same stream: they do not),
+            # and this thread returns only when they are, so that `pool` never waits on a half-filled stream
+            self._upload_done.synchronize()
 
     def _upload(self, chunks, n) -> engine.MaskPool:
         """Dense per-frame masks -> packed pool.  The frames are copied (asynchronously when the host
@@ -1002,12 +1019,17 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
         # all-sources schedule, one session per video, software-pipelined: while video v is optimised
         # (table pass, host replay, final pass, write-back), the helper thread of session v+1 uploads and
         # packs the next video's masks on its own stream
+        ws, staging = engine.Workspace(device), engine.Staging(device)
+
         def open_session(v):
             p, pl = videos[v]
-            return _Session([(p, [pl['trans'], pl['rot']])], cfg, device)
-        nxt = open_session(0)
+            return _Session([(p, [pl['trans'], pl['rot']])], cfg, device, ws=ws, staging=staging)
+        ahead = 2                                   # sessions opened (their uploads queued) ahead of the one optimised
+        opened = [open_session(v) for v in range(min(ahead, len(videos)))]
         for v, ((p, pl), seed) in enumerate(zip(videos, seeds)):
-            session, nxt = nxt, (open_session(v + 1) if v + 1 < len(videos) else None)
+            session = opened.pop(0)
+            if v + ahead < len(videos):
+                opened.append(open_session(v + ahead))
             stats.h2d_bytes += session.h2d_bytes
             _run_lists(session, [_video_stages(p, pl, cfg, _global_random.Random(seed), outs[v])], cfg, stats,
                        use_tables=True)

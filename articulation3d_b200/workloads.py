@@ -26,6 +26,7 @@ class Workload:
     cand: int            # candidate grid of the scoring pass
     width: int = 640
     height: int = 480
+    mode: int = _lib.MODE_SEQ     # transform of the pass: three-step rotations (cluster phase), composed, or translations
 
     def cfg(self) -> OptConfig:
         final = max(1, int(round(self.cand * 2 / 3)))
@@ -59,8 +60,14 @@ WORKLOADS = {
     "c3": Workload("c3", "batched opt_arti: 256 videos x 8 tracks x 120 frames, 180-angle grid",
                    256, 8, 120, 180),
     # configs[3] per-GPU shard: 1024x768, 720 rotation candidates (translation candidates are a second pass)
-    "c4_shard": Workload("c4_shard", "dense sweep shard: 8 videos x 8 tracks x 120 frames, 720-angle grid, 1024x768",
+    "c4_shard": Workload("c4_shard", "dense sweep shard (1 of 8 GPUs): 8 videos x 8 tracks x 120 frames, 720-angle grid, 1024x768",
                          8, 8, 120, 720, 1024, 768),
+    # ... and its translation candidates: the same tracks against arange(-1, 1, 0.1) along the axis direction
+    "c4_trans": Workload("c4_trans", "dense sweep shard, translation candidates: 8 videos x 8 tracks x 120 frames, "
+                         "20 offsets, 1024x768", 8, 8, 120, 20, 1024, 768, _lib.MODE_TRANSLATE),
+    # configs[3] whole: 64 videos (512 tracks) on one GPU
+    "c4": Workload("c4", "dense sweep: 64 videos x 8 tracks x 120 frames, 720-angle grid, 1024x768",
+                   64, 8, 120, 720, 1024, 768),
 }
 
 
@@ -74,13 +81,14 @@ class PassInputs:
 
 
 def build_pass(wl: Workload, seed0: int, device, source_frame: int | None = None,
-               progress=None, mode: int = _lib.MODE_SEQ, video_ids=None) -> PassInputs:
+               progress=None, mode: int | None = None, video_ids=None) -> PassInputs:
     """Render every track of ``wl`` on the device, pack the masks, and describe one pass with the
     middle frame of each track as source: cluster-phase three-step rotations (``MODE_SEQ``, the
     default), final-phase composed rotations or translations along the axis direction.
     ``video_ids``: the videos of the workload this device holds (default all); video v is always the
     scene of seed ``seed0 + v``, so shards of any world size add up to the same workload."""
     cfg = wl.cfg()
+    mode = wl.mode if mode is None else mode
     T = wl.frames
     s = T // 2 if source_frame is None else source_frame
     bits, srcs, normals, offsets, pivots, dirs = [], [], [], [], [], []

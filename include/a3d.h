@@ -156,8 +156,9 @@ int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W,
  *              A3D_OUT_BBOX_ROWS: for callers that keep proj_bits / proj_bbox between calls.  On entry the
  *              image of every slot must be zero outside the rows row_min..row_max of proj_bbox[slot] — true
  *              for a pair initialised to {proj_bits = 0, proj_bbox = {0,-1,0,-1}} and after every call in
- *              this mode; the call then writes only the rows of the slot's old box and of its new one
- *              (zeros included) and leaves the same invariant.  proj_bits is fully defined either way.
+ *              this mode; the call then writes only the 16-byte pieces that lie in a row of the slot's old
+ *              box (zeros included) or are non-zero, and leaves the same invariant.  proj_bits is fully
+ *              defined either way.
  *              (The zeros around a door-sized mask are 85 % of the projection's DRAM writes.)         */
 int a3d_project(const a3d_camera_t* cam, const a3d_job_t* jobs, int n_jobs, int max_cand,
                 int tile_cand, const uint32_t* src_bits, const int32_t* src_bbox,

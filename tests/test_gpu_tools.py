@@ -47,7 +47,8 @@ def test_inference_tool_c1_shape_matches_oracle(tmp_path):
         np.testing.assert_allclose(r["pred_tran_axis"].numpy(), w.pred_tran_axis.numpy(), rtol=1e-4, atol=1e-7)
     for k in (0, 29):                                                      # key frames clipped to the clip
         assert os.path.getsize(os.path.join(out, f"frame{k}.obj")) > 0
-    assert any(f.endswith(".mtl") for f in os.listdir(out))
+    for k in (0, 29):                                                      # the textured export, one folder per frame
+        assert os.path.getsize(os.path.join(out, "frame_{:0>4}".format(k), "arti_pred.mtl")) > 0
 
 
 @pytest.mark.parametrize("frames", [90, 300])

@@ -1,0 +1,20 @@
+#!/bin/bash
+# GPU call 4: parity suite on the single-pass rows-mode write-out + serialized uploads, bench, A/B of the experimental point body
+cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.txt
+for wl in c3_mini; do
+  (cd _ab/old && AB_ITERS=10 timeout 300 python tools/project_ab.py $wl) 2>&1 | tail -2
+  for om in 0 1; do
+    echo "new out_mode=$om"; AB_ITERS=10 AB_OUT_MODE=$om timeout 300 python tools/project_ab.py $wl 2>&1 | tail -2
+    echo "exp out_mode=$om"; A3D_LIB=$PWD/tools/_build/liba3d_exp.so AB_ITERS=10 AB_OUT_MODE=$om timeout 300 python tools/project_ab.py $wl 2>&1 | tail -2
+  done
+done > gpurun_out/r2_ab4.txt 2>&1; cat gpurun_out/r2_ab4.txt
+timeout 600 python bench.py > gpurun_out/bench_default.txt 2> gpurun_out/bench_default.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_default.err
+python - <<'PY'
+import json
+d = json.loads([l for l in open("gpurun_out/bench_default.txt").read().splitlines() if l.startswith("{")][-1])
+print({k: d[k] for k in ("value", "ms_per_step")}, d["roofline"]["kernels_ms"], "frac", d["roofline"]["frac"])
+print("e2e", {k: d["e2e"][k] for k in ("value", "ms_per_step", "ms_each_step", "videos", "device_passes_per_step_rank0")})
+print("c2", d["extras"]["c2"]["ms_per_step"], d["extras"]["c2"]["roofline"]["kernels_ms"])
+PY
+timeout 300 python tools/e2e_profile.py c3 6 > gpurun_out/r2_e2e_profile_c3_6.txt 2>&1; head -40 gpurun_out/r2_e2e_profile_c3_6.txt

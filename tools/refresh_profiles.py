@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ncu_summary  # noqa: E402
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1_final"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 
 
@@ -55,7 +55,7 @@ def pipe_pcts(rep):
 
 traffic, pipes = {}, {}
 for f in sorted(os.listdir(G)):
-    m = re.match(r"prof_(c2|c3_mini|c3_shard)_(k_[a-z_]+)\.ncu-rep$", f)
+    m = re.match(r"prof_(c2|c3_mini|c3_shard|c3|c4_shard)_(k_[a-z_]+)\.ncu-rep$", f)
     if not m:
         continue
     wl, k = m.groups()
@@ -75,46 +75,51 @@ if pipes:
     with open(os.path.join(P, "pipes.json"), "w") as f:
         json.dump(pipes, f, indent=1)
 
-lp = os.path.join(G, "launches_bench_c2.csv")
+lp = os.path.join(G, "launches_bench.csv")
 if os.path.exists(lp):
     rows = [r for r in csv.reader(open(lp)) if len(r) > 10]
     h = rows[0]
     ik, iv, ig, iid = h.index("Kernel Name"), h.index("Metric Value"), h.index("Grid Size"), h.index("ID")
     recs = [(int(r[iid]), re.sub(r"^.*?(k_[a-z_]+).*$", r"\1", r[ik]), r[ig], float(r[iv].replace(",", ""))) for r in rows[1:]]
     out = ["# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_* on "
-           "`python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-batched`",
+           "`python bench.py --workload c3_shard --steps 2 --warmup 1 --no-cpu-baseline --no-extras --e2e-videos 1`",
            "# per-launch device time (cold-cache, serialised under the profiler: compare SHARES, not absolutes)", ""]
     agg = collections.OrderedDict()
     for _, k, _, v in recs:
         a = agg.setdefault(k, [0, 0.0])
         a[0] += 1
         a[1] += v
-    out.append("## all launches of the run (build + warm-up + 2 timed passes + e2e optimize_planes runs)")
+    out.append("## all launches of the run (build + warm-up + timed passes + split passes + e2e runs)")
     for k, (n, t) in agg.items():
         out.append(f"{k:14s} n={n:4d} total={t / 1e3:9.1f} us mean={t / n / 1e3:8.2f} us")
+    # the device-resident passes: k_unproject, k_project, scoring kernel, k_finalize with the workload's job count
     passes, i = [], 0
+    big = max((int(re.sub(r"[^0-9,]", "", g).split(",")[0] or 0) for _, k, g, _ in recs if k == "k_unproject"), default=0)
     while i < len(recs) - 3:
-        if (recs[i][1] == "k_unproject" and recs[i][2].startswith("(4, 32") and recs[i + 1][1] == "k_project"
-                and recs[i + 2][1] == "k_score" and recs[i + 3][1] == "k_finalize"):
+        g0 = int(re.sub(r"[^0-9,]", "", recs[i][2]).split(",")[0] or 0)
+        if (recs[i][1] == "k_unproject" and g0 == big and recs[i + 1][1] == "k_project"
+                and recs[i + 2][1].startswith("k_score") and recs[i + 3][1] == "k_finalize"):
             passes.append([recs[i + j][3] for j in range(4)])
+            score_name = recs[i + 2][1]
             i += 4
         else:
             i += 1
     if passes:
-        out += ["", "## the device-resident C2 passes: per-pass kernel times and shares"]
+        out += ["", f"## the device-resident passes ({big} jobs): per-pass kernel times and shares"]
         m = [statistics.mean(p[j] for p in passes) / 1e3 for j in range(4)]
-        for name, v in zip(("k_unproject", "k_project", "k_score", "k_finalize"), m):
-            out.append(f"{name:12s} {v:7.2f} us  {100 * v / sum(m):5.1f} % of the pass")
-        out.append(f"{'pass total':12s} {sum(m):7.2f} us over {len(passes)} passes")
-    open(os.path.join(P, "r1_launches_bench_c2.txt"), "w").write("\n".join(out) + "\n")
+        for name, v in zip(("k_unproject", "k_project", score_name, "k_finalize"), m):
+            out.append(f"{name:12s} {v:9.2f} us  {100 * v / sum(m):5.1f} % of the pass")
+        out.append(f"{'pass total':12s} {sum(m):9.2f} us over {len(passes)} passes")
+    open(os.path.join(P, f"{tag}_launches_bench.txt"), "w").write("\n".join(out) + "\n")
 for name in ("sanitizer_racecheck.txt", "sanitizer_memcheck.txt"):
     src = os.path.join(G, name)
     if os.path.exists(src):
-        with open(src) as f, open(os.path.join(P, "r1_" + name), "w") as o:
+        with open(src) as f, open(os.path.join(P, f"{tag}_" + name), "w") as o:
             o.writelines(l for l in f if "Host Frame" not in l)
-for name, dst in (("bench_default.txt", "r1_bench_default.json"), ("bench_reference.txt", "r1_bench_reference.json"),
-                  ("bench_n2.txt", "r1_bench_n2.json"), ("bench_n4.txt", "r1_bench_n4.json"),
-                  ("bench_n8.txt", "r1_bench_n8.json")):
+for name, dst in (("bench_default.txt", f"{tag}_bench_default.json"), ("bench_reference.txt", f"{tag}_bench_reference.json"),
+                  ("bench_n2.txt", f"{tag}_bench_n2.json"), ("bench_n4.txt", f"{tag}_bench_n4.json"),
+                  ("bench_n8.txt", f"{tag}_bench_n8.json"), ("bench_c4_shard.txt", f"{tag}_bench_c4_shard.json"),
+                  ("bench_c4_trans.txt", f"{tag}_bench_c4_trans.json"), ("bench_c2.txt", f"{tag}_bench_c2.json")):
     src = os.path.join(G, name)
     if os.path.exists(src):
         lines = [l for l in open(src).read().splitlines() if l.startswith("{")]
