@@ -703,14 +703,16 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
         // proven only if both fractional parts keep more than eps from the integer boundaries (a NaN or
         // infinite eps fails the comparison)
 #if A3D_EXP
-        // dx, dy are finite (sx, sy lie in [0, 1]), so the larger magnitude decides both tests with one compare;
-        // the proven bit is a predicated OR instead of a select + add
+        // Half-rate instructions (compares, selects, shifts, logic: 2 issue cycles each on B200, measured in
+        // tools/pipes_bench.cu) are what this loop is made of, so the decision is taken on the full-rate pipe:
+        // dx, dy are finite (sx, sy lie in [0, 1]), so the larger magnitude decides both tests; s = dm + (eps - 0.5)
+        // is negative exactly when the point is proven (s = 0 counts as unproven, which is the safe side; a NaN
+        // or infinite eps gives +inf or the canonical positive NaN), and its sign bit is the operand of the RED.
         const float dm = fmaxf(fabsf(dx), fabsf(dy));
-        uint32_t one;
-        asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t@p or.b32 %1, %1, %4;\n\t}"
-            : "=r"(one), "+r"(proven) : "f"(dm), "f"(-neg_thr), "r"(1u << k));
+        const uint32_t one = __float_as_uint(__fadd_rn(dm, neg_thr)) >> 31;
         const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
         red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
+        proven = proven + proven + one;                 // one 3-input add; bit 7 - k = point k
 #else
         const uint32_t one = (fabsf(dx) <= -neg_thr && fabsf(dy) <= -neg_thr) ? 1u : 0u;
         const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
@@ -718,7 +720,14 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
         proven += one << k;
 #endif
     }
+#if A3D_EXP
+    // bit (n - 1 - k) of `proven` is point k: reverse the n low bits
+    const int n = kFull ? kProjPX : nvalid;
+    const uint32_t un = ~proven & ((1u << n) - 1u);
+    return __brev(un) >> (32 - n);
+#else
     return ~proven & (kFull ? 0xffu : ((1u << nvalid) - 1u));
+#endif
 }
 
 // Phase B: the exact chain for the (candidate, point) pairs of one item that phase A could not prove.
@@ -857,6 +866,75 @@ __device__ __forceinline__ void worker_sync(int barrier_id) {
     else asm volatile("bar.sync 2, %0;" ::"n"(kStride) : "memory");
 }
 
+// Streams a worker's tile out of shared memory, with popcount + bounding box per candidate.
+// (row, uint4 column) of a thread's elements advance by constants: no division in the loop; the occupied word
+// columns are collected as a bit mask (pitch <= 32 words).
+// kRows = false (A3D_OUT_FULL): every word is written.  kRows = true (A3D_OUT_BBOX_ROWS): the slot's image in
+// proj_bits is zero outside the rows of proj_bbox[slot] (the caller's promise on entry, this kernel's on exit),
+// so a 16-byte piece is written only if it lies in a row of the slot's OLD box (whatever it holds now, zeros
+// included) or is non-zero — one pass, no box needed in advance.  A door-sized mask occupies an eighth of the
+// frame's rows; the zeros around it were 85 % of the pass's DRAM writes.
+template <bool kRows, int kStride>
+__device__ __forceinline__ void write_tile(const a3d_job_t& job, int nc, int H, int pitch, int words,
+                                           const uint32_t* __restrict__ masks, const int* __restrict__ gid,
+                                           int* __restrict__ red, uint32_t* __restrict__ proj_bits,
+                                           int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox, int tid,
+                                           int bar) {
+    const int p4 = pitch >> 2, n4 = H * p4;
+    const int row0 = tid / p4, col0 = tid - row0 * p4;
+    const int drow = kStride / p4, dcol = kStride - drow * p4;
+    for (int c = 0; c < nc; ++c) {
+        if (gid[c] < 0) continue;
+        const size_t g = (size_t)job.cand_begin + gid[c];
+        const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
+        uint4* d4 = reinterpret_cast<uint4*>(proj_bits + g * words);
+        int wlo = 0, whi = -1;                       // rows of the old box: always written
+        if (kRows) { wlo = proj_bbox[4 * g]; whi = proj_bbox[4 * g + 1]; }
+        MaskStat s = stat_identity();
+        if (pitch <= 32) {
+            uint32_t colmask = 0;
+            int row = row0, col = col0;
+            for (int i = tid; i < n4; i += kStride) {
+                const uint4 v = s4[i];
+                const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
+                if (!kRows || nzv || (row >= wlo && row <= whi)) d4[i] = v;
+                if (nzv) {
+                    s.popc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+                    s.rmin = min(s.rmin, row);
+                    s.rmax = max(s.rmax, row);
+                    const uint32_t nz = (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
+                    colmask |= nz << (4 * col);
+                }
+                row += drow; col += dcol;
+                if (col >= p4) { col -= p4; ++row; }
+            }
+            colmask = __reduce_or_sync(0xffffffffu, colmask);
+            if (colmask) { s.cmin = __ffs(colmask) - 1; s.cmax = 31 - __clz(colmask); }
+        } else {
+            for (int i = tid; i < n4; i += kStride) {
+                const uint4 v = s4[i];
+                const int row = i / p4;
+                const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
+                if (!kRows || nzv || (row >= wlo && row <= whi)) d4[i] = v;
+                if (nzv) {
+                    const int cc = (i - row * p4) << 2;
+                    stat_add_word(s, v.x, row, cc);
+                    stat_add_word(s, v.y, row, cc + 1);
+                    stat_add_word(s, v.z, row, cc + 2);
+                    stat_add_word(s, v.w, row, cc + 3);
+                }
+            }
+        }
+        stat_block_accumulate(red + 5 * c, s);
+    }
+    worker_sync<kStride>(bar);                     // (the old boxes are all read before any is replaced)
+    for (int c = tid; c < nc; c += kStride) {
+        if (gid[c] < 0) continue;
+        const size_t g = (size_t)job.cand_begin + gid[c];
+        stat_store(red + 5 * c, proj_popc + g, proj_bbox + 4 * g);
+    }
+}
+
 template <bool kFilter, int kStride>
 __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& job, int jid, int c0, int want, bool extra,
                                              int slots, const float* __restrict__ xform,
@@ -955,68 +1033,8 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
     }
     worker_sync<kStride>(bar);
 
-    // ---- stream the tile out, with popcount + bounding box per candidate ----------
-    // (row, uint4 column) of a thread's elements advance by constants: no division in the loop; the
-    // occupied word columns are collected as a bit mask (pitch <= 32 words).
-    // A3D_OUT_FULL: every word is written.  A3D_OUT_BBOX_ROWS: the slot's image in proj_bits is zero outside
-    // the rows of proj_bbox[slot] (the caller's promise on entry, this kernel's on exit), so a 16-byte piece
-    // is written only if it lies in a row of the slot's OLD box (whatever it holds now, zeros included) or is
-    // non-zero — one pass, no box needed in advance.  A door-sized mask occupies an eighth of the frame's rows;
-    // the zeros around it were 85 % of the pass's DRAM writes.
-    const int p4 = pitch >> 2, n4 = H * p4;
-    const int row0 = tid / p4, col0 = tid - row0 * p4;
-    const int drow = kStride / p4, dcol = kStride - drow * p4;
-    for (int c = 0; c < nc; ++c) {
-        if (gid[c] < 0) continue;
-        const size_t g = (size_t)job.cand_begin + gid[c];
-        const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
-        uint4* d4 = reinterpret_cast<uint4*>(proj_bits + g * words);
-        // rows that are always written: all of them, or those of the old box
-        int wlo = 0, whi = H - 1;
-        if (rows_only) { wlo = proj_bbox[4 * g]; whi = proj_bbox[4 * g + 1]; }
-        MaskStat s = stat_identity();
-        if (pitch <= 32) {
-            uint32_t colmask = 0;
-            int row = row0, col = col0;
-            for (int i = tid; i < n4; i += kStride) {
-                const uint4 v = s4[i];
-                const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
-                if (nzv || (row >= wlo && row <= whi)) d4[i] = v;
-                if (nzv) {
-                    s.popc += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-                    s.rmin = min(s.rmin, row);
-                    s.rmax = max(s.rmax, row);
-                    const uint32_t nz = (v.x ? 1u : 0u) | (v.y ? 2u : 0u) | (v.z ? 4u : 0u) | (v.w ? 8u : 0u);
-                    colmask |= nz << (4 * col);
-                }
-                row += drow; col += dcol;
-                if (col >= p4) { col -= p4; ++row; }
-            }
-            colmask = __reduce_or_sync(0xffffffffu, colmask);
-            if (colmask) { s.cmin = __ffs(colmask) - 1; s.cmax = 31 - __clz(colmask); }
-        } else {
-            for (int i = tid; i < n4; i += kStride) {
-                const uint4 v = s4[i];
-                const int row = i / p4;
-                const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
-                if (nzv || (row >= wlo && row <= whi)) d4[i] = v;
-                if (nzv) {
-                    const int cc = (i - row * p4) << 2;
-                    stat_add_word(s, v.x, row, cc);
-                    stat_add_word(s, v.y, row, cc + 1);
-                    stat_add_word(s, v.z, row, cc + 2);
-                    stat_add_word(s, v.w, row, cc + 3);
-                }
-            }
-        }
-        stat_block_accumulate(red + 5 * c, s);
-    }
-    worker_sync<kStride>(bar);                     // (the old boxes are all read before any is replaced)
-    for (int c = tid; c < nc; c += kStride) {
-        if (gid[c] < 0) continue;
-        const size_t g = (size_t)job.cand_begin + gid[c];
-        stat_store(red + 5 * c, proj_popc + g, proj_bbox + 4 * g);
-    }
+    if (rows_only) write_tile<true, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar);
+    else write_tile<false, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar);
 }
 
 // worker id -> (job, first candidate, candidates, extra): from the caller's tile map, else uniform tiles

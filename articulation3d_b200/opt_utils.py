@@ -539,6 +539,17 @@ def _upload_executor():
     return _uploader
 
 
+_preparer = None                   # ONE helper thread for the host-side preparation of the next video's table pass
+
+
+def _prepare_executor():
+    global _preparer
+    if _preparer is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _preparer = ThreadPoolExecutor(max_workers=1, thread_name_prefix="a3d-prepare")
+    return _preparer
+
+
 def _upload_stream(device) -> "torch.cuda.Stream":
     key = str(device)
     st = _upload_streams.get(key)
@@ -727,10 +738,10 @@ class _Session:
         return host.numpy()
 
     # -- all-sources schedule -----------------------------------------------------------
-    def cluster_tables(self, lists, stats: Stats | None = None, legacy: bool = False):
-        """``lists``: [(video index, planes, translation)].  ONE scheduling step for the cluster phase of
-        all those track lists: every frame of every track is a source (job), its targets are all
-        frames of its track.  Returns one list of ``TrackTable`` per entry of ``lists``."""
+    def _prepare_groups(self, lists, legacy: bool = False):
+        """Host half of ``cluster_tables``: for all tracks of ``lists`` the geometry of every frame as a source,
+        its candidate transforms and the job arrays — CPU work only (no access to the mask pool), so a helper
+        thread can run it while the video's masks are still being uploaded and the previous video is optimised."""
         cfg = self.cfg
         groups = {}                                   # translation flag -> per-track bookkeeping
         for li, (v, planes, translation) in enumerate(lists):
@@ -738,10 +749,9 @@ class _Session:
                 frames = list(plane['ids'].keys())
                 boxes = [plane['ids'][f] for f in frames]
                 groups.setdefault(bool(translation), []).append((li, ti, v, frames, boxes))
-        out = [[None] * len(planes) for _, planes, _ in lists]
+        prepared = []
         for translation, tracks in groups.items():
             cgrid, _, cmode, _ = _phase_setup(translation, legacy, cfg)
-            geos = []
             by_video = {}
             for k, (li, ti, v, frames, boxes) in enumerate(tracks):
                 by_video.setdefault(v, []).append(k)
@@ -756,7 +766,6 @@ class _Session:
                     T = len(tracks[k][3])
                     geo_of_track[k] = (g, o, o + T)
                     o += T
-                geos.append((g, ks))
             # one job list over all tracks, in track order
             src, ntg, tgt, parts = [], [], [], []
             for k, (li, ti, v, frames, boxes) in enumerate(tracks):
@@ -772,9 +781,28 @@ class _Session:
                                                          g.dir_vec[a:b], g.pivot[a:b]))
             geo = geometry.concat_rows(parts)
             xform, _ = _xforms_rows(geo.dir_vec, geo.pivot, cgrid, cmode)
-            src = np.concatenate(src)
-            res = self.run_rows(src, np.full(len(src), cmode, dtype=np.int32), geo, xform, np.concatenate(ntg),
-                                np.concatenate(tgt), stats)
+            prepared.append((tracks, parts, geo, xform, np.concatenate(src), np.concatenate(ntg), np.concatenate(tgt), cmode))
+        return prepared
+
+    def prefetch_tables(self, lists, legacy: bool = False):
+        """Start ``_prepare_groups(lists)`` on the preparation thread; ``cluster_tables`` of the same lists
+        picks the result up."""
+        self._prep_key = (tuple((v, id(planes), bool(t)) for v, planes, t in lists), legacy)
+        self._prep_future = _prepare_executor().submit(self._prepare_groups, lists, legacy)
+
+    def cluster_tables(self, lists, stats: Stats | None = None, legacy: bool = False):
+        """``lists``: [(video index, planes, translation)].  ONE scheduling step for the cluster phase of
+        all those track lists: every frame of every track is a source (job), its targets are all
+        frames of its track.  Returns one list of ``TrackTable`` per entry of ``lists``."""
+        key = (tuple((v, id(planes), bool(t)) for v, planes, t in lists), legacy)
+        fut, self._prep_future = getattr(self, "_prep_future", None), None
+        if fut is not None and getattr(self, "_prep_key", None) == key:
+            prepared = fut.result()
+        else:
+            prepared = self._prepare_groups(lists, legacy)
+        out = [[None] * len(planes) for _, planes, _ in lists]
+        for tracks, parts, geo, xform, src, ntg, tgt, cmode in prepared:
+            res = self.run_rows(src, np.full(len(src), cmode, dtype=np.int32), geo, xform, ntg, tgt, stats)
             o = 0
             for k, (li, ti, v, frames, boxes) in enumerate(tracks):
                 T = len(frames)
@@ -784,6 +812,7 @@ class _Session:
                                          parts[k])
                 o += T * T
         return out
+
 
 def _table_units(lists, cfg: OptConfig) -> int:
     """Device work of the all-sources schedule for these track lists, in units."""
@@ -1023,7 +1052,11 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
 
         def open_session(v):
             p, pl = videos[v]
-            return _Session([(p, [pl['trans'], pl['rot']])], cfg, device, ws=ws, staging=staging)
+            sess = _Session([(p, [pl['trans'], pl['rot']])], cfg, device, ws=ws, staging=staging)
+            lists = [(0, planes, tr) for planes, tr in ((pl['trans'], True), (pl['rot'], False)) if planes]
+            if lists and sess.n_masks:
+                sess.prefetch_tables(lists)           # geometry + candidate transforms of all sources, off this thread
+            return sess
         ahead = 2                                   # sessions opened (their uploads queued) ahead of the one optimised
         opened = [open_session(v) for v in range(min(ahead, len(videos)))]
         for v, ((p, pl), seed) in enumerate(zip(videos, seeds)):
