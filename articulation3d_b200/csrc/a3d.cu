@@ -653,9 +653,6 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
 // [2] of those, pairs of exact-only candidates, [3] warp-iterations of the exact loop
 __device__ unsigned long long g_filter_stats[4];
 #endif
-#ifndef A3D_EXP
-#define A3D_EXP 0
-#endif
 constexpr float kMagic = 12582912.f;                 // 1.5 * 2^23: x + kMagic holds rint(x) in its low mantissa bits
 // Phase A of one (item, candidate): the cheap pixel of up to 8 points; proven ones are splatted, the
 // others come back as a bit mask (bit k = point k needs the exact chain).
@@ -702,32 +699,12 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
         const float neg_thr = fmaf(ce, fabsf(r), fc.c0h);         // eps - 0.5
         // proven only if both fractional parts keep more than eps from the integer boundaries (a NaN or
         // infinite eps fails the comparison)
-#if A3D_EXP
-        // Half-rate instructions (compares, selects, shifts, logic: 2 issue cycles each on B200, measured in
-        // tools/pipes_bench.cu) are what this loop is made of, so the decision is taken on the full-rate pipe:
-        // dx, dy are finite (sx, sy lie in [0, 1]), so the larger magnitude decides both tests; s = dm + (eps - 0.5)
-        // is negative exactly when the point is proven (s = 0 counts as unproven, which is the safe side; a NaN
-        // or infinite eps gives +inf or the canonical positive NaN), and its sign bit is the operand of the RED.
-        const float dm = fmaxf(fabsf(dx), fabsf(dy));
-        const uint32_t one = __float_as_uint(__fadd_rn(dm, neg_thr)) >> 31;
-        const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
-        red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
-        proven = proven + proven + one;                 // one 3-input add; bit 7 - k = point k
-#else
         const uint32_t one = (fabsf(dx) <= -neg_thr && fabsf(dy) <= -neg_thr) ? 1u : 0u;
         const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
         red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
         proven += one << k;
-#endif
     }
-#if A3D_EXP
-    // bit (n - 1 - k) of `proven` is point k: reverse the n low bits
-    const int n = kFull ? kProjPX : nvalid;
-    const uint32_t un = ~proven & ((1u << n) - 1u);
-    return __brev(un) >> (32 - n);
-#else
     return ~proven & (kFull ? 0xffu : ((1u << nvalid) - 1u));
-#endif
 }
 
 // Phase B: the exact chain for the (candidate, point) pairs of one item that phase A could not prove.

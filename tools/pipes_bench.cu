@@ -14,7 +14,7 @@
 
 enum Op { FFMA, FFMA2, FADD, FMUL, IMAD, LOP3, IADD3, SHF, FSETP_SEL, FMNMX, MUFU, RED_SMEM, RED_SMEM_PRED_OFF,
           MIX_FFMA_LOP3, MIX_FFMA_FADD, MIX_FFMA_IMAD, MIX_3FFMA_1LOP3, FFMA_SAT, FFMA_IMM, FSETP_ONLY, MIX_FFMA2_LOP3,
-          MIX_FFMA_MUFU8, N_OPS };
+          MIX_FFMA_MUFU8, POPC, F2I, I2F, IMNMX, MUFU_DEP, FSETP_CHAIN, N_OPS };
 
 template <int OP>
 __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, float fb, float fc, uint32_t ub, uint32_t uc,
@@ -55,6 +55,16 @@ __global__ void __launch_bounds__(1024, 1) k(uint32_t* out, float fb, float fc, 
                 asm volatile("{.reg .pred p; setp.gt.f32 p, %1, %2; @p add.u32 %0, %0, 1;}" : "+r"(u[i]) : "f"(a[i]), "f"(fb));
             if (OP == FMNMX) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(fb));
             if (OP == MUFU) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+            if (OP == MUFU_DEP) {                 // rcp of a moving value (a plain rcp chain has a two-cycle fixed point)
+                asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+                asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(fb));
+            }
+            if (OP == POPC) asm volatile("popc.b32 %0, %0;" : "+r"(u[i]));
+            if (OP == F2I) asm volatile("{.reg .s32 t; cvt.rzi.s32.f32 t, %1; add.s32 %0, %0, t;}" : "+r"(u[i]) : "f"(a[i]));
+            if (OP == I2F) asm volatile("{.reg .f32 t; cvt.rn.f32.s32 t, %1; add.rn.f32 %0, %0, t;}" : "+f"(a[i]) : "r"(u[i]));
+            if (OP == IMNMX) asm volatile("min.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(ub));
+            if (OP == FSETP_CHAIN)                // the compare depends on the moving value: it cannot be hoisted
+                asm volatile("{.reg .pred p; setp.gt.f32 p, %0, %1; @p add.rn.f32 %0, %0, %2;}" : "+f"(a[i]) : "f"(fb), "f"(fc));
             if (OP == RED_SMEM) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr + 128u * i), "r"(u[i]) : "memory");
             if (OP == RED_SMEM_PRED_OFF)
                 asm volatile("{.reg .pred p; setp.eq.u32 p, %2, 12345; @p red.shared.or.b32 [%0], %1;}" ::"r"(saddr + 128u * i), "r"(u[i]), "r"(ub) : "memory");
@@ -143,7 +153,12 @@ int main() {
     run<FSETP_SEL>("FSETP + SEL", 2);
     run<FSETP_ONLY>("FSETP + @p IADD", 2);
     run<FMNMX>("FMNMX", 1);
-    run<MUFU>("MUFU.RCP", 1);
+    run<MUFU_DEP>("MUFU.RCP + FADD", 2);
+    run<POPC>("POPC", 1);
+    run<F2I>("F2I.TRUNC + IADD3", 2);
+    run<I2F>("I2F + FADD", 2);
+    run<IMNMX>("IMNMX (min.s32)", 1);
+    run<FSETP_CHAIN>("FSETP + @p FADD", 2);
     run<RED_SMEM>("RED.shared.or (no conflict)", 1);
     run<RED_SMEM_PRED_OFF>("ISETP + @!p RED.shared", 2);
     run<MIX_FFMA_LOP3>("FFMA + LOP3", 2);
