@@ -16,6 +16,7 @@ NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-fmad=false",                       # belt and braces: the exact paths use *_rn intrinsics
+    "-Xcompiler", "-ffp-contract=off",   # host helpers: every float64 operation rounded separately
     "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
     "-I", os.path.join(ROOT, "include"),
 ]

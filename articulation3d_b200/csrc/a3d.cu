@@ -2116,6 +2116,36 @@ int a3d_pitch_words(int W) { return W > 0 ? pitch_words(W) : 0; }
 // Host-side planner of projection CTAs for grids of about one wave (see include/a3d.h).  Cost model in
 // point units, from the ncu instruction counts of k_project<filter>: a CTA costs
 // kPlanFixed + tile * (kPlanPerCand + points); the job's extra CTA kPlanFixed + kPlanPerCand + 2.5 points.
+// HOST helper: unit quaternions -> candidate transforms.  The host builds the candidates of a pass in float64
+// exactly as the reference does (pytorch3d axis_angle_to_matrix via quaternions, utils/opt_utils.py:428-431):
+// norms, sin / cos and the quaternion come from the same torch calls; what is left — nine entries of ~4
+// multiplications and additions each — is IEEE arithmetic that is bit-identical in any order-preserving
+// implementation, and as ~40 separate array operations over (sources x candidates) elements it was the largest
+// single piece of host time of the public API (30 ms per 8-track video).  One fused pass here, every operation
+// rounded separately in the order of the reference expression, the result rounded once to fp32 (what Rotate
+// stores) into rows of 12 floats (entries 9..11 left as they are).
+int a3d_host_quat_to_xform(const double* q, const double* two_s, int64_t n, float* xform_out) {
+    if (n < 0 || (n > 0 && (!q || !two_s || !xform_out))) return fail(A3D_EINVAL, "a3d_host_quat_to_xform: bad argument");
+    for (int64_t e = 0; e < n; ++e) {
+        const volatile double r = q[4 * e], i = q[4 * e + 1], j = q[4 * e + 2], k = q[4 * e + 3], s = two_s[e];
+        const double ii = i * i, jj = j * j, kk = k * k;
+        const double ij = i * j, ik = i * k, jk = j * k;
+        const double ir = i * r, jr = j * r, kr = k * r;
+        float* o = xform_out + 12 * e;
+        double t;
+        t = jj + kk; t = s * t; o[0] = (float)(1.0 - t);
+        t = ij - kr; o[1] = (float)(s * t);
+        t = ik + jr; o[2] = (float)(s * t);
+        t = ij + kr; o[3] = (float)(s * t);
+        t = ii + kk; t = s * t; o[4] = (float)(1.0 - t);
+        t = jk - ir; o[5] = (float)(s * t);
+        t = ik - jr; o[6] = (float)(s * t);
+        t = jk + ir; o[7] = (float)(s * t);
+        t = ii + jj; t = s * t; o[8] = (float)(1.0 - t);
+    }
+    return A3D_OK;
+}
+
 int a3d_plan_tiles(const a3d_job_t* jobs_host, int n_jobs, int tile_max, int sm_count, int32_t* tile_map_out,
                    int cap_tiles, int* tile_cand_out) {
     const double kPlanFixed = 21500.0, kPlanPerCand = 3000.0;

@@ -172,16 +172,41 @@ def _axis_angle_to_matrix(axis_angle: torch.Tensor) -> torch.Tensor:
 
 def _rotation_entries(grid, dir_vec) -> torch.Tensor:
     """(A,) grid x (..., 3) float64 axis -> (..., A, 9) float64 entries: fp32 angles times the float64
-    axis, matrix in float64."""
+    axis, matrix in float64 (all torch: the form the tests compare with the oracle's)."""
     angles = torch.as_tensor(np.asarray(grid), dtype=torch.float32)[:, None]       # (A,1)
     d = torch.as_tensor(np.asarray(dir_vec, dtype=np.float64))
     return _axis_angle_to_matrix(angles * d[..., None, :])
 
 
+def _rotation_xforms(grid, dir_vec) -> np.ndarray:
+    """(A,) grid x (..., 3) float64 axis -> (..., A, 12) fp32 candidate rows [R row-major | 0 0 0].
+
+    The same values as ``_rotation_entries(...).to(float32)``: norms, sin / cos, the quaternion and
+    ``two_s`` are the same torch calls; the nine entries (products and sums of quaternion components, IEEE
+    arithmetic in the order of ``_axis_angle_to_matrix``) are evaluated in one fused pass by the library's
+    host helper instead of ~40 array operations (tests/test_host_logic.py compares the bits)."""
+    from . import _lib
+    angles = torch.as_tensor(np.asarray(grid), dtype=torch.float32)[:, None]       # (A,1)
+    d = torch.as_tensor(np.asarray(dir_vec, dtype=np.float64))
+    axis_angle = angles * d[..., None, :]
+    t = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
+    half = t * 0.5
+    k = torch.sin(half) / t
+    small = t.abs() < 1e-6
+    if bool(small.any()):
+        k = torch.where(small, 0.5 - (t * t) / 48, k)
+    q = torch.cat([torch.cos(half), axis_angle * k], dim=-1).contiguous()
+    two_s = (2.0 / (q * q).sum(-1)).contiguous()
+    out = np.zeros(tuple(q.shape[:-1]) + (12,), dtype=np.float32)
+    _lib.check(_lib.load().a3d_host_quat_to_xform(q.data_ptr(), two_s.data_ptr(), two_s.numel(), out.ctypes.data),
+               "a3d_host_quat_to_xform")
+    return out
+
+
 def rotation_matrices(grid, dir_vec) -> np.ndarray:
     """(A,) grid x (..., 3) float64 axis -> (..., A, 3, 3) fp32 (what ``Rotate`` keeps)."""
-    m = _rotation_entries(grid, dir_vec)
-    return m.to(torch.float32).reshape(m.shape[:-1] + (3, 3)).numpy()
+    x = _rotation_xforms(grid, dir_vec)
+    return np.ascontiguousarray(x[..., :9]).reshape(x.shape[:-1] + (3, 3))
 
 
 def xforms_seq(R: np.ndarray) -> np.ndarray:
@@ -193,10 +218,7 @@ def xforms_seq(R: np.ndarray) -> np.ndarray:
 
 def xforms_seq_from_dirs(grid, dir_vec) -> np.ndarray:
     """``xforms_seq(rotation_matrices(grid, dir_vec))`` without the intermediate copies."""
-    m = _rotation_entries(grid, dir_vec)
-    out = torch.zeros(m.shape[:-1] + (12,), dtype=torch.float32)
-    out[..., :9] = m                                  # float64 -> fp32 rounding, as Rotate stores it
-    return out.numpy()
+    return _rotation_xforms(grid, dir_vec)
 
 
 def xforms_composed(R: np.ndarray, pivot: np.ndarray) -> np.ndarray:

@@ -361,6 +361,10 @@ def gpu_arm(args, wl):
                          "(use --impl reference for the CPU oracle port)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # torchrun exports OMP_NUM_THREADS=1 for every rank; the host side of the public API (float64 candidate
+        # transforms, packing bookkeeping) is torch CPU work, so each rank takes its share of the box's cores
+        torch.set_num_threads(max(1, (os.cpu_count() or world) // world))
     dist = None
     if world > 1:
         import torch.distributed as dist_

@@ -109,6 +109,13 @@ int a3d_project_max_tile(int H, int W);
 int a3d_plan_tiles(const a3d_job_t* jobs_host, int n_jobs, int tile_max, int sm_count,
                    int32_t* tile_map_out, int cap_tiles, int* tile_cand_out);
 
+/* HOST helper: the 3x3 rotation entries of n unit quaternions, as pytorch3d's quaternion_to_matrix evaluates
+ * them in float64 (the reference's axis_angle_to_matrix, utils/opt_utils.py:428-431), rounded once to fp32
+ * (what Rotate stores) into the first nine floats of each 12-float candidate row.
+ *   q      HOST [n][4] float64 {r, i, j, k};  two_s  HOST [n] float64 = 2 / |q|^2
+ *   xform_out  HOST [n][12] fp32 (entries 9..11 untouched)                                          */
+int a3d_host_quat_to_xform(const double* q, const double* two_s, int64_t n, float* xform_out);
+
 /* (a7/a8 input stage) threshold + bit-pack.  Replaces the per-visit
  * `(pred_mask > 0.5)` of opt_utils.py:471-473 and `pred_mask.nonzero()` of :409.
  *   src      [n][H][W] of dtype (A3D_F32 | A3D_U8), contiguous

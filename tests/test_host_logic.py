@@ -459,3 +459,26 @@ def test_axis_angle_matrices_equal_oracle_form():
     aa[5, 3] = 0
     a, b = geometry._axis_angle_to_matrix(aa).reshape(300, 45, 3, 3), restated.axis_angle_to_matrix64(aa)
     assert torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))
+
+
+def test_fused_candidate_rows_equal_the_torch_form():
+    """``geometry._rotation_xforms`` (quaternion entries in one fused pass of the library's host helper) must be
+    bit-equal to the all-torch form the oracle comparison above pins, including tiny angles (Taylor branch),
+    the zero angle and angles past pi."""
+    from articulation3d_b200 import OptConfig
+    rng = np.random.RandomState(3)
+    d = rng.randn(300, 3)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[0] = [0.0, 0.0, 1.0]
+    d[1] = [1e-9, 0.0, 0.0]                                         # |axis_angle| below the 1e-6 switch
+    cfg = OptConfig()
+    for grid in (cfg.rot_cluster_grid, cfg.rot_final_grid, cfg.legacy_grid, np.array([0.0, 1e-8, -1e-7, 3.5, -4.0])):
+        want = geometry._rotation_entries(grid, d).to(torch.float32).numpy()
+        got = geometry._rotation_xforms(grid, d)
+        assert got.shape == want.shape[:-1] + (12,) and got.dtype == np.float32
+        assert np.array_equal(got[..., :9].view(np.uint32), want.view(np.uint32))
+        assert not got[..., 9:].any()
+        R = geometry.rotation_matrices(grid, d)
+        assert np.array_equal(R.reshape(want.shape).view(np.uint32), want.view(np.uint32))
+    one = geometry._rotation_xforms(cfg.rot_final_grid, d[7])       # a single axis (final phase of one track)
+    assert np.array_equal(one, geometry._rotation_xforms(cfg.rot_final_grid, d[7:8])[0])

@@ -13,8 +13,10 @@ from articulation3d_b200 import OptConfig, adapter, engine, opt_utils, rle, synt
 
 cfg = OptConfig.scaled(200, 150)
 preds, _ = synth.make_video(5, 2, 12, cfg, kinds=[0, 1])
-for kernel, proj, sched in (("ldg", "exact", "cta"), ("tma", "filter", "cta"), ("mma", "filter", "persistent")):
+for kernel, proj, sched, out in (("ldg", "exact", "cta", "rows"), ("tma", "filter", "cta", "full"),
+                                 ("mma", "filter", "persistent", "rows")):
     os.environ["A3D_SCORE_KERNEL"] = kernel
+    os.environ["A3D_PROJ_OUT"] = out                 # both output modes of the projection
     os.environ["A3D_PROJECT_KERNEL"] = proj          # both projection kernels, both CTA schedulers
     os.environ["A3D_PROJECT_SCHED"] = sched
     engine._tile_cache.clear()                       # the largest tile depends on the scheduler
@@ -27,6 +29,16 @@ for kernel, proj, sched in (("ldg", "exact", "cta"), ("tma", "filter", "cta"), (
             if pl.get('has_rot'):
                 _ = pl['reg_masks'][next(iter(pl['reg_masks']))]
     print(kernel, [pl.get('has_rot') for cat in planes for pl in planes[cat]])
+# the pipelined batch API (upload and preparation threads, shared workspace), both schedules
+for sched in ("table", "chain"):
+    os.environ["A3D_SCHEDULE"] = sched
+    vids = []
+    for v in range(3):
+        pv, _ = synth.make_video(20 + v, 2, 11, cfg, kinds=[0, 1])
+        vids.append((pv, opt_utils.track_planes(pv, cfg)))
+    opt_utils.optimize_videos(vids, [1, 2, 3], cfg=cfg, device="cuda:0")
+    print("optimize_videos", sched, [pl.get('has_rot') for _, planes in vids for cat in planes for pl in planes[cat]])
+os.environ.pop("A3D_SCHEDULE")
 H, W = 150, 200
 rles = [rle.encode(m.numpy() > 0.5) for m in preds[3].pred_masks]
 pool = engine.rle_to_pool(rles, H, W, "cuda:0")
