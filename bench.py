@@ -54,8 +54,10 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the sampler is started ahead of the
+    warm-up (nvidia-smi needs a few hundred ms to deliver its first line) and every line carries its own
+    timestamp, so only the samples that fall inside the timed region are reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -65,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -75,9 +77,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0: float | None = None, t1: float | None = None):
+        """``t0``, ``t1``: time.time() at the start / end of the timed region."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -86,22 +89,30 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for seen, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                when = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((when, float(f[2]), float(f[3]), [nm for nm, val in zip(names, f[6:10]) if val.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in rows if t0 is not None and t0 - 0.02 <= r[0] <= t1 + 0.02]
+        where = "inside the timed region"
+        if len(inside) < 2 and rows and t0 is not None:
+            # a timed region shorter than two sampling periods: the samples nearest to it (same load: warm-up
+            # steps before, the split steps after)
+            inside = sorted(rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:4]
+            where = "nearest to the timed region (shorter than two sampling periods)"
+        if t0 is None:
+            inside, where = rows, "whole run"
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "samples": len(sm), "sampled": where, "reasons": sorted({x for r in inside for x in r[3]})}
 
 
 # --------------------------------------------------------------------------
@@ -213,7 +224,7 @@ def _committed(name, wl_name, kernel_key):
     return {"value": v, "source": f"committed ncu capture, profiles/{name}.json ({d.get('_source', '')})"}
 
 
-def measure_pass(wl, video_ids, steps, warmup, dev, rank, world, dist, sample_clocks=True, gather=True):
+def measure_pass(wl, video_ids, steps, warmup, dev, rank, world, dist, sample_clocks=True, gather=True, streams=1):
     """Device-resident scoring passes over this rank's videos of the workload: K timed steps with CUDA
     events on the launching stream -> dict(value, ms, roofline, ...).  ``value`` is the whole job: the units
     of all ranks over the slowest rank's step time."""
@@ -221,13 +232,18 @@ def measure_pass(wl, video_ids, steps, warmup, dev, rank, world, dist, sample_cl
 
     inp = workloads.build_pass(wl, seed0=2020, device=dev, video_ids=video_ids)
     gather = gather and world > 1
-    # two sets of pass buffers when ranks exchange results: the gather of step k reads the result block of
-    # step k in place while step k+1 writes the other set (no staging copy in the step)
-    wss = [engine.Workspace(dev) for _ in range(2 if gather else 1)]
-    ws = wss[0]
     packed_bytes = inp.pool.bits.numel() * 4
     l2_bytes = 126 * 2 ** 20
     flush = None if packed_bytes > 2 * l2_bytes else torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+    # Steps are independent passes; ``streams`` = 2 lets consecutive steps alternate between two streams, each
+    # with its own set of pass buffers, so that the last, partly filled wave of step k overlaps step k+1
+    # (an experiment switch: see --streams).  Small workloads (L2 flush between steps) always use one.
+    n_streams = 1 if flush is not None else max(1, min(2, streams))
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(n_streams)] if n_streams > 1 else [torch.cuda.current_stream()]
+    # two sets of pass buffers also when ranks exchange results: the gather of step k reads the result block of
+    # step k in place while step k+1 writes the other set (no staging copy in the step)
+    wss = [engine.Workspace(dev) for _ in range(2 if (gather or n_streams > 1) else 1)]
+    ws = wss[0]
     # multi-GPU: the only exchange of the path is the gather of the fixed-size per-track-frame records
     # {angle_id, inter, union} (12 B each): ONE all_gather_into_tensor per step on a side stream,
     # double-buffered, so the collective of step k overlaps the kernels of step k+1.
@@ -243,60 +259,83 @@ def measure_pass(wl, video_ids, steps, warmup, dev, rank, world, dist, sample_cl
     step_no = [0]
 
     def one_step(evs=None, split=False):
-        """One pass through the C ABI.  split=False: a3d_pass, the call the package makes.  split=True:
-        a3d_project | a3d_score with an event between the two launch groups, for the per-kernel durations
-        of the roofline."""
-        if flush is not None:
-            flush.zero_()
-        if evs:
+        """One pass through the C ABI.  split=False: a3d_pass, the call the package makes, on the step's lane.
+        split=True: a3d_project | a3d_score on the current stream with an event between the two launch groups,
+        for the per-kernel durations of the roofline."""
+        if split:
+            if flush is not None:
+                flush.zero_()
             evs[0].record()
-        b = step_no[0] & 1 if (gather and not split) else 0
-        if gather and not split and comm_done[b] is not None:
-            torch.cuda.current_stream().wait_event(comm_done[b])         # buffer set b free again
-        res = _run_split(engine, inp, ws, evs) if split else engine.run_pass(inp.cfg, inp.pool, inp.dbatch, wss[b])
-        if gather and not split:
-            rec = res.block[:3].reshape(-1)                   # the three rows are contiguous in the result block
-            if send is not None:
-                send[b][:n_rec].copy_(rec)
-                rec = send[b]
-            ready = torch.cuda.Event()
-            ready.record()
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ready)
-                dist.all_gather_into_tensor(gathered[b], rec)
-                comm_done[b] = torch.cuda.Event(enable_timing=True)
-                comm_done[b].record()
-            step_no[0] += 1
-        if evs:
+            res = _run_split(engine, inp, ws, evs)
             evs[2].record()
+            return res
+        b = step_no[0] & 1 if len(wss) > 1 else 0
+        lane = lanes[step_no[0] % len(lanes)]
+        with torch.cuda.stream(lane):
+            if flush is not None:
+                flush.zero_()
+            if evs:
+                evs[0].record()
+            if gather and comm_done[b] is not None:
+                lane.wait_event(comm_done[b])                         # buffer set b free again
+            res = engine.run_pass(inp.cfg, inp.pool, inp.dbatch, wss[b])
+            if gather:
+                rec = res.block[:3].reshape(-1)               # the three rows are contiguous in the result block
+                if send is not None:
+                    send[b][:n_rec].copy_(rec)
+                    rec = send[b]
+                ready = torch.cuda.Event()
+                ready.record()
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(ready)
+                    dist.all_gather_into_tensor(gathered[b], rec)
+                    comm_done[b] = torch.cuda.Event(enable_timing=True)
+                    comm_done[b].record()
+            if evs:
+                evs[2].record()
+        step_no[0] += 1
         return res
 
+    sampler = ClockSampler(dev.index).start() if (rank == 0 and sample_clocks) else None
     for _ in range(max(warmup, 3)):
         one_step()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(dev.index).start() if (rank == 0 and sample_clocks) else None
     events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
-    wall0 = time.perf_counter()
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main = torch.cuda.current_stream()
+    wall0, region0 = time.perf_counter(), time.time()
     # Let the host run ahead of the device: the GPU spins ~40 ms while all K steps are
-    # enqueued, so the event intervals below contain kernel time only, never launch gaps.
+    # enqueued, so the timed interval below contains kernel time only, never launch gaps.
     torch.cuda._sleep(int(0.04 * 1.9e9))
+    t_begin.record()
+    for lane in lanes:
+        lane.wait_event(t_begin)
     for k in range(steps):
         one_step(events[k])
+    for lane in lanes:                                  # join: the timed region ends when every lane has drained
+        done = torch.cuda.Event()
+        done.record(lane)
+        main.wait_event(done)
+    if gather:
+        main.wait_event(comm_done[(step_no[0] - 1) & 1])          # ... and the last gather has landed
+        if steps > 1:
+            main.wait_event(comm_done[(step_no[0] - 2) & 1])
+    t_end.record()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if sampler else None
-    # the timed K steps (each interval includes any wait on a previous gather, never the L2 flush)
-    t_step = sum(e[0].elapsed_time(e[2]) for e in events) / steps
-    if gather:
-        # exposed tail of the last (un-overlapped) gather, amortised over the K steps
-        last = comm_done[(step_no[0] - 1) & 1]
-        t_step += max(0.0, events[-1][2].elapsed_time(last)) / steps
+    wall, region1 = time.perf_counter() - wall0, time.time()
+    clocks = sampler.stop(region0, region1) if sampler else None
+    # the timed K steps: one device interval from the first launch to the last lane / gather draining
+    # (with one lane and an L2 flush between steps: the sum of the per-step intervals, which leave the flush out)
+    if flush is not None:
+        t_step = sum(e[0].elapsed_time(e[2]) for e in events) / steps
+    else:
+        t_step = t_begin.elapsed_time(t_end) / steps
     # the same K steps again as a3d_project | a3d_score, for the kernel durations of the roofline
     split_events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     torch.cuda._sleep(int(0.04 * 1.9e9))
@@ -344,7 +383,7 @@ def measure_pass(wl, video_ids, steps, warmup, dev, rank, world, dist, sample_cl
     torch.cuda.empty_cache()
     return {"value": value, "ms_per_step": t_step, "roofline": roofline, "units_per_step": units_all,
             "units_per_step_per_gpu": units_all // world, "jobs_per_gpu": n_jobs, "per_rank_ms": per_rank_ms,
-            "packed_mask_bytes_per_gpu": packed_bytes,
+            "packed_mask_bytes_per_gpu": packed_bytes, "streams": n_streams,
             "l2": "flushed between steps (256 MiB write)" if flush is not None else "inputs exceed L2",
             "clocks": clocks, "wall_s": wall}
 
@@ -372,7 +411,7 @@ def gpu_arm(args, wl):
         dist.init_process_group("nccl", device_id=dev)
 
     mine = list(a3d_dist.shard_range(wl.videos, rank, world))
-    m = measure_pass(wl, mine, args.steps, args.warmup, dev, rank, world, dist)
+    m = measure_pass(wl, mine, args.steps, args.warmup, dev, rank, world, dist, streams=args.streams)
     # ---- e2e through the public API with host buffers, sharded like the device-resident pass -----
     e2e = _e2e(wl, dev, rank, world, dist, steps=max(1, min(args.steps, 5)), videos_per_rank=args.e2e_videos)
 
@@ -408,8 +447,9 @@ def gpu_arm(args, wl):
                        "packed_mask_bytes_per_gpu": m["packed_mask_bytes_per_gpu"], "l2": m["l2"],
                        "per_rank_ms_per_step": m["per_rank_ms"],
                        "step": "one a3d_pass call (k_unproject, k_project, scoring kernel, k_finalize) on device-resident "
-                               "inputs + the record gather; roofline.kernels_ms from the same K steps issued as "
-                               "a3d_project | a3d_score",
+                               "inputs + the record gather; consecutive (independent) steps alternate between "
+                               f"{m['streams']} stream(s) with their own pass buffers; timed as ONE device interval over the K "
+                               "steps; roofline.kernels_ms from the same K steps issued alone as a3d_project | a3d_score",
                        "kernels": "chosen by the library from the grid: projection = homography filter with proven "
                                   "truncation (reference chain for the unproven pairs); scoring = tcgen05 kind::i8 "
                                   "contraction of the bit masks; identical results to the reference chain / AND+POPC",
@@ -628,6 +668,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--e2e-videos", type=int, default=6, help="host clips per GPU of the e2e leg")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="streams the timed steps alternate between; 2 was measured: 3 %% faster on a 256-job shard, "
+                         "5 %% slower on the 2048-job headline (CTAs of two projection kernels interleave)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="skip the extra single-video (c2) pass and the pack stream reported under 'extras'")
