@@ -1592,50 +1592,13 @@ __device__ __forceinline__ void expand_store(uint32_t w, uint32_t dst, uint32_t 
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kc_stride), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]) : "memory");
 }
 
-// Order of the jobs for grids of a few waves: the hardware hands CTAs out in index order, so a 256-job shard
-// (1.7 waves of one-CTA jobs whose cost varies 3x with the mask size) ends on whatever the last indices cost.
-// Largest first (LPT) lets the short jobs fill the tail.  One CTA; key = pixels of the middle candidate + of
-// the middle target (both proportional to the words a job's CTAs expand); bitonic sort of (key, job) in shared
-// memory, descending.
-constexpr int kOrderMax = 4096;
-__global__ void __launch_bounds__(1024)
-k_order_jobs(const a3d_job_t* __restrict__ jobs, int n_jobs, int n_pad, const int32_t* __restrict__ tgt_popc,
-             const int32_t* __restrict__ tgt_index, const int32_t* __restrict__ proj_popc, int32_t* __restrict__ order) {
-    __shared__ unsigned long long key[kOrderMax];
-    for (int j = threadIdx.x; j < n_pad; j += blockDim.x) {
-        unsigned long long k = 0ull;                              // padding sorts last
-        if (j < n_jobs) {
-            const a3d_job_t job = jobs[j];
-            unsigned cost = 1u;
-            if (job.n_cand > 0) cost += (unsigned)proj_popc[(size_t)job.cand_begin + job.n_cand / 2];
-            if (job.n_tgt > 0) cost += (unsigned)tgt_popc[tgt_index[(size_t)job.tgt_begin + job.n_tgt / 2]];
-            k = ((unsigned long long)cost << 32) | (unsigned)(0x7fffffff - j);   // ties: lower index first
-        }
-        key[j] = k;
-    }
-    __syncthreads();
-    for (int size = 2; size <= n_pad; size <<= 1)
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
-                const int p = i ^ stride;
-                if (p > i) {
-                    const bool desc = (i & size) == 0;
-                    const unsigned long long a = key[i], b = key[p];
-                    if ((a < b) == desc) { key[i] = b; key[p] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    for (int j = threadIdx.x; j < n_jobs; j += blockDim.x) order[j] = 0x7fffffff - (int)(key[j] & 0xffffffffull);
-}
-
 __global__ void __launch_bounds__(kMmaThreads, 1)
 k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, int ct_tiles, int ctile,
             const uint32_t* __restrict__ tgt_bits, const int32_t* __restrict__ tgt_popc,
             const int32_t* __restrict__ tgt_bbox, const int32_t* __restrict__ tgt_index,
             const uint32_t* __restrict__ proj_bits, const int32_t* __restrict__ proj_popc,
             const int32_t* __restrict__ proj_bbox, unsigned long long* __restrict__ key_ws,
-            int32_t* __restrict__ inter_tab, int packed, const int32_t* __restrict__ job_order) {
+            int32_t* __restrict__ inter_tab, int packed) {
     extern __shared__ __align__(1024) uint8_t stage_mem[];
     __shared__ const uint32_t* s_ptr[kMmaM + kMmaNMax];       // first word of every mask of the tile
     __shared__ int s_pc[kMmaNMax];                            // pixel counts of the candidates
@@ -1644,9 +1607,8 @@ k_score_mma(const a3d_job_t* __restrict__ jobs, int H, int pitch, int tt_tiles, 
     __shared__ uint32_t s_tmem;
 
     const int per_job = tt_tiles * ct_tiles;
-    const int slot = blockIdx.x / per_job;
-    const int rem = blockIdx.x - slot * per_job;
-    const int jid = job_order ? job_order[slot] : slot;            // (written by k_order_jobs, the previous launch)
+    const int jid = blockIdx.x / per_job;
+    const int rem = blockIdx.x - jid * per_job;
     const a3d_job_t job = jobs[jid];
     const int tb = (rem / ct_tiles) * kMmaM;
     const int cb = (rem % ct_tiles) * ctile;
@@ -2524,21 +2486,9 @@ static int score_impl(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_t
         if (nblocks > 0x7fffffffLL) return fail(A3D_ELIMIT, "a3d_score: too many (job, tile) blocks");
         const size_t smem = (size_t)kMmaStages * mma_stage_bytes(ctile);
         A3D_CUDA_TRY(cudaFuncSetAttribute(k_score_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // few waves of CTAs: largest jobs first (A3D_SCORE_ORDER=0 | 1 forces)
-        int32_t* order = nullptr;
-        const char* env_order = getenv("A3D_SCORE_ORDER");
-        const bool want_order = env_order ? env_order[0] == '1' : nblocks < 8LL * device_sm_count();
-        if (want_order && n_jobs > 1 && n_jobs <= kOrderMax) {
-            int n_pad = 2;
-            while (n_pad < n_jobs) n_pad <<= 1;
-            A3D_CUDA_TRY(cudaMallocAsync((void**)&order, sizeof(int32_t) * (size_t)n_jobs, s));
-            k_order_jobs<<<1, 1024, 0, s>>>(jobs, n_jobs, n_pad, tgt_popc, tgt_index, proj_popc, order);
-            A3D_CUDA_TRY(cudaGetLastError());
-        }
-        A3D_CUDA_TRY(launch(k_score_mma, dim3((unsigned)nblocks), dim3(kMmaThreads), smem, s, pdl && !order, jobs, H, pitch,
-                            tt_tiles, ct_tiles, ctile, tgt_bits, tgt_popc, tgt_bbox, tgt_index, proj_bits, proj_popc,
-                            proj_bbox, (unsigned long long*)key_ws, inter_tab, packed, (const int32_t*)order));
-        if (order) A3D_CUDA_TRY(cudaFreeAsync(order, s));
+        A3D_CUDA_TRY(launch(k_score_mma, dim3((unsigned)nblocks), dim3(kMmaThreads), smem, s, pdl, jobs, H, pitch, tt_tiles,
+                            ct_tiles, ctile, tgt_bits, tgt_popc, tgt_bbox, tgt_index, proj_bits, proj_popc, proj_bbox,
+                            (unsigned long long*)key_ws, inter_tab, packed));
     } else if (tma_ok) {
         // mask tiles staged by TMA: one tensor map per (array, box width)
         TmaMaps maps;
