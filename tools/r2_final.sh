@@ -10,6 +10,8 @@ timeout 400 python bench.py --workload c2 --no-extras --no-cpu-baseline --e2e-vi
 for wl in c4_shard c4_trans; do
   timeout 600 python bench.py --workload $wl --steps 10 --e2e-videos 2 --no-extras --no-cpu-baseline > gpurun_out/bench_$wl.txt 2> gpurun_out/bench_$wl.err; echo "$wl rc=$?"
 done
+for fr in 30 300; do timeout 300 python -m articulation3d_b200.tools.inference --output gpurun_out/inference_$fr --frames $fr --tracks 4 --save-obj 2>&1 | tail -1; done > gpurun_out/r2_inference_tool.txt
+rm -rf gpurun_out/inference_30 gpurun_out/inference_300
 tools/_build/pipes_bench > gpurun_out/r2_pipes_bench.txt 2>&1
 M=smsp__inst_executed.sum,sm__inst_executed_pipe_alu.sum,sm__inst_executed_pipe_fma.sum,sm__inst_executed_pipe_fmaheavy.sum,sm__inst_executed_pipe_fmalite.sum,sm__inst_executed_pipe_xu.sum,sm__inst_executed_pipe_lsu.sum,sm__inst_executed_pipe_uniform.sum,sm__inst_executed_pipe_cbu.sum,sm__inst_executed_pipe_adu.sum,smsp__inst_executed_op_shared_atom.sum,sm__cycles_active.sum,gpu__time_duration.sum
 timeout 300 ncu --clock-control none -k regex:k_project -s 1 -c 1 --metrics $M python tools/profile_pass.py --workload c3_mini --passes 2 > gpurun_out/r2_ncu_pipes_k_project.txt 2>&1
@@ -26,5 +28,5 @@ tail -2 gpurun_out/sanitizer_memcheck.txt gpurun_out/sanitizer_racecheck.txt
 timeout 200 python tools/score_ab.py c3_shard ldg mma tma > gpurun_out/score_ab_c3_shard.txt 2>&1; tail -3 gpurun_out/score_ab_c3_shard.txt
 python tools/refresh_profiles.py r2 > gpurun_out/refresh.log 2>&1; tail -1 gpurun_out/refresh.log | cut -c1-200
 mkdir -p gpurun_out/profiles_new; cp profiles/r2_* profiles/traffic.json profiles/pipes.json gpurun_out/profiles_new/ 2>/dev/null
-cp gpurun_out/r2_pipes_bench.txt gpurun_out/r2_ncu_pipes_k_project.txt gpurun_out/profiles_new/
+cp gpurun_out/r2_pipes_bench.txt gpurun_out/r2_ncu_pipes_k_project.txt gpurun_out/r2_inference_tool.txt gpurun_out/profiles_new/
 find gpurun_out -name '*.ncu-rep' ! -name 'prof_c3_shard_k_project.ncu-rep' -delete; du -sh gpurun_out | tail -1
