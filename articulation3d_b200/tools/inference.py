@@ -35,6 +35,9 @@ def main(argv=None):
     cfg = OptConfig()
     preds, _ = synth.make_video(args.seed, args.tracks, args.frames, cfg)
     records = io.preds_to_records(preds, video_id="synthetic00_0_0")
+    torch.zeros(1, device=args.device)                       # CUDA context and library load are not the optimiser's time
+    opt_utils._lib.load()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     planes = opt_utils.track_planes(preds, cfg)
     opt_preds = opt_utils.optimize_planes(preds, planes, '3dc', cfg=cfg, device=args.device)
