@@ -65,6 +65,9 @@ class OptConfig:
     # (track-frame x candidate evaluations) of device work
     schedule: str = "auto"
     table_max_units: int = 96_000_000
+    # optimize_videos: videos optimised concurrently (worker threads, each with its own stream and pass
+    # buffers; results are independent of it: every video draws from its own seeded generator)
+    pipeline_workers: int = 2
 
     @property
     def cx(self) -> float:

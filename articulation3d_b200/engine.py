@@ -250,7 +250,6 @@ def plan_tiles(jobs: np.ndarray, max_tile: int, sm_count: int | None = None, fix
     return int(tmap[:, 2].max()), tmap
 
 
-_plan_buf = {}
 
 
 _sm_cache: dict = {}
@@ -276,9 +275,7 @@ def plan_tiles_native(jobs: np.ndarray, max_tile: int, sm_count: int | None = No
     lib = _lib.load()
     if sm_count is None:
         sm_count = plan_sm_count()
-    buf = _plan_buf.get(sm_count)
-    if buf is None:
-        buf = _plan_buf[sm_count] = np.empty((2 * sm_count, 4), dtype=np.int32)
+    buf = np.empty((2 * sm_count, 4), dtype=np.int32)          # per call: worker threads plan concurrently
     jobs = np.ascontiguousarray(jobs)
     tile = C.c_int(0)
     n = _lib.check(lib.a3d_plan_tiles(jobs.ctypes.data, len(jobs), max_tile, sm_count, buf.ctypes.data, len(buf),

@@ -697,12 +697,19 @@ class _Session:
         res = self._pass(batch, None, stats)
         host = self.staging.results_host(res.block.numel())
         host.view(4, -1).copy_(res.block, non_blocking=True)                 # one D2H into pinned memory
-        masks = {}
-        for j, s in enumerate(specs):           # enqueued before the sync: the gathers overlap the D2H
-            if s.keep_masks:
+        # the winning masks of all jobs that keep theirs: ONE gather into ONE block (enqueued before the sync, so
+        # it overlaps the D2H); the jobs' RegMasks hold views of it.  (A block per job was a fresh cudaMalloc per
+        # track — the blocks stay alive with the results — and cost more than the final pass itself.)
+        masks, keep = {}, [j for j, s in enumerate(specs) if s.keep_masks]
+        if keep:
+            spans, parts, o = {}, [], 0
+            for j in keep:
                 a, n = int(batch.jobs[j]["tgt_begin"]), int(batch.jobs[j]["n_tgt"])
-                gidx = res.best_cand[a:a + n] + int(batch.jobs[j]["cand_begin"])
-                masks[j] = res.masks(gidx)                          # copy out of the workspace
+                parts.append(res.best_cand[a:a + n] + int(batch.jobs[j]["cand_begin"]))
+                spans[j] = (o, o + n)
+                o += n
+            block = res.masks(torch.cat(parts) if len(parts) > 1 else parts[0])      # copy out of the workspace
+            masks = {j: block[lo:hi] for j, (lo, hi) in spans.items()}
         torch.cuda.current_stream().synchronize()
         packed = host.numpy().reshape(4, -1)
         out = []
@@ -1048,24 +1055,77 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
         # all-sources schedule, one session per video, software-pipelined: while video v is optimised
         # (table pass, host replay, final pass, write-back), the helper thread of session v+1 uploads and
         # packs the next video's masks on its own stream
-        ws, staging = engine.Workspace(device), engine.Staging(device)
+        # ... and `pipeline_workers` videos are optimised at a time, each by its own thread on its own stream
+        # with its own pass buffers: most of a video's time on the host is spent inside torch / CUDA calls
+        # that release the interpreter lock (waiting for the table pass, float64 array arithmetic, copies).
+        n_workers = max(1, min(int(os.environ.get("A3D_PIPELINE_WORKERS") or cfg.pipeline_workers), len(videos)))
+        wss = [(engine.Workspace(device), engine.Staging(device)) for _ in range(n_workers)]
+        ahead = n_workers + 1                       # sessions opened (uploads / preparation queued) ahead, in video order
+        sessions, next_open, open_lock = {}, [0], threading.Lock()
 
-        def open_session(v):
-            p, pl = videos[v]
-            sess = _Session([(p, [pl['trans'], pl['rot']])], cfg, device, ws=ws, staging=staging)
-            lists = [(0, planes, tr) for planes, tr in ((pl['trans'], True), (pl['rot'], False)) if planes]
-            if lists and sess.n_masks:
-                sess.prefetch_tables(lists)           # geometry + candidate transforms of all sources, off this thread
-            return sess
-        ahead = 2                                   # sessions opened (their uploads queued) ahead of the one optimised
-        opened = [open_session(v) for v in range(min(ahead, len(videos)))]
-        for v, ((p, pl), seed) in enumerate(zip(videos, seeds)):
-            session = opened.pop(0)
-            if v + ahead < len(videos):
-                opened.append(open_session(v + ahead))
-            stats.h2d_bytes += session.h2d_bytes
-            _run_lists(session, [_video_stages(p, pl, cfg, _global_random.Random(seed), outs[v])], cfg, stats,
-                       use_tables=True)
+        def open_upto(last):
+            with open_lock:                         # in order: the upload and preparation queues are FIFO
+                while next_open[0] <= min(last, len(videos) - 1):
+                    v = next_open[0]
+                    p, pl = videos[v]
+                    ws, staging = wss[v % n_workers]
+                    sess = _Session([(p, [pl['trans'], pl['rot']])], cfg, device, ws=ws, staging=staging)
+                    lists = [(0, planes, tr) for planes, tr in ((pl['trans'], True), (pl['rot'], False)) if planes]
+                    if lists and sess.n_masks:
+                        sess.prefetch_tables(lists)   # geometry + candidate transforms of all sources, off the workers
+                    sessions[v] = sess
+                    next_open[0] += 1
+
+        def work(w, stream, wstats):
+            torch.cuda.set_device(device)
+            with torch.cuda.stream(stream):
+                for v in range(w, len(videos), n_workers):
+                    open_upto(v + ahead - 1)
+                    with open_lock:
+                        session = sessions.pop(v)
+                    p, pl = videos[v]
+                    wstats.h2d_bytes += session.h2d_bytes
+                    _run_lists(session, [_video_stages(p, pl, cfg, _global_random.Random(seeds[v]), outs[v])], cfg,
+                               wstats, use_tables=True)
+
+        open_upto(ahead - 1)
+        main = torch.cuda.current_stream(device)
+        if n_workers == 1:
+            work(0, main, stats)
+        else:
+            streams = [torch.cuda.Stream(device=device) for _ in range(n_workers)]
+            start = torch.cuda.Event()
+            start.record(main)
+            wstats = [Stats() for _ in range(n_workers)]
+            errors = []
+
+            def guarded(w):
+                try:
+                    streams[w].wait_event(start)
+                    work(w, streams[w], wstats[w])
+                except BaseException as e:             # re-raised below, on the caller's thread
+                    errors.append(e)
+            threads = [threading.Thread(target=guarded, args=(w,), name=f"a3d-video-{w}") for w in range(n_workers)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+            for w, st in enumerate(streams):          # later work on the caller's stream sees the workers' results
+                done = torch.cuda.Event()
+                done.record(st)
+                main.wait_event(done)
+            for _, pl in videos:                      # the kept masks were allocated on a worker's stream
+                for cat in ('trans', 'rot'):
+                    for plane in pl[cat]:
+                        rm = plane.get('reg_masks')
+                        if isinstance(rm, RegMasks) and rm.packed is not None and rm.packed.is_cuda:
+                            rm.packed.record_stream(main)
+            for ws_ in wstats:
+                for f in ("units_visited", "units_computed", "passes", "jobs", "h2d_bytes", "d2h_bytes"):
+                    setattr(stats, f, getattr(stats, f) + getattr(ws_, f))
+                stats.schedule = ws_.schedule or stats.schedule
         return [o[0] for o in outs]
     session = _Session([(p, [pl['trans'], pl['rot']]) for p, pl in videos], cfg, device)
     stats.h2d_bytes += session.h2d_bytes
