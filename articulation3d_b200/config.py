@@ -66,8 +66,10 @@ class OptConfig:
     schedule: str = "auto"
     table_max_units: int = 96_000_000
     # optimize_videos: videos optimised concurrently (worker threads, each with its own stream and pass
-    # buffers; results are independent of it: every video draws from its own seeded generator)
-    pipeline_workers: int = 2
+    # buffers; results are independent of it: every video draws from its own seeded generator).  Measured on
+    # the 8-track, 120-frame clips: 2 workers 247-830 ms per 6 clips against 266-270 ms for one (the host side is
+    # Python under one interpreter lock), so one is the default.
+    pipeline_workers: int = 1
 
     @property
     def cx(self) -> float:

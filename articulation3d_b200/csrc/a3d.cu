@@ -531,8 +531,14 @@ __device__ __forceinline__ void exact_pixel(float px, float py, float pz, const 
 // Hits on the same destination word are merged in registers before one shared-memory atomic.  Words
 // are tracked by their 32-bit shared-memory byte address; the flush of the pending word is one
 // predicated RED (no branch).
+// A3D_ABLATE_* (debug builds of tools/ablate.sh only): leave one part of k_project out to measure what it costs;
+// the results are then wrong by construction.
 __device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t bits) {
+#ifdef A3D_ABLATE_RED
+    asm volatile("" ::"r"(addr), "r"(bits) : "memory");           // operands still computed, no atomic
+#else
     asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
+#endif
 }
 
 struct WordMerge {
@@ -678,6 +684,9 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
     }
 #endif
     if (h[10] != 0.f) return 0u;                       // exact-only candidate: handled by the straight-line chain
+#ifdef A3D_ABLATE_PHASE_A
+    return 0u;
+#endif
     const float h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3], h4 = h[4], h5 = h[5], h6 = h[6], h7 = h[7], h8 = h[8];
     const float ce = __fadd_ru(C, h[9]);
     // bits of (kMagic + n) = 0x4B400000 + n: fold the constant out of  row * pitch4 + (col >> 5) * 4
@@ -716,6 +725,9 @@ __device__ __forceinline__ void splat_exact_list(unsigned long long todo, int c_
                                                  uint32_t masks_s, int words4) {
 #ifdef A3D_FILTER_STATS
     atomicAdd(&g_filter_stats[1], (unsigned long long)__popcll(todo));
+#endif
+#ifdef A3D_ABLATE_EXACT_LIST
+    return;
 #endif
     while (todo) {
 #ifdef A3D_FILTER_STATS
@@ -1010,6 +1022,9 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
     }
     worker_sync<kStride>(bar);
 
+#ifdef A3D_ABLATE_WRITE
+    return;
+#endif
     if (rows_only) write_tile<true, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar);
     else write_tile<false, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar);
 }
