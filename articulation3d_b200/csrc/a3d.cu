@@ -659,6 +659,7 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
 // [2] of those, pairs of exact-only candidates, [3] warp-iterations of the exact loop
 __device__ unsigned long long g_filter_stats[4];
 #endif
+constexpr uint32_t kMagicRowBits = 0x4B400000u;      // bit pattern of kMagic: kMagic + row has the bits kMagicRowBits + row
 constexpr float kMagic = 12582912.f;                 // 1.5 * 2^23: x + kMagic holds rint(x) in its low mantissa bits
 // Phase A of one (item, candidate): the cheap pixel of up to 8 points; proven ones are splatted, the
 // others come back as a bit mask (bit k = point k needs the exact chain).
@@ -675,7 +676,7 @@ struct FilterConst {
 template <bool kFull>
 __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjPX], const float (&ys)[kProjPX],
                                                         const float C, int nvalid, const float* __restrict__ h,
-                                                        const FilterConst& fc, uint32_t cm) {
+                                                        const FilterConst& fc, uint32_t cm, uint32_t& rlo, uint32_t& rhi) {
 #ifdef A3D_FILTER_STATS
     atomicAdd(&g_filter_stats[0], (unsigned long long)(kFull ? 8 : nvalid));
     if (h[10] != 0.f) {
@@ -712,6 +713,8 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
         const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
         red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
         proven += one << k;
+        rlo = min(rlo, tyb);                           // rows this thread touched (bits of kMagic + row: same order)
+        rhi = max(rhi, tyb);
     }
     return ~proven & (kFull ? 0xffu : ((1u << nvalid) - 1u));
 }
@@ -722,7 +725,7 @@ template <int kMode>
 __device__ __forceinline__ void splat_exact_list(unsigned long long todo, int c_begin, const float* __restrict__ gX,
                                                  int cap, const float* __restrict__ xf, float ax, float ay, float az,
                                                  float f, float cx, float cy, float wmax, float hmax, int pitch4,
-                                                 uint32_t masks_s, int words4) {
+                                                 uint32_t masks_s, int words4, uint32_t& rlo, uint32_t& rhi) {
 #ifdef A3D_FILTER_STATS
     atomicAdd(&g_filter_stats[1], (unsigned long long)__popcll(todo));
 #endif
@@ -741,6 +744,8 @@ __device__ __forceinline__ void splat_exact_list(unsigned long long todo, int c_
         int col, rw;
         exact_pixel<kMode>(px, py, pz, xf + 12 * c, ax, ay, az, f, cx, cy, wmax, hmax, col, rw);
         red_or_shared(word_addr(masks_s + (uint32_t)c * (uint32_t)words4, rw, col, pitch4), 1u << (col & 31));
+        rlo = min(rlo, kMagicRowBits + (uint32_t)rw);
+        rhi = max(rhi, kMagicRowBits + (uint32_t)rw);
     }
 }
 
@@ -748,8 +753,9 @@ template <int kMode, int kStride>
 __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t& job, int npts, int nc,
                                                  const float* __restrict__ pcd, const float* __restrict__ xf,
                                                  const float* __restrict__ hf, int x0, int y0,
-                                                 uint32_t* __restrict__ masks, int words, int tid) {
+                                                 uint32_t* __restrict__ masks, int words, int tid, int* __restrict__ rows) {
     const int cap = job.pcd_cap;
+    uint32_t rlo = 0xffffffffu, rhi = 0u;             // image rows this thread splats into, over all its candidates
     const float* base = pcd + (size_t)A3D_PCD_PLANES * job.pcd_begin;
     const uint4* XY4 = reinterpret_cast<const uint4*>(base + 3 * (size_t)cap);
     const float4* C4 = reinterpret_cast<const float4*>(base + 4 * (size_t)cap);
@@ -792,11 +798,11 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
             const int ce = min(nc, cb + 8);
             for (int c = cb; c < ce; ++c) {
                 const uint32_t unc = splat_points_filter<true>(xs, ys, C, kProjPX, hf + kHF * c, fc,
-                                                               masks_s + (uint32_t)(c * words4));
+                                                               masks_s + (uint32_t)(c * words4), rlo, rhi);
                 todo |= (unsigned long long)unc << (8 * (c - cb));
             }
             splat_exact_list<kMode>(todo, cb, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy,
-                                    wmax, hmax, pitch4, masks_s, words4);
+                                    wmax, hmax, pitch4, masks_s, words4, rlo, rhi);
         }
     }
     // last, partial round: its items are dealt out in (item, group of g candidates) units so that all threads
@@ -819,12 +825,20 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
             unsigned long long todo = 0;
             for (int c = cb; c < ce; ++c) {
                 const uint32_t unc = splat_points_filter<false>(xs, ys, C, nvalid, hf + kHF * c, fc,
-                                                                masks_s + (uint32_t)(c * words4));
+                                                                masks_s + (uint32_t)(c * words4), rlo, rhi);
                 todo |= (unsigned long long)unc << (8 * (c - cb));
             }
             splat_exact_list<kMode>(todo, cb, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy,
-                                    wmax, hmax, pitch4, masks_s, words4);
+                                    wmax, hmax, pitch4, masks_s, words4, rlo, rhi);
         }
+    }
+    // the rows the worker's tile occupies: everything outside them is still zero in shared memory, so the
+    // statistics / write-out pass only walks these rows (a door-sized mask: an eighth of the frame)
+    rlo = __reduce_min_sync(0xffffffffu, rlo);
+    rhi = __reduce_max_sync(0xffffffffu, rhi);
+    if ((tid & 31) == 0 && rhi >= rlo) {
+        atomicMin(&rows[0], (int)(rlo - kMagicRowBits));
+        atomicMax(&rows[1], (int)(rhi - kMagicRowBits));
     }
 }
 
@@ -845,7 +859,7 @@ struct ProjSmem {
     int* red;          // [slots][5]
     float* hf;         // [slots][kHF]   (filter only)
     int* gid;          // [slots] candidate of the slot, -1 = not mine
-    int* ctl;          // [2] nflag, nlist
+    int* ctl;          // [4] nflag, nlist, first and last image row the tile's splats touched
 };
 
 template <int kStride>
@@ -868,22 +882,32 @@ __device__ __forceinline__ void write_tile(const a3d_job_t& job, int nc, int H, 
                                            const uint32_t* __restrict__ masks, const int* __restrict__ gid,
                                            int* __restrict__ red, uint32_t* __restrict__ proj_bits,
                                            int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox, int tid,
-                                           int bar) {
-    const int p4 = pitch >> 2, n4 = H * p4;
-    const int row0 = tid / p4, col0 = tid - row0 * p4;
+                                           int bar, int r_lo, int r_hi) {
+    // [r_lo, r_hi]: the image rows the tile's splats touched (recorded by the splat loops); every other row of the
+    // masks in shared memory is still zero, so statistics and copies only walk these rows — a door-sized mask
+    // occupies an eighth of the frame, and the walk over all rows was a fifth of the kernel.  Rows outside are
+    // zero-filled in the destination where the mode asks for it (all of them, or those of the slot's old box).
+    const int p4 = pitch >> 2;
+    const bool any = r_hi >= r_lo;
+    const int lo4 = any ? r_lo * p4 : 0, hi4 = any ? (r_hi + 1) * p4 : 0;
+    const int row0 = r_lo + tid / p4, col0 = tid - (tid / p4) * p4;
     const int drow = kStride / p4, dcol = kStride - drow * p4;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     for (int c = 0; c < nc; ++c) {
         if (gid[c] < 0) continue;
         const size_t g = (size_t)job.cand_begin + gid[c];
         const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
         uint4* d4 = reinterpret_cast<uint4*>(proj_bits + g * words);
-        int wlo = 0, whi = -1;                       // rows of the old box: always written
-        if (kRows) { wlo = proj_bbox[4 * g]; whi = proj_bbox[4 * g + 1]; }
+        int wlo = 0, whi = H - 1;                    // rows that are written whatever they hold: all, or the old box
+        if (kRows) { wlo = max(proj_bbox[4 * g], 0); whi = min(proj_bbox[4 * g + 1], H - 1); }
+        // zero-fill of the always-written rows outside the tile's rows
+        for (int i = wlo * p4 + tid; i < min(lo4, (whi + 1) * p4); i += kStride) d4[i] = zero4;
+        for (int i = max(hi4, wlo * p4) + tid; i < (whi + 1) * p4; i += kStride) d4[i] = zero4;
         MaskStat s = stat_identity();
         if (pitch <= 32) {
             uint32_t colmask = 0;
             int row = row0, col = col0;
-            for (int i = tid; i < n4; i += kStride) {
+            for (int i = lo4 + tid; i < hi4; i += kStride) {
                 const uint4 v = s4[i];
                 const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
                 if (!kRows || nzv || (row >= wlo && row <= whi)) d4[i] = v;
@@ -900,7 +924,7 @@ __device__ __forceinline__ void write_tile(const a3d_job_t& job, int nc, int H, 
             colmask = __reduce_or_sync(0xffffffffu, colmask);
             if (colmask) { s.cmin = __ffs(colmask) - 1; s.cmax = 31 - __clz(colmask); }
         } else {
-            for (int i = tid; i < n4; i += kStride) {
+            for (int i = lo4 + tid; i < hi4; i += kStride) {
                 const uint4 v = s4[i];
                 const int row = i / p4;
                 const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
@@ -958,7 +982,7 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
             red[5 * i + 3] = 0x7fffffff; red[5 * i + 4] = -1;
             gid[i] = extra ? -1 : c0 + i;
         }
-        if (tid == 0) { sm.ctl[0] = 0; sm.ctl[1] = 0; }
+        if (tid == 0) { sm.ctl[0] = 0; sm.ctl[1] = 0; sm.ctl[2] = 0x7fffffff; sm.ctl[3] = -1; }
     }
     worker_sync<kStride>(bar);
     if (first) {
@@ -1000,12 +1024,16 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
     } else if (extra) {
         return;
     }
+    // rows the write-out has to walk: those the filter path recorded, or all of them when a reference-chain
+    // splat (exact kernel, the extra worker, exact-only candidates left in the tile) took part
+    bool all_rows = !kFilter || extra;
     if (npts > 0) {
         if (kFilter && !extra) {
-            if (job.mode == A3D_MODE_SEQ) splat_job_filter<A3D_MODE_SEQ, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid);
-            else if (job.mode == A3D_MODE_COMPOSED) splat_job_filter<A3D_MODE_COMPOSED, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid);
-            else splat_job_filter<A3D_MODE_TRANSLATE, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid);
+            if (job.mode == A3D_MODE_SEQ) splat_job_filter<A3D_MODE_SEQ, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid, sm.ctl + 2);
+            else if (job.mode == A3D_MODE_COMPOSED) splat_job_filter<A3D_MODE_COMPOSED, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid, sm.ctl + 2);
+            else splat_job_filter<A3D_MODE_TRANSLATE, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid, sm.ctl + 2);
             if (!moved && sm.ctl[0] > 0) {
+                all_rows = true;
                 // more exact-only candidates than the extra worker holds: each tile runs its own
                 for (int c = 0; c < nc; ++c) {
                     if (hf[kHF * c + 10] == 0.f) continue;
@@ -1025,8 +1053,9 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
 #ifdef A3D_ABLATE_WRITE
     return;
 #endif
-    if (rows_only) write_tile<true, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar);
-    else write_tile<false, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar);
+    const int r_lo = all_rows ? 0 : sm.ctl[2], r_hi = all_rows ? H - 1 : sm.ctl[3];        // (after the splat's barrier)
+    if (rows_only) write_tile<true, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar, r_lo, r_hi);
+    else write_tile<false, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar, r_lo, r_hi);
 }
 
 // worker id -> (job, first candidate, candidates, extra): from the caller's tile map, else uniform tiles
@@ -1053,7 +1082,7 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
           uint32_t* __restrict__ proj_bits, int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox,
           bool rows_only) {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int ctl[2];
+    __shared__ int ctl[4];
     int jid, c0, want;
     bool extra;
     decode_work<kFilter>(blockIdx.x, tile_map, tile_cand, tiles_per_job, jid, c0, want, extra);
@@ -1082,7 +1111,7 @@ k_project_p(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, in
             const int4* __restrict__ tile_map, uint32_t* __restrict__ proj_bits, int32_t* __restrict__ proj_popc,
             int32_t* __restrict__ proj_bbox, bool rows_only) {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int ctl[2][2];
+    __shared__ int ctl[2][4];
     __shared__ int next_work[2];
     const int g = threadIdx.x / kGroupThreads, tid = threadIdx.x - g * kGroupThreads;
     const int words = cam.H * cam.pitch;

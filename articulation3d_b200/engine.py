@@ -416,6 +416,8 @@ class DeviceBatch:
         hv[om:om + nm] = tmap.view(np.uint8).reshape(-1)
         dev = staging.device_block(total) if staging is not None else torch.empty(total, dtype=torch.uint8, device=device)
         dev[:total].copy_(host[:total], non_blocking=True)
+        if staging is not None:
+            staging.host_done()
         self.jobs = dev[oj:oj + nj]
         self.xform = dev[ox:ox + nx].view(torch.float32).view(-1, 12)
         self.tgt_index = dev[ot:ot + nt].view(torch.int32)
@@ -438,16 +440,39 @@ class DeviceBatch:
 
 
 class Staging:
-    """Reusable pinned-host / device byte blocks for the per-pass descriptors and results."""
+    """Reusable pinned-host / device byte blocks for the per-pass descriptors and results.
+
+    Passes are enqueued without waiting for the device (several chunks of one table pass, the next video's
+    table pass ahead of the current video's final pass), so the pinned block a pass's descriptors are copied
+    from must not be refilled before that copy has run: ``host`` hands out a small ring of blocks, each
+    guarded by the event recorded after its copy (``host_done``).  The device block needs no ring: all passes
+    of one ``Staging`` are issued on one stream, where the next copy into it queues behind the kernels that
+    read it."""
+    RING = 4
 
     def __init__(self, device):
         self.device = torch.device(device)
-        self._host = self._dev = self._res_host = None
+        self._ring = [None] * self.RING          # pinned blocks
+        self._busy = [None] * self.RING          # event after the last H2D out of the block
+        self._next = 0
+        self._dev = self._res_host = None
 
     def host(self, n):
-        if self._host is None or self._host.numel() < n:
-            self._host = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
-        return self._host
+        i = self._next
+        self._next = (i + 1) % self.RING
+        self._slot = i
+        if self._busy[i] is not None:
+            self._busy[i].synchronize()          # long done unless four passes are in flight
+            self._busy[i] = None
+        if self._ring[i] is None or self._ring[i].numel() < n:
+            self._ring[i] = torch.empty(max(n, 1 << 16), dtype=torch.uint8).pin_memory()
+        return self._ring[i]
+
+    def host_done(self):
+        """Call after enqueuing the copy out of the block ``host`` returned last."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self._busy[self._slot] = ev
 
     def device_block(self, n):
         if self._dev is None or self._dev.numel() < n:

@@ -720,10 +720,11 @@ class _Session:
         return out
 
     def run_rows(self, sources, modes, geo: geometry.SourceGeometryRows, xform, n_tgt, tgt_index,
-                 stats: Stats | None = None) -> np.ndarray:
+                 stats: Stats | None = None, wait: bool = True):
         """Jobs given as arrays (one row of ``geo`` / ``xform[i]`` per job) -> (4, sum n_tgt) int32
         results {cand, inter, union, iou bits}.  Split into as many device passes as the
-        projected-mask workspace budget asks for; all passes are enqueued before the one sync."""
+        projected-mask workspace budget asks for; all passes are enqueued before the one sync.
+        ``wait=False``: nothing is waited for — returns (pinned int32 tensor of its own, event)."""
         S = len(sources)
         n_tgt = np.asarray(n_tgt, dtype=np.int64)
         A = xform.shape[1]
@@ -731,7 +732,9 @@ class _Session:
         per_pass = max(1, int(_PROJ_BUDGET_BYTES // (per_cand * max(A, 1))))
         t_begin = np.zeros(S + 1, dtype=np.int64)
         np.cumsum(n_tgt, out=t_begin[1:])
-        host = self.staging.results_host(4 * int(t_begin[-1])).view(4, -1)
+        total = 4 * int(t_begin[-1])
+        host = (self.staging.results_host(total) if wait else torch.empty(max(total, 1), dtype=torch.int32).pin_memory()[:total])
+        host = host.view(4, -1)
         src_points = self.pool.source_points
         for lo in range(0, S, per_pass):
             hi = min(S, lo + per_pass)
@@ -741,6 +744,10 @@ class _Session:
                                             n_tgt[lo:hi], src_points)
             res = self._pass(batch, None, stats)
             host[:, t_begin[lo]:t_begin[hi]].copy_(res.block, non_blocking=True)
+        if not wait:
+            done = torch.cuda.Event()
+            done.record()
+            return host, done
         torch.cuda.current_stream().synchronize()
         return host.numpy()
 
@@ -797,19 +804,29 @@ class _Session:
         self._prep_key = (tuple((v, id(planes), bool(t)) for v, planes, t in lists), legacy)
         self._prep_future = _prepare_executor().submit(self._prepare_groups, lists, legacy)
 
-    def cluster_tables(self, lists, stats: Stats | None = None, legacy: bool = False):
-        """``lists``: [(video index, planes, translation)].  ONE scheduling step for the cluster phase of
-        all those track lists: every frame of every track is a source (job), its targets are all
-        frames of its track.  Returns one list of ``TrackTable`` per entry of ``lists``."""
+    def launch_tables(self, lists, stats: Stats | None = None, legacy: bool = False):
+        """First half of ``cluster_tables``: enqueues the all-sources pass(es) of ``lists`` and the D2H of
+        their result blocks, waits for nothing on the device.  ``finish_tables`` turns the handle into tables."""
         key = (tuple((v, id(planes), bool(t)) for v, planes, t in lists), legacy)
         fut, self._prep_future = getattr(self, "_prep_future", None), None
         if fut is not None and getattr(self, "_prep_key", None) == key:
             prepared = fut.result()
         else:
             prepared = self._prepare_groups(lists, legacy)
-        out = [[None] * len(planes) for _, planes, _ in lists]
+        pending = []
         for tracks, parts, geo, xform, src, ntg, tgt, cmode in prepared:
-            res = self.run_rows(src, np.full(len(src), cmode, dtype=np.int32), geo, xform, ntg, tgt, stats)
+            host, done = self.run_rows(src, np.full(len(src), cmode, dtype=np.int32), geo, xform, ntg, tgt, stats,
+                                       wait=False)
+            pending.append((tracks, parts, host, done))
+        return key, [len(planes) for _, planes, _ in lists], pending
+
+    @staticmethod
+    def finish_tables(handle):
+        _, sizes, pending = handle
+        out = [[None] * n for n in sizes]
+        for tracks, parts, host, done in pending:
+            done.synchronize()
+            res = host.numpy()
             o = 0
             for k, (li, ti, v, frames, boxes) in enumerate(tracks):
                 T = len(frames)
@@ -819,6 +836,12 @@ class _Session:
                                          parts[k])
                 o += T * T
         return out
+
+    def cluster_tables(self, lists, stats: Stats | None = None, legacy: bool = False):
+        """``lists``: [(video index, planes, translation)].  ONE scheduling step for the cluster phase of
+        all those track lists: every frame of every track is a source (job), its targets are all
+        frames of its track.  Returns one list of ``TrackTable`` per entry of ``lists``."""
+        return self.finish_tables(self.launch_tables(lists, stats, legacy))
 
 
 def _table_units(lists, cfg: OptConfig) -> int:
@@ -931,18 +954,25 @@ def _default_device(device):
 # ---------------------------------------------------------------------------
 # public API (reference signatures)
 # ---------------------------------------------------------------------------
+def _table_lists(video_lists):
+    return [(v, planes, translation) for v, stages in enumerate(video_lists)
+            for (_, planes, translation, _, _) in stages if planes]
+
+
 def _run_lists(session: _Session, video_lists, cfg: OptConfig, stats: Stats, legacy: bool = False,
-               use_tables: bool | None = None):
+               use_tables: bool | None = None, launched=None):
     """Drive track lists to completion.  ``video_lists``: per video a list of stages
     ``(preds_fn, planes, translation, rng, after)``; the stages of a video run in order (their RNG
     consumption is sequential), videos advance in lock-step.  ``preds_fn()`` gives the stage's input
     predictions, ``after()`` is called when the stage is done (write-back)."""
-    lists = [(v, planes, translation) for v, stages in enumerate(video_lists)
-             for (_, planes, translation, _, _) in stages if planes]
+    lists = _table_lists(video_lists)
     tables = {}
     if lists and session.n_masks and (use_tables if use_tables is not None else _use_tables(lists, cfg)):
         stats.schedule = "table"
-        for (v, planes, translation), tabs in zip(lists, session.cluster_tables(lists, stats, legacy=legacy)):
+        # ``launched``: the all-sources passes of these lists were already enqueued (optimize_videos does that
+        # one video ahead, so the device works on them while the host replays the previous video)
+        got = session.finish_tables(launched) if launched is not None else session.cluster_tables(lists, stats, legacy=legacy)
+        for (v, planes, translation), tabs in zip(lists, got):
             tables[(v, translation)] = tabs
     elif lists:
         stats.schedule = "chain"
@@ -1079,14 +1109,24 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
         def work(w, stream, wstats):
             torch.cuda.set_device(device)
             with torch.cuda.stream(stream):
-                for v in range(w, len(videos), n_workers):
+                def start(v):
+                    """Session of video v with its table passes enqueued (device work for the time the host
+                    spends on the video before it)."""
                     open_upto(v + ahead - 1)
                     with open_lock:
                         session = sessions.pop(v)
                     p, pl = videos[v]
                     wstats.h2d_bytes += session.h2d_bytes
-                    _run_lists(session, [_video_stages(p, pl, cfg, _global_random.Random(seeds[v]), outs[v])], cfg,
-                               wstats, use_tables=True)
+                    stages = [_video_stages(p, pl, cfg, _global_random.Random(seeds[v]), outs[v])]
+                    lists = _table_lists(stages)
+                    launched = session.launch_tables(lists, wstats) if lists and session.n_masks else None
+                    return session, stages, launched
+                mine = list(range(w, len(videos), n_workers))
+                nxt = start(mine[0]) if mine else None
+                for i, v in enumerate(mine):
+                    session, stages, launched = nxt
+                    nxt = start(mine[i + 1]) if i + 1 < len(mine) else None
+                    _run_lists(session, stages, cfg, wstats, use_tables=True, launched=launched)
 
         open_upto(ahead - 1)
         main = torch.cuda.current_stream(device)

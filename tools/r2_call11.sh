@@ -1,0 +1,14 @@
+cd "${GRAFT_REPO_ROOT:-.}"; mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.txt
+for wl in c3_mini c2; do
+  echo "== $wl old"; (cd _ab/old && AB_ITERS=10 timeout 300 python tools/project_ab.py $wl) 2>&1 | tail -2
+  for om in 0 1; do echo "== $wl new out_mode=$om"; AB_ITERS=10 AB_OUT_MODE=$om timeout 300 python tools/project_ab.py $wl 2>&1 | tail -2; done
+done 2>&1 | tee gpurun_out/r2_ab11.txt
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_c11.txt 2>/dev/null
+python - <<'PY'
+import json
+d = json.loads([l for l in open("gpurun_out/bench_c11.txt").read().splitlines() if l.startswith("{")][-1])
+print({k: d[k] for k in ("value", "ms_per_step")}, d["roofline"]["kernels_ms"], "frac", d["roofline"]["frac"])
+print("e2e", {k: d["e2e"][k] for k in ("value", "ms_per_step", "ms_each_step", "videos", "device_passes_per_step_rank0")})
+print("c2", d["extras"]["c2"]["ms_per_step"], d["extras"]["c2"]["roofline"]["kernels_ms"])
+PY
