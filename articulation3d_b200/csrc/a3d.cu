@@ -659,7 +659,6 @@ __device__ __forceinline__ void splat_job(const Cam& cam, const a3d_job_t& job, 
 // [2] of those, pairs of exact-only candidates, [3] warp-iterations of the exact loop
 __device__ unsigned long long g_filter_stats[4];
 #endif
-constexpr uint32_t kMagicRowBits = 0x4B400000u;      // bit pattern of kMagic: kMagic + row has the bits kMagicRowBits + row
 constexpr float kMagic = 12582912.f;                 // 1.5 * 2^23: x + kMagic holds rint(x) in its low mantissa bits
 // Phase A of one (item, candidate): the cheap pixel of up to 8 points; proven ones are splatted, the
 // others come back as a bit mask (bit k = point k needs the exact chain).
@@ -676,7 +675,7 @@ struct FilterConst {
 template <bool kFull>
 __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjPX], const float (&ys)[kProjPX],
                                                         const float C, int nvalid, const float* __restrict__ h,
-                                                        const FilterConst& fc, uint32_t cm, uint32_t& rlo, uint32_t& rhi) {
+                                                        const FilterConst& fc, uint32_t cm) {
 #ifdef A3D_FILTER_STATS
     atomicAdd(&g_filter_stats[0], (unsigned long long)(kFull ? 8 : nvalid));
     if (h[10] != 0.f) {
@@ -713,8 +712,6 @@ __device__ __forceinline__ uint32_t splat_points_filter(const float (&xs)[kProjP
         const uint32_t txb = __float_as_uint(tx), tyb = __float_as_uint(ty);
         red_or_shared(tyb * (uint32_t)fc.pitch4 + cmk + ((txb >> 5) << 2), one << (txb & 31));
         proven += one << k;
-        rlo = min(rlo, tyb);                           // rows this thread touched (bits of kMagic + row: same order)
-        rhi = max(rhi, tyb);
     }
     return ~proven & (kFull ? 0xffu : ((1u << nvalid) - 1u));
 }
@@ -725,7 +722,7 @@ template <int kMode>
 __device__ __forceinline__ void splat_exact_list(unsigned long long todo, int c_begin, const float* __restrict__ gX,
                                                  int cap, const float* __restrict__ xf, float ax, float ay, float az,
                                                  float f, float cx, float cy, float wmax, float hmax, int pitch4,
-                                                 uint32_t masks_s, int words4, uint32_t& rlo, uint32_t& rhi) {
+                                                 uint32_t masks_s, int words4) {
 #ifdef A3D_FILTER_STATS
     atomicAdd(&g_filter_stats[1], (unsigned long long)__popcll(todo));
 #endif
@@ -744,8 +741,67 @@ __device__ __forceinline__ void splat_exact_list(unsigned long long todo, int c_
         int col, rw;
         exact_pixel<kMode>(px, py, pz, xf + 12 * c, ax, ay, az, f, cx, cy, wmax, hmax, col, rw);
         red_or_shared(word_addr(masks_s + (uint32_t)c * (uint32_t)words4, rw, col, pitch4), 1u << (col & 31));
-        rlo = min(rlo, kMagicRowBits + (uint32_t)rw);
-        rhi = max(rhi, kMagicRowBits + (uint32_t)rw);
+    }
+}
+
+// Phase B for a whole warp: the unproven pairs of the 32 items the warp just ran phase A on, dealt to the lanes
+// one pair each.  Left to its owner, a lane with 1-3 unproven pairs (0.6 % of 48) drags the whole warp through
+// 2-4 passes of the reference chain with 2-4 lanes active — the ablation build without this list ran 15 %
+// faster.  Here the pairs are numbered across the warp (prefix sum of the per-lane counts by shuffles — no
+// shared memory is left for a queue), every lane finds the owner of pair number `lane` by binary search over
+// the prefix sums, fetches the owner's mask and item by shuffle, and one pass of the chain serves up to 32 pairs.
+// All 32 lanes must call it together.
+template <int kMode>
+__device__ __forceinline__ void splat_exact_list_warp(unsigned long long todo, int item, int c_begin,
+                                                      const float* __restrict__ base, int cap, const float* __restrict__ xf,
+                                                      float ax, float ay, float az, float f, float cx, float cy, float wmax,
+                                                      float hmax, int pitch4, uint32_t masks_s, int words4) {
+    const unsigned kAll = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int cnt = __popcll(todo);
+    if (!__any_sync(kAll, cnt != 0)) return;
+#ifdef A3D_FILTER_STATS
+    atomicAdd(&g_filter_stats[1], (unsigned long long)cnt);
+#endif
+#ifdef A3D_ABLATE_EXACT_LIST
+    return;
+#endif
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(kAll, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int excl = incl - cnt;
+    const int total = __shfl_sync(kAll, incl, 31);
+    for (int b0 = 0; b0 < total; b0 += 32) {
+#ifdef A3D_FILTER_STATS
+        if (lane == 0) atomicAdd(&g_filter_stats[3], 1ull);
+#endif
+        const int idx = b0 + lane;
+        int src = 0;                                    // lanes whose pairs all come before pair idx
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(kAll, incl, src + step - 1);
+            if (v <= idx) src += step;
+        }
+        src = min(src, 31);
+        const unsigned lo = __shfl_sync(kAll, (unsigned)todo, src), hi = __shfl_sync(kAll, (unsigned)(todo >> 32), src);
+        const int sitem = __shfl_sync(kAll, item, src);
+        const int sexcl = __shfl_sync(kAll, excl, src);
+        const int scb = __shfl_sync(kAll, c_begin, src);               // (differs between lanes in the last round)
+        if (idx < total) {
+            unsigned long long t = ((unsigned long long)hi << 32) | lo;
+            for (int r = idx - sexcl; r > 0; --r) t &= t - 1;     // the (idx - sexcl)-th set bit of the owner's mask
+            const int b = __ffsll((long long)t) - 1;
+            const int c = scb + (b >> 3), k = b & 7;
+            const float* gX = base + (size_t)sitem * kProjPX;
+            float px = __ldg(gX + k), py = __ldg(gX + cap + k), pz = __ldg(gX + 2 * (size_t)cap + k);
+            if (kMode == A3D_MODE_SEQ) { px = __fsub_rn(px, ax); py = __fsub_rn(py, ay); pz = __fsub_rn(pz, az); }
+            int col, rw;
+            exact_pixel<kMode>(px, py, pz, xf + 12 * c, ax, ay, az, f, cx, cy, wmax, hmax, col, rw);
+            red_or_shared(word_addr(masks_s + (uint32_t)c * (uint32_t)words4, rw, col, pitch4), 1u << (col & 31));
+        }
     }
 }
 
@@ -753,9 +809,8 @@ template <int kMode, int kStride>
 __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t& job, int npts, int nc,
                                                  const float* __restrict__ pcd, const float* __restrict__ xf,
                                                  const float* __restrict__ hf, int x0, int y0,
-                                                 uint32_t* __restrict__ masks, int words, int tid, int* __restrict__ rows) {
+                                                 uint32_t* __restrict__ masks, int words, int tid) {
     const int cap = job.pcd_cap;
-    uint32_t rlo = 0xffffffffu, rhi = 0u;             // image rows this thread splats into, over all its candidates
     const float* base = pcd + (size_t)A3D_PCD_PLANES * job.pcd_begin;
     const uint4* XY4 = reinterpret_cast<const uint4*>(base + 3 * (size_t)cap);
     const float4* C4 = reinterpret_cast<const float4*>(base + 4 * (size_t)cap);
@@ -798,11 +853,17 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
             const int ce = min(nc, cb + 8);
             for (int c = cb; c < ce; ++c) {
                 const uint32_t unc = splat_points_filter<true>(xs, ys, C, kProjPX, hf + kHF * c, fc,
-                                                               masks_s + (uint32_t)(c * words4), rlo, rhi);
+                                                               masks_s + (uint32_t)(c * words4));
                 todo |= (unsigned long long)unc << (8 * (c - cb));
             }
+#ifdef A3D_NO_WARP_LIST               // A/B build: every lane walks its own list
             splat_exact_list<kMode>(todo, cb, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy,
-                                    wmax, hmax, pitch4, masks_s, words4, rlo, rhi);
+                                    wmax, hmax, pitch4, masks_s, words4);
+#else
+            // (every thread of the warp is here: nfull is a multiple of the stride)
+            splat_exact_list_warp<kMode>(todo, item, cb, base, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy, wmax, hmax,
+                                         pitch4, masks_s, words4);
+#endif
         }
     }
     // last, partial round: its items are dealt out in (item, group of g candidates) units so that all threads
@@ -816,29 +877,33 @@ __device__ __forceinline__ void splat_job_filter(const Cam& cam, const a3d_job_t
             if (rounds * t <= best) { best = rounds * t; g = t; }
         }
         const int ngroups = (nc + g - 1) / g;
-        for (int u = tid; u < tail * ngroups; u += kStride) {
-            const int grp = u / tail, item = nfull + (u - grp * tail);
-            const int cb = grp * g, ce = min(nc, cb + g);
-            float xs[kProjPX], ys[kProjPX], C;
-            const int nvalid = min(kProjPX, npts - item * kProjPX);
-            load_item(item, xs, ys, C, nvalid);
+        const int nunits = tail * ngroups;
+        for (int u0 = 0; u0 < nunits; u0 += kStride) {              // same trip count for every thread of the warp
+            const int u = u0 + tid;
             unsigned long long todo = 0;
-            for (int c = cb; c < ce; ++c) {
-                const uint32_t unc = splat_points_filter<false>(xs, ys, C, nvalid, hf + kHF * c, fc,
-                                                                masks_s + (uint32_t)(c * words4), rlo, rhi);
-                todo |= (unsigned long long)unc << (8 * (c - cb));
+            int item = nfull, cb = 0;
+            if (u < nunits) {
+                const int grp = u / tail;
+                item = nfull + (u - grp * tail);
+                cb = grp * g;
+                const int ce = min(nc, cb + g);
+                float xs[kProjPX], ys[kProjPX], C;
+                const int nvalid = min(kProjPX, npts - item * kProjPX);
+                load_item(item, xs, ys, C, nvalid);
+                for (int c = cb; c < ce; ++c) {
+                    const uint32_t unc = splat_points_filter<false>(xs, ys, C, nvalid, hf + kHF * c, fc,
+                                                                    masks_s + (uint32_t)(c * words4));
+                    todo |= (unsigned long long)unc << (8 * (c - cb));
+                }
             }
+#ifdef A3D_NO_WARP_LIST
             splat_exact_list<kMode>(todo, cb, base + (size_t)item * kProjPX, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy,
-                                    wmax, hmax, pitch4, masks_s, words4, rlo, rhi);
+                                    wmax, hmax, pitch4, masks_s, words4);
+#else
+            splat_exact_list_warp<kMode>(todo, item, cb, base, cap, xf, ax, ay, az, cam.f, cam.cx, cam.cy, wmax, hmax,
+                                         pitch4, masks_s, words4);
+#endif
         }
-    }
-    // the rows the worker's tile occupies: everything outside them is still zero in shared memory, so the
-    // statistics / write-out pass only walks these rows (a door-sized mask: an eighth of the frame)
-    rlo = __reduce_min_sync(0xffffffffu, rlo);
-    rhi = __reduce_max_sync(0xffffffffu, rhi);
-    if ((tid & 31) == 0 && rhi >= rlo) {
-        atomicMin(&rows[0], (int)(rlo - kMagicRowBits));
-        atomicMax(&rows[1], (int)(rhi - kMagicRowBits));
     }
 }
 
@@ -859,7 +924,7 @@ struct ProjSmem {
     int* red;          // [slots][5]
     float* hf;         // [slots][kHF]   (filter only)
     int* gid;          // [slots] candidate of the slot, -1 = not mine
-    int* ctl;          // [4] nflag, nlist, first and last image row the tile's splats touched
+    int* ctl;          // [2] nflag, nlist
 };
 
 template <int kStride>
@@ -882,32 +947,22 @@ __device__ __forceinline__ void write_tile(const a3d_job_t& job, int nc, int H, 
                                            const uint32_t* __restrict__ masks, const int* __restrict__ gid,
                                            int* __restrict__ red, uint32_t* __restrict__ proj_bits,
                                            int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox, int tid,
-                                           int bar, int r_lo, int r_hi) {
-    // [r_lo, r_hi]: the image rows the tile's splats touched (recorded by the splat loops); every other row of the
-    // masks in shared memory is still zero, so statistics and copies only walk these rows — a door-sized mask
-    // occupies an eighth of the frame, and the walk over all rows was a fifth of the kernel.  Rows outside are
-    // zero-filled in the destination where the mode asks for it (all of them, or those of the slot's old box).
-    const int p4 = pitch >> 2;
-    const bool any = r_hi >= r_lo;
-    const int lo4 = any ? r_lo * p4 : 0, hi4 = any ? (r_hi + 1) * p4 : 0;
-    const int row0 = r_lo + tid / p4, col0 = tid - (tid / p4) * p4;
+                                           int bar) {
+    const int p4 = pitch >> 2, n4 = H * p4;
+    const int row0 = tid / p4, col0 = tid - row0 * p4;
     const int drow = kStride / p4, dcol = kStride - drow * p4;
-    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     for (int c = 0; c < nc; ++c) {
         if (gid[c] < 0) continue;
         const size_t g = (size_t)job.cand_begin + gid[c];
         const uint4* s4 = reinterpret_cast<const uint4*>(masks + (size_t)c * words);
         uint4* d4 = reinterpret_cast<uint4*>(proj_bits + g * words);
-        int wlo = 0, whi = H - 1;                    // rows that are written whatever they hold: all, or the old box
-        if (kRows) { wlo = max(proj_bbox[4 * g], 0); whi = min(proj_bbox[4 * g + 1], H - 1); }
-        // zero-fill of the always-written rows outside the tile's rows
-        for (int i = wlo * p4 + tid; i < min(lo4, (whi + 1) * p4); i += kStride) d4[i] = zero4;
-        for (int i = max(hi4, wlo * p4) + tid; i < (whi + 1) * p4; i += kStride) d4[i] = zero4;
+        int wlo = 0, whi = -1;                       // rows of the old box: always written
+        if (kRows) { wlo = proj_bbox[4 * g]; whi = proj_bbox[4 * g + 1]; }
         MaskStat s = stat_identity();
         if (pitch <= 32) {
             uint32_t colmask = 0;
             int row = row0, col = col0;
-            for (int i = lo4 + tid; i < hi4; i += kStride) {
+            for (int i = tid; i < n4; i += kStride) {
                 const uint4 v = s4[i];
                 const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
                 if (!kRows || nzv || (row >= wlo && row <= whi)) d4[i] = v;
@@ -924,7 +979,7 @@ __device__ __forceinline__ void write_tile(const a3d_job_t& job, int nc, int H, 
             colmask = __reduce_or_sync(0xffffffffu, colmask);
             if (colmask) { s.cmin = __ffs(colmask) - 1; s.cmax = 31 - __clz(colmask); }
         } else {
-            for (int i = lo4 + tid; i < hi4; i += kStride) {
+            for (int i = tid; i < n4; i += kStride) {
                 const uint4 v = s4[i];
                 const int row = i / p4;
                 const bool nzv = (v.x | v.y | v.z | v.w) != 0u;
@@ -982,7 +1037,7 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
             red[5 * i + 3] = 0x7fffffff; red[5 * i + 4] = -1;
             gid[i] = extra ? -1 : c0 + i;
         }
-        if (tid == 0) { sm.ctl[0] = 0; sm.ctl[1] = 0; sm.ctl[2] = 0x7fffffff; sm.ctl[3] = -1; }
+        if (tid == 0) { sm.ctl[0] = 0; sm.ctl[1] = 0; }
     }
     worker_sync<kStride>(bar);
     if (first) {
@@ -1024,16 +1079,12 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
     } else if (extra) {
         return;
     }
-    // rows the write-out has to walk: those the filter path recorded, or all of them when a reference-chain
-    // splat (exact kernel, the extra worker, exact-only candidates left in the tile) took part
-    bool all_rows = !kFilter || extra;
     if (npts > 0) {
         if (kFilter && !extra) {
-            if (job.mode == A3D_MODE_SEQ) splat_job_filter<A3D_MODE_SEQ, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid, sm.ctl + 2);
-            else if (job.mode == A3D_MODE_COMPOSED) splat_job_filter<A3D_MODE_COMPOSED, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid, sm.ctl + 2);
-            else splat_job_filter<A3D_MODE_TRANSLATE, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid, sm.ctl + 2);
+            if (job.mode == A3D_MODE_SEQ) splat_job_filter<A3D_MODE_SEQ, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid);
+            else if (job.mode == A3D_MODE_COMPOSED) splat_job_filter<A3D_MODE_COMPOSED, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid);
+            else splat_job_filter<A3D_MODE_TRANSLATE, kStride>(cam, job, npts, nc, pcd, xf, hf, x0, y0, masks, words, tid);
             if (!moved && sm.ctl[0] > 0) {
-                all_rows = true;
                 // more exact-only candidates than the extra worker holds: each tile runs its own
                 for (int c = 0; c < nc; ++c) {
                     if (hf[kHF * c + 10] == 0.f) continue;
@@ -1053,9 +1104,8 @@ __device__ __forceinline__ void project_tile(const Cam& cam, const a3d_job_t& jo
 #ifdef A3D_ABLATE_WRITE
     return;
 #endif
-    const int r_lo = all_rows ? 0 : sm.ctl[2], r_hi = all_rows ? H - 1 : sm.ctl[3];        // (after the splat's barrier)
-    if (rows_only) write_tile<true, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar, r_lo, r_hi);
-    else write_tile<false, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar, r_lo, r_hi);
+    if (rows_only) write_tile<true, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar);
+    else write_tile<false, kStride>(job, nc, H, pitch, words, masks, gid, red, proj_bits, proj_popc, proj_bbox, tid, bar);
 }
 
 // worker id -> (job, first candidate, candidates, extra): from the caller's tile map, else uniform tiles
@@ -1082,7 +1132,7 @@ k_project(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, int 
           uint32_t* __restrict__ proj_bits, int32_t* __restrict__ proj_popc, int32_t* __restrict__ proj_bbox,
           bool rows_only) {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int ctl[4];
+    __shared__ int ctl[2];
     int jid, c0, want;
     bool extra;
     decode_work<kFilter>(blockIdx.x, tile_map, tile_cand, tiles_per_job, jid, c0, want, extra);
@@ -1111,7 +1161,7 @@ k_project_p(const Cam cam, const a3d_job_t* __restrict__ jobs, int tile_cand, in
             const int4* __restrict__ tile_map, uint32_t* __restrict__ proj_bits, int32_t* __restrict__ proj_popc,
             int32_t* __restrict__ proj_bbox, bool rows_only) {
     extern __shared__ __align__(16) uint32_t smem[];
-    __shared__ int ctl[2][4];
+    __shared__ int ctl[2][2];
     __shared__ int next_work[2];
     const int g = threadIdx.x / kGroupThreads, tid = threadIdx.x - g * kGroupThreads;
     const int words = cam.H * cam.pitch;
