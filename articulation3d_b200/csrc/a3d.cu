@@ -2181,6 +2181,21 @@ static int score_impl(int H, int W, const a3d_job_t* jobs, int n_jobs, int max_t
                       int32_t* best_cand, int32_t* best_inter, int32_t* best_union, float* best_iou,
                       void* stream, bool zero_keys, bool pdl);
 
+// a3d_fetch_host_block: grid-stride copy of 16-byte pieces, four independent loads in flight per thread (the
+// source is host memory: every load is a PCIe round trip)
+__global__ void __launch_bounds__(256) k_fetch_block(uint4* __restrict__ dst, const uint4* __restrict__ src, int64_t n16) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < n16) v[u] = src[i + u * stride];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i + u * stride < n16) dst[i + u * stride] = v[u];
+    }
+}
+
 extern "C" {
 
 int a3d_version(void) { return A3D_VERSION; }
@@ -2307,6 +2322,27 @@ int a3d_project_max_tile(int H, int W) {
     return tile;
 }
 
+// Pinned host block -> device block by SM loads over PCIe (see include/a3d.h): the pass descriptors of a
+// pipeline must not queue on the H2D copy engine behind a gigabyte of mask uploads.
+int a3d_fetch_host_block(void* dst_dev, const void* src_host_pinned, int64_t nbytes, void* stream) {
+    if (nbytes < 0) return fail(A3D_EINVAL, "a3d_fetch_host_block: nbytes < 0");
+    if (nbytes == 0) return A3D_OK;
+    if (!dst_dev || !src_host_pinned) return fail(A3D_EINVAL, "a3d_fetch_host_block: null pointer");
+    if (((uintptr_t)dst_dev | (uintptr_t)src_host_pinned) & 15) return fail(A3D_EINVAL, "a3d_fetch_host_block: blocks must be 16-byte aligned");
+    void* src_dev = nullptr;
+    if (cudaHostGetDevicePointer(&src_dev, const_cast<void*>(src_host_pinned), 0) != cudaSuccess || !src_dev) {
+        cudaGetLastError();
+        return fail(A3D_EINVAL, "a3d_fetch_host_block: the source is not pinned (device-mapped) host memory");
+    }
+    const int64_t n16 = (nbytes + 15) / 16;
+    const int64_t want = (n16 + 4 * 256 - 1) / (4 * 256);
+    const int cap = device_sm_count();
+    k_fetch_block<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<uint4*>(dst_dev), reinterpret_cast<const uint4*>(src_dev), n16);
+    A3D_CUDA_TRY(cudaGetLastError());
+    return A3D_OK;
+}
+
 int a3d_pack_masks(const void* src, int dtype, int64_t n, int H, int W, float thresh,
                    uint32_t* bits_gt, uint32_t* bits_nz, void* stream) {
     if (n < 0 || H <= 0 || W <= 0) return fail(A3D_EINVAL, "a3d_pack_masks: bad shape");
@@ -2342,6 +2378,57 @@ int a3d_pack_masks(const void* src, int dtype, int64_t n, int H, int W, float th
     }
     A3D_CUDA_TRY(cudaGetLastError());
     return A3D_OK;
+}
+
+// The whole upload of a clip's dense masks in one call (see include/a3d.h): frame copies into a device
+// staging block with a bounded number in flight, a pack launch whenever the block is full.  Called from a
+// helper thread through ctypes, i.e. WITHOUT the interpreter lock: driven from Python, every one of the
+// ~120 frame copies per clip needed the lock back after waiting for its predecessor, and lost the copy
+// engine's slack whenever another thread held it.
+int a3d_upload_masks(const void* const* chunks, const int64_t* chunk_masks, int n_chunks, int dtype, int H, int W,
+                     float thresh, void* stage_dev, int64_t stage_cap_masks, uint32_t* bits_gt, uint32_t* bits_nz,
+                     int depth, void* stream) {
+    if (n_chunks < 0 || H <= 0 || W <= 0 || stage_cap_masks <= 0) return fail(A3D_EINVAL, "a3d_upload_masks: bad shape");
+    if (n_chunks == 0) return A3D_OK;
+    if (!chunks || !chunk_masks || !stage_dev || !bits_gt) return fail(A3D_EINVAL, "a3d_upload_masks: null pointer");
+    if (dtype != A3D_F32 && dtype != A3D_U8) return fail(A3D_EINVAL, "a3d_upload_masks: unknown dtype %d", dtype);
+    const size_t per_mask = (size_t)H * W * (dtype == A3D_F32 ? 4 : 1);
+    const size_t words = (size_t)H * pitch_words(W);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (depth > 64) depth = 64;
+    cudaEvent_t ev[64];
+    for (int i = 0; i < depth; ++i)
+        if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            for (int j = 0; j < i; ++j) cudaEventDestroy(ev[j]);
+            return fail(A3D_ECUDA, "a3d_upload_masks: cudaEventCreate: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    int rc = A3D_OK;
+    cudaError_t ce = cudaSuccess;
+    int64_t fill = 0, done = 0;                       // masks in the staging block / masks packed so far
+    auto flush = [&]() {
+        if (fill == 0 || rc != A3D_OK) return;
+        rc = a3d_pack_masks(stage_dev, dtype, fill, H, W, thresh, bits_gt + (size_t)done * words,
+                            bits_nz ? bits_nz + (size_t)done * words : nullptr, stream);
+        done += fill;
+        fill = 0;
+    };
+    for (int i = 0; i < n_chunks && rc == A3D_OK; ++i) {
+        const int64_t k = chunk_masks[i];
+        if (k < 0 || k > stage_cap_masks || (k > 0 && !chunks[i])) { rc = fail(A3D_EINVAL, "a3d_upload_masks: chunk %d: bad size or pointer", i); break; }
+        if (k == 0) continue;
+        if (fill + k > stage_cap_masks) flush();      // (the copies that follow are ordered after the pack by the stream)
+        if (rc != A3D_OK) break;
+        if (depth > 0 && i >= depth && (ce = cudaEventSynchronize(ev[i % depth])) != cudaSuccess) break;
+        ce = cudaMemcpyAsync((char*)stage_dev + (size_t)fill * per_mask, chunks[i], (size_t)k * per_mask,
+                             cudaMemcpyHostToDevice, s);
+        if (ce != cudaSuccess) break;
+        if (depth > 0 && (ce = cudaEventRecord(ev[i % depth], s)) != cudaSuccess) break;
+        fill += k;
+    }
+    if (ce == cudaSuccess) flush();
+    for (int i = 0; i < depth; ++i) cudaEventDestroy(ev[i]);
+    if (ce != cudaSuccess) return fail(A3D_ECUDA, "a3d_upload_masks: %s", cudaGetErrorString(ce));
+    return rc;
 }
 
 int a3d_mask_meta(const uint32_t* bits, int64_t n, int H, int W, int32_t* popc, int32_t* bbox,

@@ -79,8 +79,9 @@ def optimize_videos_sharded(videos, seeds, cfg=None, device=None, optimize_fn=No
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     mine = list(shard_range(len(videos), rank, world))
-    outs = optimize_fn([videos[i] for i in mine], [seeds[i] for i in mine], cfg=cfg, device=device) if mine else []
-    fr, tr = pack_records(mine, [videos[i][1] for i in mine])
+    local = [videos[i] for i in mine]          # entries (preds, None) are tracked by optimize_videos, in place
+    outs = optimize_fn(local, [seeds[i] for i in mine], cfg=cfg, device=device) if mine else []
+    fr, tr = pack_records(mine, [pl for _, pl in local])
     if device is not None and dist.is_initialized() and dist.get_backend(group) == "nccl":
         fr, tr = fr.to(device), tr.to(device)
     return outs, mine, all_gather_rows(fr, group), all_gather_rows(tr, group)

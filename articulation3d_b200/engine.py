@@ -407,7 +407,7 @@ class DeviceBatch:
         oj, ox = 0, (nj + 15) & ~15
         ot = (ox + nx + 15) & ~15
         om = (ot + nt + 15) & ~15
-        total = max(om + nm, 16)
+        total = (max(om + nm, 16) + 15) & ~15
         host = staging.host(total) if staging is not None else torch.empty(total, dtype=torch.uint8).pin_memory()
         hv = host.numpy()
         hv[oj:oj + nj] = batch.jobs.view(np.uint8).reshape(-1)
@@ -415,7 +415,15 @@ class DeviceBatch:
         hv[ot:ot + nt] = batch.tgt_index.view(np.uint8).reshape(-1)
         hv[om:om + nm] = tmap.view(np.uint8).reshape(-1)
         dev = staging.device_block(total) if staging is not None else torch.empty(total, dtype=torch.uint8, device=device)
-        dev[:total].copy_(host[:total], non_blocking=True)
+        if staging is not None and os.environ.get("A3D_DESC_COPY") != "dma":
+            # by a kernel that reads the pinned block over PCIe: a DMA copy would queue on the host-to-device
+            # copy engine behind the mask uploads of the next video (and its submission blocks while that
+            # engine's queue is full: 14 ms per video, measured with tools/e2e_timeline.py)
+            with torch.cuda.device(dev.device):
+                _lib.check(_lib.load().a3d_fetch_host_block(dev.data_ptr(), host.data_ptr(), total, _stream_ptr()),
+                           "a3d_fetch_host_block")
+        else:
+            dev[:total].copy_(host[:total], non_blocking=True)
         if staging is not None:
             staging.host_done()
         self.jobs = dev[oj:oj + nj]

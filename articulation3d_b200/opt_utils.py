@@ -526,6 +526,7 @@ def _write_back(preds, planes, cfg: OptConfig, kind: str):
 # device session: mask pool + job driver
 # ---------------------------------------------------------------------------
 _UPLOAD_CHUNK_BYTES = 1 << 29      # dense masks staged on the device per pack call
+_UPLOAD_DEPTH = 8                  # host -> device frame copies in flight (0 = no limit)
 _PROJ_BUDGET_BYTES = 6 << 30       # projected-mask workspace of one device pass
 _uploader = None                   # ONE helper thread: uploads of successive sessions queue up instead of sharing PCIe
 _upload_streams: dict = {}         # device -> the stream all uploads of that device run on
@@ -581,10 +582,22 @@ class _Session:
                 boxes = sorted(need[f])
                 if _has(preds[f], 'pred_masks'):
                     m = preds[f].pred_masks
-                    sel = m if len(boxes) == m.shape[0] else m[boxes]
-                    if tuple(sel.shape[1:]) != (cfg.height, cfg.width):
-                        raise ValueError(f"mask shape {tuple(sel.shape[1:])} != camera {cfg.height}x{cfg.width}")
-                    chunks.append(sel)
+                    if tuple(m.shape[1:]) != (cfg.height, cfg.width):
+                        raise ValueError(f"mask shape {tuple(m.shape[1:])} != camera {cfg.height}x{cfg.width}")
+                    if len(boxes) == m.shape[0]:
+                        chunks.append(m)
+                    else:
+                        # a frame with untracked boxes: runs of consecutive box ids as VIEWS of the frame's
+                        # tensor.  (`m[boxes]` gathers into a fresh pageable tensor: a host copy per such frame
+                        # plus a staged, synchronous transfer at a fifth of the pinned rate — 5-10 % of the
+                        # frames of the synthetic clips, 10 of the 31 ms of a clip's upload.)
+                        a = prev = boxes[0]
+                        for b in boxes[1:]:
+                            if b != prev + 1:
+                                chunks.append(m[a:prev + 1])
+                                a = b
+                            prev = b
+                        chunks.append(m[a:prev + 1])
                 else:                        # run-length masks, decoded on the device
                     rles.extend(preds[f].pred_rle[b] for b in boxes)
                 for b in boxes:
@@ -633,6 +646,7 @@ class _Session:
             # the next session's copies must not start before this one's are through (same stream: they do not),
             # and this thread returns only when they are, so that `pool` never waits on a half-filled stream
             self._upload_done.synchronize()
+            self._upload_keep = None
 
     def _upload(self, chunks, n) -> engine.MaskPool:
         """Dense per-frame masks -> packed pool.  The frames are copied (asynchronously when the host
@@ -652,7 +666,35 @@ class _Session:
         builder = engine.PoolBuilder(n, H, W, self.device, with_nonzero=(dt == torch.float32),
                                      thresh=cfg.mask_thresh)
         stage = torch.empty(cap, H, W, dtype=dt, device=self.device)
+        depth = int(os.environ.get("A3D_UPLOAD_DEPTH") or _UPLOAD_DEPTH)
+        if all(not c.is_cuda for c in chunks) and os.environ.get("A3D_UPLOAD") != "python":
+            # host masks: the whole loop below as ONE library call, outside the interpreter lock
+            # (a3d_upload_masks, include/a3d.h)
+            import ctypes as C
+            cs = []
+            for c in chunks:
+                if c.dtype == torch.bool:
+                    c = c.view(torch.uint8) if c.is_contiguous() else c.to(torch.uint8)
+                if c.dtype != dt:
+                    c = c.to(dt)
+                cs.append(c.contiguous())
+            self._upload_keep = cs                     # converted copies must outlive their transfers
+            ptrs = (C.c_void_p * len(cs))(*[c.data_ptr() for c in cs])
+            counts = (C.c_int64 * len(cs))(*[int(c.shape[0]) for c in cs])
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.load().a3d_upload_masks(
+                    ptrs, counts, len(cs), _lib.A3D_F32 if dt == torch.float32 else _lib.A3D_U8, H, W,
+                    float(cfg.mask_thresh), stage.data_ptr(), cap, builder.bits.data_ptr(),
+                    builder.nz.data_ptr() if builder.nz is not None else None, depth,
+                    torch.cuda.current_stream().cuda_stream), "a3d_upload_masks")
+            builder.fill = n
+            return builder.finish()
         fill = 0
+        # At most `depth` frame copies are in flight.  Submitted all at once (120 copies, 1.2 GB per clip) they
+        # fill the copy engine's queue, the submitting call then blocks INSIDE the driver, and every other
+        # thread's next CUDA call — the launch of the previous video's table pass — waits for it: 14 ms per
+        # video (tools/e2e_timeline.py).
+        inflight = []
         for c in chunks:
             if c.dtype == torch.bool:
                 c = c.view(torch.uint8) if c.is_contiguous() else c.to(torch.uint8)
@@ -664,6 +706,12 @@ class _Session:
                 fill = 0
             stage[fill:fill + k].copy_(c, non_blocking=True)
             fill += k
+            if depth > 0 and not c.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+                inflight.append(ev)
+                if len(inflight) > depth:
+                    inflight.pop(0).synchronize()
         if fill:
             builder.append(stage[:fill])
         return builder.finish()
@@ -743,7 +791,10 @@ class _Session:
                                             np.full(hi - lo, A), tgt_index[t_begin[lo]:t_begin[hi]],
                                             n_tgt[lo:hi], src_points)
             res = self._pass(batch, None, stats)
-            host[:, t_begin[lo]:t_begin[hi]].copy_(res.block, non_blocking=True)
+            # row by row: a column slice of the (4, n) block is strided, and a strided device -> host copy is
+            # staged through a temporary and WAITED for (the host then sat out the whole table pass here)
+            for r in range(4):
+                host[r, t_begin[lo]:t_begin[hi]].copy_(res.block[r], non_blocking=True)
         if not wait:
             done = torch.cuda.Event()
             done.record()
@@ -1079,9 +1130,22 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
     stats = stats if stats is not None else Stats()
     device = _default_device(device)
     outs = [[None] for _ in videos]
-    per_video = [[(v, pl['trans'], True), (v, pl['rot'], False)] for v, (p, pl) in enumerate(videos)]
     dense = all(_has(f, 'pred_masks') for p, _ in videos for f in p[:1])
-    if videos and dense and all(_use_tables(l, cfg) for l in per_video):
+    # ``(preds, None)``: the video is tracked here (``track_planes``) — in the pipelined schedule below when its
+    # turn to be uploaded comes, i.e. behind the transfers of the videos before it instead of in front of all
+    # of them; ``videos[i]`` is replaced by ``(preds, planes)``
+    lazy = [pl is None for _, pl in videos]
+    mode = os.environ.get("A3D_SCHEDULE") or cfg.schedule
+    if not (videos and dense and any(lazy) and mode in ("table", "auto") and isinstance(videos, list)):
+        for v, (p, pl) in enumerate(videos):
+            if pl is None:
+                videos[v] = (p, track_planes(p, cfg))
+        lazy = [False] * len(videos)
+
+    def tables_for(v):
+        p, pl = videos[v]
+        return _use_tables([(v, pl['trans'], True), (v, pl['rot'], False)], cfg)
+    if videos and dense and all(lazy[v] or tables_for(v) for v in range(len(videos))):
         # all-sources schedule, one session per video, software-pipelined: while video v is optimised
         # (table pass, host replay, final pass, write-back), the helper thread of session v+1 uploads and
         # packs the next video's masks on its own stream
@@ -1098,6 +1162,9 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
                 while next_open[0] <= min(last, len(videos) - 1):
                     v = next_open[0]
                     p, pl = videos[v]
+                    if pl is None:
+                        pl = track_planes(p, cfg)
+                        videos[v] = (p, pl)
                     ws, staging = wss[v % n_workers]
                     sess = _Session([(p, [pl['trans'], pl['rot']])], cfg, device, ws=ws, staging=staging)
                     lists = [(0, planes, tr) for planes, tr in ((pl['trans'], True), (pl['rot'], False)) if planes]

@@ -564,6 +564,11 @@ def _e2e(wl, dev, rank, world, dist, steps, videos_per_rank):
     seeds = [2020 + v for v in range(n_videos)]
     saved = {v: [(p.pred_tran_axis.clone(), p.pred_rot_axis.clone(), p.pred_planes.clone()) for p in clips[v]]
              for v in mine}
+    # the clips are ~10^5 long-lived Python objects: keep the cyclic collector's full passes (tens of ms, at
+    # allocation-count-dependent moments) off them, as a long-running host process would
+    import gc
+    gc.collect()
+    gc.freeze()
 
     def restore():          # optimize_planes rebinds / mutates the axis fields of its inputs
         for v in mine:
@@ -577,8 +582,9 @@ def _e2e(wl, dev, rank, world, dist, steps, videos_per_rank):
             return opt_utils.optimize_videos(videos, sds, cfg=cfg, device=device, stats=stats)
         t0 = time.perf_counter()
         # remote videos are never touched by this rank: placeholders keep the global numbering
-        vids = [(clips[v], opt_utils.track_planes(clips[v], cfg)) if v in clips else (None, None)
-                for v in range(n_videos)]
+        # (preds, None): optimize_videos runs track_planes itself, video by video inside its upload pipeline
+        vids = [(clips[v], None) for v in range(n_videos)] if world == 1 else \
+               [(clips[v], None) if v in clips else (None, None) for v in range(n_videos)]
         outs, ids, fr, tr = a3d_dist.optimize_videos_sharded(vids, seeds, cfg=cfg, device=dev, optimize_fn=fn)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -617,7 +623,7 @@ def _e2e(wl, dev, rank, world, dist, steps, videos_per_rank):
            "d2h_bytes_per_step": d2h // steps, "ms_per_step": 1e3 * secs / steps, "ms_each_step": each,
            "api": f"dist.optimize_videos_sharded -> optimize_videos('3dc') on {n_videos} video(s) of the {wl.name} "
                   f"clip shape ({wl.tracks} tracks x {wl.frames} frames, {videos_per_rank} per GPU), fp32 host masks "
-                  f"(pinned); timed: track_planes, H2D, packing, all device passes, D2H, write-back, record gather; "
+                  f"(pinned); timed: track_planes (inside the batch call, pipelined with the uploads), H2D, packing, all device passes, D2H, write-back, record gather; "
                   f"units = visited (frame, candidate) pairs as the reference counts them",
            "videos": n_videos, "schedule": sched, "device_passes_per_step_rank0": passes // steps,
            "gathered_records": {"track_frames": n_frame_rec, "tracks": n_track_rec}}

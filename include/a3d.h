@@ -116,6 +116,29 @@ int a3d_plan_tiles(const a3d_job_t* jobs_host, int n_jobs, int tile_max, int sm_
  *   xform_out  HOST [n][12] fp32 (entries 9..11 untouched)                                          */
 int a3d_host_quat_to_xform(const double* q, const double* two_s, int64_t n, float* xform_out);
 
+/* Dense HOST masks of a clip -> packed bits, as one call: what `a3d_pack_masks` does for device-resident masks,
+ * with the host-to-device copies in front.  chunks[i] points at chunk_masks[i] contiguous H x W masks of `dtype`
+ * in host memory (pinned for asynchronous copies); they are copied one after the other into the device staging
+ * block stage_dev (room for stage_cap_masks masks; every chunk must fit), which is packed into the next slots of
+ * bits_gt / bits_nz (as a3d_pack_masks) whenever the next chunk does not fit and at the end.  At most `depth`
+ * chunk copies are in flight (0 = no limit): submitted all at once, a gigabyte of copies fills the copy
+ * engine's queue and the submitting call blocks inside the driver, holding up every other thread's CUDA calls.
+ * Everything is enqueued on `stream`; the call returns when the last copy is SUBMITTED (not done).
+ * Replaces the `.cuda()` of the per-frame `pred_masks` (reference utils/opt_utils.py:409, 471-473).            */
+int a3d_upload_masks(const void* const* chunks, const int64_t* chunk_masks, int n_chunks, int dtype, int H, int W,
+                     float thresh, void* stage_dev, int64_t stage_cap_masks, uint32_t* bits_gt, uint32_t* bits_nz,
+                     int depth, void* stream);
+
+/* Copies a block of PINNED host memory (cudaHostAlloc / cudaHostRegister: e.g. torch's pin_memory) into device
+ * memory with a kernel that reads the host block over PCIe, instead of a cudaMemcpyAsync.  For the per-pass
+ * descriptor block (jobs | candidate transforms | target indices, a3d_job_t above) of a caller that uploads
+ * masks on another stream at the same time: a DMA copy of the descriptors queues on the host-to-device copy
+ * engine behind every mask copy already submitted (measured: the submitting thread blocks for 14 ms per video,
+ * the pass starts a whole upload late); the kernel is ordered by `stream` alone.  Both blocks 16-byte aligned;
+ * the tail up to the next multiple of 16 bytes is copied too (size the blocks accordingly).
+ * No reference counterpart (the reference keeps everything in torch tensors).                       */
+int a3d_fetch_host_block(void* dst_dev, const void* src_host_pinned, int64_t nbytes, void* stream);
+
 /* (a7/a8 input stage) threshold + bit-pack.  Replaces the per-visit
  * `(pred_mask > 0.5)` of opt_utils.py:471-473 and `pred_mask.nonzero()` of :409.
  *   src      [n][H][W] of dtype (A3D_F32 | A3D_U8), contiguous

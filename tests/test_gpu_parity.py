@@ -357,6 +357,45 @@ def test_optimize_videos_equals_per_video_calls(schedule):
             assert torch.equal(x.pred_tran_axis, y.pred_tran_axis)
 
 
+@pytest.mark.parametrize("variant", ["lazy_tracking", "python_upload", "dma_descriptors", "uint8_masks"])
+def test_optimize_videos_host_paths_agree(variant, monkeypatch):
+    """The batch API's host-side variants — videos tracked inside the pipeline (``(preds, None)``), the upload
+    loop in Python instead of a3d_upload_masks, the pass descriptors by DMA instead of a3d_fetch_host_block,
+    uint8 masks — give the records of the default path."""
+    seeds = [11, 12, 13, 14]
+    clips = [synth.make_video(300 + s, 3, 14, kinds=[0, 1, 0])[0] for s in seeds]
+
+    def run(lazy, as_u8=False):
+        vids = []
+        for c in clips:
+            p = synth.clone_preds(c)
+            for q in p:
+                m = q.pred_masks.cpu()
+                q.pred_masks = ((m > 0.5).to(torch.uint8) if as_u8 else m).pin_memory()
+            vids.append((p, None if lazy else opt_utils.track_planes(p)))
+        outs = opt_utils.optimize_videos(vids, seeds, device=DEV)
+        return outs, [pl for _, pl in vids]
+
+    base_o, base_pl = run(False)
+    if variant == "python_upload":
+        monkeypatch.setenv("A3D_UPLOAD", "python")
+    elif variant == "dma_descriptors":
+        monkeypatch.setenv("A3D_DESC_COPY", "dma")
+    o, pl = run(variant == "lazy_tracking", as_u8=(variant == "uint8_masks"))
+    for pa, pb in zip(base_pl, pl):
+        for cat in ("trans", "rot"):
+            assert len(pa[cat]) == len(pb[cat])
+            for a, b in zip(pa[cat], pb[cat]):
+                assert a['ids'] == b['ids'] and a['has_rot'] == b['has_rot']
+                if a['has_rot']:
+                    for k in ("angle_id", "inter", "union"):
+                        assert np.array_equal(a['fit'][k], b['fit'][k])
+    for oa, ob in zip(base_o, o):
+        for x, y in zip(oa, ob):
+            assert np.array_equal(np.asarray(x.scores), np.asarray(y.scores))
+            assert torch.equal(x.pred_rot_axis, y.pred_rot_axis) and torch.equal(x.pred_tran_axis, y.pred_tran_axis)
+
+
 def _table_properties(res, batch, pool):
     """Size-independent invariants of one pass (used where the oracle is too slow)."""
     popc = pool.popc.cpu().numpy()
