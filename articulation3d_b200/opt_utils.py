@@ -1123,7 +1123,8 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
     ``(preds, planes)``; video i draws its source frames from
     ``random.Random(seeds[i])`` (the reference seeds one process per video,
     tools/inference.py:172), so the result of every video equals
-    ``random.seed(seeds[i]); optimize_planes(preds, planes, '3dc')``.  All videos share one
+    ``random.seed(seeds[i]); optimize_planes(preds, planes, '3dc')``.  ``planes`` may be None: the video is
+    then tracked here (``track_planes``) and ``videos[i]`` becomes ``(preds, planes)``.  All videos share one
     device session; their cluster phases are answered from one all-sources pass (few videos) or
     advance in lock-step, one job per video per device pass (many videos)."""
     cfg = cfg or OptConfig()
@@ -1134,9 +1135,11 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
     # ``(preds, None)``: the video is tracked here (``track_planes``) — in the pipelined schedule below when its
     # turn to be uploaded comes, i.e. behind the transfers of the videos before it instead of in front of all
     # of them; ``videos[i]`` is replaced by ``(preds, planes)``
+    if not isinstance(videos, list):
+        videos = list(videos)
     lazy = [pl is None for _, pl in videos]
     mode = os.environ.get("A3D_SCHEDULE") or cfg.schedule
-    if not (videos and dense and any(lazy) and mode in ("table", "auto") and isinstance(videos, list)):
+    if not (videos and dense and any(lazy) and mode in ("table", "auto")):
         for v, (p, pl) in enumerate(videos):
             if pl is None:
                 videos[v] = (p, track_planes(p, cfg))
