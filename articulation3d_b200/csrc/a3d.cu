@@ -11,6 +11,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <time.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -2418,7 +2419,17 @@ int a3d_upload_masks(const void* const* chunks, const int64_t* chunk_masks, int 
         if (k == 0) continue;
         if (fill + k > stage_cap_masks) flush();      // (the copies that follow are ordered after the pack by the stream)
         if (rc != A3D_OK) break;
-        if (depth > 0 && i >= depth && (ce = cudaEventSynchronize(ev[i % depth])) != cudaSuccess) break;
+        if (depth > 0 && i >= depth) {
+            // polled with short sleeps: cudaEventSynchronize either spins on a core for the whole upload (eight
+            // ranks of a node share its cores with their hosts' work) or, as a blocking-sync event, wakes up
+            // late enough to drain the copies in flight (measured: 181 against 165 ms per 6 clips)
+            while ((ce = cudaEventQuery(ev[i % depth])) == cudaErrorNotReady) {
+                struct timespec ts = {0, 20000};
+                nanosleep(&ts, nullptr);
+                cudaGetLastError();                   // (not-ready is recorded as the thread's last error)
+            }
+            if (ce != cudaSuccess) break;
+        }
         ce = cudaMemcpyAsync((char*)stage_dev + (size_t)fill * per_mask, chunks[i], (size_t)k * per_mask,
                              cudaMemcpyHostToDevice, s);
         if (ce != cudaSuccess) break;

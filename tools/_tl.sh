@@ -1,6 +1,9 @@
 cd "${GRAFT_REPO_ROOT:-.}"
-python tools/upload_probe.py 2>&1 | sed -n 2,2p
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tools.py tests/test_gpu_adapter.py -x -q -m gpu -k "optimize or tools or videos or adapter" 2>&1 | tail -3
-TL_FINE=1 python tools/e2e_timeline.py c3 6 > gpurun_out/r2_e2e_timeline6.txt 2>&1
-head -3 gpurun_out/r2_e2e_timeline6.txt
-TL_QUIET=1 python tools/e2e_timeline.py c3 6 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_adapter.py -x -q -m gpu -k "upload or fetch" 2>&1 | tail -2
+timeout 400 python bench.py --no-extras --no-cpu-baseline --steps 5 > gpurun_out/bench_quick.txt 2> gpurun_out/bench_quick.err; echo "quick rc=$?"
+python - <<'PY'
+import json
+for f in ("bench_quick",):
+    d = json.loads([l for l in open(f"gpurun_out/{f}.txt").read().splitlines() if l.startswith("{")][-1])
+    print(f, d["value"], d["ms_per_step"], "e2e", {k: d["e2e"][k] for k in ("value", "ms_per_step", "ms_each_step", "videos")})
+PY
