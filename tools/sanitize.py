@@ -39,6 +39,16 @@ for sched in ("table", "chain"):
     opt_utils.optimize_videos(vids, [1, 2, 3], cfg=cfg, device="cuda:0")
     print("optimize_videos", sched, [pl.get('has_rot') for _, planes in vids for cat in planes for pl in planes[cat]])
 os.environ.pop("A3D_SCHEDULE")
+# pinned host masks, videos tracked inside the pipeline (a3d_upload_masks with asynchronous copies, frames with
+# untracked boxes as views, a3d_fetch_host_block for the descriptors)
+vids = []
+for v in range(3):
+    pv, _ = synth.make_video(30 + v, 3, 12, cfg, kinds=[0, 1, 0])
+    for q in pv:
+        q.pred_masks = q.pred_masks.pin_memory()
+    vids.append((pv, None))
+opt_utils.optimize_videos(vids, [4, 5, 6], cfg=cfg, device="cuda:0")
+print("optimize_videos lazy/pinned", [pl.get('has_rot') for _, planes in vids for cat in planes for pl in planes[cat]])
 H, W = 150, 200
 rles = [rle.encode(m.numpy() > 0.5) for m in preds[3].pred_masks]
 pool = engine.rle_to_pool(rles, H, W, "cuda:0")
