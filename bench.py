@@ -407,10 +407,14 @@ def gpu_arm(args, wl):
                          "(use --impl reference for the CPU oracle port)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # torchrun exports OMP_NUM_THREADS=1 for every rank; the host side of the public API (float64 candidate
-        # transforms, packing bookkeeping) is torch CPU work, so each rank takes its share of the box's cores
-        torch.set_num_threads(max(1, (os.cpu_count() or world) // world))
+    # Intra-op threads of the host side (small float64 array work of the public API).  torchrun's OMP_NUM_THREADS=1
+    # per rank is kept: with cores // world threads per rank (round 2's first choice) the idle OpenMP workers of
+    # the ranks spin on every core of the box and starve the upload / preparation / NCCL threads — 612 ms per e2e
+    # step at N = 2 against 167 ms with one thread (gpurun_out/bench_n2_t1.txt); at N = 1 one, two, four and sixteen
+    # threads measure the same (the step is bound by the H2D copy), four is taken.
+    torch.set_num_threads(1 if world > 1 else min(4, os.cpu_count() or 1))
+    if os.environ.get("A3D_BENCH_THREADS"):              # experiment switch: intra-op threads of the host side
+        torch.set_num_threads(int(os.environ["A3D_BENCH_THREADS"]))
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -590,14 +594,18 @@ def _e2e(wl, dev, rank, world, dist, steps, videos_per_rank):
         dt = time.perf_counter() - t0
         return dt, stats, fr, tr
 
+    per_rank = []
+
     def synced_run():
         if dist:
             dist.barrier()
         dt, st, fr, tr = run()
         if dist:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            t = torch.zeros(world, device=dev, dtype=torch.float64)
+            t[rank] = dt
+            dist.all_reduce(t)
+            per_rank.append([round(1e3 * float(x), 1) for x in t.tolist()])
+            dt = float(t.max().item())
         return dt, st, fr, tr
 
     synced_run()
@@ -627,6 +635,8 @@ def _e2e(wl, dev, rank, world, dist, steps, videos_per_rank):
                   f"units = visited (frame, candidate) pairs as the reference counts them",
            "videos": n_videos, "schedule": sched, "device_passes_per_step_rank0": passes // steps,
            "gathered_records": {"track_frames": n_frame_rec, "tracks": n_track_rec}}
+    if per_rank:
+        out["ms_each_step_per_rank"] = per_rank[1:]
     # SURVEY test tier T5 on the real thing: the records every rank received must equal what ONE GPU computes.
     # Videos are independent (each draws from its own seeded generator), so rank 0 re-runs, alone and untimed,
     # its own videos plus the first video of every other rank (rendered from its seed) and compares their rows.

@@ -1,11 +1,8 @@
 cd "${GRAFT_REPO_ROOT:-.}"
-free -g | head -2; grep -i -E "AnonHugePages|HugePages_Total|thp" /proc/meminfo | head; cat /sys/kernel/mm/transparent_hugepage/enabled
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "full_size or c_oracle_on_every or baseline" 2>&1 | tail -1
-free -g | head -2
-timeout 400 python bench.py --no-extras --no-cpu-baseline --steps 5 > gpurun_out/bench_quick.txt 2> gpurun_out/bench_quick.err; echo "quick rc=$?"
+A3D_BENCH_THREADS=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 --no-extras > gpurun_out/bench_n2_t1.txt 2> gpurun_out/bench_n2_t1.err; echo rc=$?
 python - <<'PY'
 import json
-d = json.loads([l for l in open("gpurun_out/bench_quick.txt").read().splitlines() if l.startswith("{")][-1])
-print("e2e", {k: d["e2e"][k] for k in ("value", "ms_per_step", "ms_each_step", "videos")})
+d = json.loads([l for l in open("gpurun_out/bench_n2_t1.txt").read().splitlines() if l.startswith("{")][-1])
+e = d["e2e"]; print("e2e", {k: e.get(k) for k in ("value", "ms_per_step", "ms_each_step", "ms_each_step_per_rank")})
 PY
-python tools/h2d_probe.py
+tail -3 gpurun_out/bench_n2_t1.err
