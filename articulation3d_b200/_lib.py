@@ -42,7 +42,7 @@ assert JOB_DTYPE.itemsize == 72, JOB_DTYPE.itemsize
 EXPORTS = (
     "a3d_version", "a3d_last_error_string", "a3d_pitch_words", "a3d_project_max_tile",
     "a3d_pack_masks", "a3d_mask_meta", "a3d_project", "a3d_score", "a3d_pass", "a3d_emit_masks",
-    "a3d_rle_to_bits", "a3d_plane_offsets", "a3d_plan_tiles", "a3d_host_quat_to_xform", "a3d_fetch_host_block", "a3d_upload_masks",
+    "a3d_rle_to_bits", "a3d_plane_offsets", "a3d_plan_tiles", "a3d_host_quat_to_xform", "a3d_fetch_host_block", "a3d_upload_masks", "a3d_host_rle_counts",
 )
 
 _lib = None
@@ -89,6 +89,8 @@ def load():
     lib.a3d_host_quat_to_xform.argtypes = [vp, vp, i64, vp]
     lib.a3d_fetch_host_block.restype = C.c_int
     lib.a3d_fetch_host_block.argtypes = [vp, vp, i64, vp]
+    lib.a3d_host_rle_counts.restype = C.c_int64
+    lib.a3d_host_rle_counts.argtypes = [vp, vp, i64, vp, i64, vp, vp]
     lib.a3d_upload_masks.restype = C.c_int
     lib.a3d_upload_masks.argtypes = [vp, vp, i32, i32, i32, i32, f32, vp, i64, vp, vp, i32, vp]
     lib.a3d_emit_masks.restype = C.c_int

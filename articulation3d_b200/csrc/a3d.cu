@@ -2246,6 +2246,51 @@ int a3d_host_quat_to_xform(const double* q, const double* two_s, int64_t n, floa
     return A3D_OK;
 }
 
+// COCO compressed RLE strings -> run lengths (see include/a3d.h; format restated in articulation3d_b200/rle.py).
+// The per-mask Python loop this replaces cost 40 us per simple mask — 39 ms per 960-mask clip, more than the
+// dense upload of the same clip.
+int64_t a3d_host_rle_counts(const uint8_t* chars, const int64_t* begin, int64_t n, uint32_t* counts_out, int64_t cap,
+                            int64_t* count_begin_out, int64_t* run_sum_out) {
+    if (n < 0 || (n > 0 && (!chars || !begin))) return fail(A3D_EINVAL, "a3d_host_rle_counts: bad argument");
+    int64_t total = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t p = begin[i];
+        const int64_t end = begin[i + 1];
+        if (p < 0 || end < p) return fail(A3D_EINVAL, "a3d_host_rle_counts: string %lld: bad offsets", (long long)i);
+        if (count_begin_out) count_begin_out[i] = total;
+        int64_t m = 0, sum = 0;
+        long long prev1 = 0, prev2 = 0;                 // counts m-1 and m-2 (before the cast to uint32)
+        while (p < end) {
+            unsigned long long x = 0;
+            int k = 0;
+            for (;;) {
+                if (p >= end || k > 12) return fail(A3D_EINVAL, "a3d_host_rle_counts: string %lld is truncated or malformed", (long long)i);
+                const unsigned c = (unsigned)chars[p++] - 48u;
+                x |= (unsigned long long)(c & 0x1Fu) << (5 * k);
+                ++k;
+                if (!(c & 0x20u)) {
+                    if (c & 0x10u) x |= ~0ULL << (5 * k);        // sign extension from bit 4 of the last group
+                    break;
+                }
+            }
+            long long v = (long long)x;
+            if (m > 2) v += prev2;                      // counts beyond the third are differences to the count two back
+            prev2 = prev1;
+            prev1 = v;
+            if (counts_out) {
+                if (total >= cap) return fail(A3D_EINVAL, "a3d_host_rle_counts: counts_out holds %lld, more are needed", (long long)cap);
+                counts_out[total] = (uint32_t)v;
+            }
+            sum += (int64_t)(uint32_t)v;
+            ++total;
+            ++m;
+        }
+        if (run_sum_out) run_sum_out[i] = sum;
+    }
+    if (count_begin_out) count_begin_out[n] = total;
+    return total;
+}
+
 int a3d_plan_tiles(const a3d_job_t* jobs_host, int n_jobs, int tile_max, int sm_count, int32_t* tile_map_out,
                    int cap_tiles, int* tile_cand_out) {
     const double kPlanFixed = 21500.0, kPlanPerCand = 3000.0;

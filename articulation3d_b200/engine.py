@@ -666,18 +666,25 @@ def rle_to_pool(rles, H: int, W: int, device) -> MaskPool:
     device = torch.device(device)
     if device.type != "cuda":
         raise _lib.A3DError("rle_to_pool needs a CUDA device (the hot path has no CPU fallback)")
-    runs = []
     for r in rles:
         if list(r["size"]) != [H, W]:
             raise ValueError(f"RLE size {r['size']} != {[H, W]}")
-        c = _rle.rle_counts(r)
-        if int(c.astype(np.int64).sum()) != H * W:
+    n = len(rles)
+    if n and all(isinstance(r["counts"], (bytes, str)) for r in rles):
+        # compressed strings (what the reference's records hold): all masks in one call of the host helper
+        flat, begin, sums = _rle.strings_to_counts([r["counts"] for r in rles])
+        if not np.all(sums == H * W):
             raise ValueError("RLE run lengths do not cover the mask")
-        runs.append(c)
-    n = len(runs)
-    begin = np.zeros(n + 1, dtype=np.int64)
-    begin[1:] = np.cumsum([len(c) for c in runs])
-    flat = np.concatenate(runs).astype(np.uint32) if n else np.zeros(0, np.uint32)
+    else:
+        runs = []
+        for r in rles:
+            c = _rle.rle_counts(r)
+            if int(c.astype(np.int64).sum()) != H * W:
+                raise ValueError("RLE run lengths do not cover the mask")
+            runs.append(c)
+        begin = np.zeros(n + 1, dtype=np.int64)
+        begin[1:] = np.cumsum([len(c) for c in runs])
+        flat = np.concatenate(runs).astype(np.uint32) if n else np.zeros(0, np.uint32)
     pitch = _lib.pitch_words(W)
     with torch.cuda.device(device):
         d_counts = torch.from_numpy(flat.view(np.int32)).to(device)

@@ -45,6 +45,29 @@ def string_to_counts(s) -> np.ndarray:
     return np.asarray(counts, dtype=np.int64).astype(np.uint32)
 
 
+def strings_to_counts(strings):
+    """Many compressed strings at once, decoded by the library's host helper (``a3d_host_rle_counts``: the
+    per-string Python loop above costs 40 us per simple mask).  Returns (flat uint32 counts, int64 begin[n+1],
+    int64 run sums[n])."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    bs = [x.encode("ascii") if isinstance(x, str) else bytes(x) for x in strings]
+    n = len(bs)
+    begin = np.zeros(n + 1, dtype=np.int64)
+    if n:
+        np.cumsum([len(b) for b in bs], out=begin[1:])
+    blob = b"".join(bs)
+    chars = np.frombuffer(blob, dtype=np.uint8) if blob else np.zeros(1, np.uint8)
+    cbeg = np.zeros(n + 1, dtype=np.int64)
+    sums = np.zeros(max(n, 1), dtype=np.int64)
+    # every count takes at least one character
+    counts = np.empty(max(len(blob), 1), dtype=np.uint32)
+    total = _lib.check(lib.a3d_host_rle_counts(chars.ctypes.data, begin.ctypes.data, n, counts.ctypes.data, len(counts),
+                                               cbeg.ctypes.data, sums.ctypes.data), "a3d_host_rle_counts")
+    return counts[:total], cbeg, sums[:n]
+
+
 def counts_to_string(counts) -> bytes:
     """Run lengths -> compressed COCO RLE string."""
     counts = [int(c) for c in counts]

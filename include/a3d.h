@@ -109,6 +109,17 @@ int a3d_project_max_tile(int H, int W);
 int a3d_plan_tiles(const a3d_job_t* jobs_host, int n_jobs, int tile_max, int sm_count,
                    int32_t* tile_map_out, int cap_tiles, int* tile_cand_out);
 
+/* HOST helper: run lengths of n COCO compressed RLE strings (the `counts` of the reference's prediction records,
+ * evaluation/arti_evaluation.py:153-180; decoded there with pycocotools' C extension, utils/arti_vis.py:135,182)
+ * — the input of a3d_rle_to_bits.
+ *   chars            HOST the n strings back to back;  begin  HOST [n+1] byte offsets into chars
+ *   counts_out       HOST uint32 [cap], or NULL to only count (first of two calls)
+ *   count_begin_out  HOST int64 [n+1] first count of every mask (may be NULL)
+ *   run_sum_out      HOST int64 [n] sum of the mask's runs — must equal H*W (may be NULL)
+ * Returns the total number of counts, or a negative A3D_E* code (truncated / malformed string, cap too small). */
+int64_t a3d_host_rle_counts(const uint8_t* chars, const int64_t* begin, int64_t n, uint32_t* counts_out, int64_t cap,
+                            int64_t* count_begin_out, int64_t* run_sum_out);
+
 /* HOST helper: the 3x3 rotation entries of n unit quaternions, as pytorch3d's quaternion_to_matrix evaluates
  * them in float64 (the reference's axis_angle_to_matrix, utils/opt_utils.py:428-431), rounded once to fp32
  * (what Rotate stores) into the first nine floats of each 12-float candidate row.

@@ -73,3 +73,34 @@ def test_ray_table_matches_reference_loop_on_a_subgrid():
     a = adapter.get_K_inv_dot_xy_1(48, 64)
     b = restated.get_K_inv_dot_xy_1(48, 64)
     assert np.array_equal(a, b)
+
+
+def test_native_string_decoder_equals_python_decoder():
+    """a3d_host_rle_counts (host helper of liba3d.so) against rle.string_to_counts on structured, dense-random and
+    degenerate masks, str and bytes inputs, an empty string; malformed strings are refused."""
+    from articulation3d_b200 import _lib
+    rng = np.random.RandomState(3)
+    H, W = 120, 160
+    masks = []
+    m = np.zeros((H, W), bool); masks.append(m.copy())
+    m[:] = True; masks.append(m.copy())
+    m[:] = False; m[20:90, 30:100] = True; masks.append(m.copy())
+    masks.append(rng.rand(H, W) < 0.5)
+    masks.append(rng.rand(H, W) < 0.01)
+    m = np.zeros((H, W), bool); m[0, 0] = m[-1, -1] = True; masks.append(m.copy())
+    m = np.zeros((H, W), bool); m[:, ::2] = True; masks.append(m.copy())          # equal long runs: zero differences
+    rls = [rle.encode(x) for x in masks]
+    strings = [r["counts"] if i % 2 else r["counts"].decode("ascii") for i, r in enumerate(rls)] + [b""]
+    flat, begin, sums = rle.strings_to_counts(strings)
+    assert flat.dtype == np.uint32 and begin[0] == 0 and begin[-1] == len(flat)
+    for i, r in enumerate(rls):
+        assert np.array_equal(flat[begin[i]:begin[i + 1]], rle.string_to_counts(r["counts"])), i
+        assert sums[i] == H * W
+    assert begin[-2] == begin[-1] and sums[-1] == 0
+    big = np.zeros((900, 1200), bool); big[7:880, 5:1190] = True                    # counts beyond 2^15 / 2^20
+    f, b, s = rle.strings_to_counts([rle.encode(big)["counts"]])
+    assert np.array_equal(f, rle.string_to_counts(rle.encode(big)["counts"])) and s[0] == 900 * 1200
+    f, b, s = rle.strings_to_counts([])
+    assert len(f) == 0 and list(b) == [0]
+    with pytest.raises(_lib.A3DError):
+        rle.strings_to_counts([b"0P"])                                              # continuation bit on the last character
