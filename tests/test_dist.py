@@ -59,25 +59,36 @@ def _make_videos(n):
     return vids
 
 
-def _worker(rank, world, port, n_videos, q):
+def _fake_optimize_lazy(videos, seeds, cfg=None, device=None):
+    """As ``optimize_videos`` does for entries ``(preds, None)``: the planes appear in place (here: the ones
+    _make_videos would have given the video whose seed this is)."""
+    for i, ((preds, planes), seed) in enumerate(zip(videos, seeds)):
+        if planes is None:
+            videos[i] = (preds, _make_videos(seed - 100 + 1)[seed - 100][1])
+    return _fake_optimize(videos, seeds, cfg=cfg, device=device)
+
+
+def _worker(rank, world, port, n_videos, q, lazy=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         vids = _make_videos(n_videos)
+        if lazy:                                 # untracked videos; remote ones are never touched
+            vids = [(p, None) for p, _ in vids]
         outs, mine, fr, tr = a3d_dist.optimize_videos_sharded(vids, list(range(100, 100 + n_videos)),
-                                                              optimize_fn=_fake_optimize)
+                                                              optimize_fn=_fake_optimize_lazy if lazy else _fake_optimize)
         q.put((rank, mine, fr.numpy(), tr.numpy()))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_videos", [5, 1])
-def test_sharded_gather_world2_gloo(n_videos):
+@pytest.mark.parametrize("n_videos,lazy", [(5, False), (1, False), (5, True)])
+def test_sharded_gather_world2_gloo(n_videos, lazy):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_videos, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_videos, q, lazy)) for r in range(world)]
     for p in procs:
         p.start()
     got = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
