@@ -39,6 +39,16 @@ def test_no_gpu_means_loud_failure():
         opt_utils.optimize_planes(preds, planes, '3dc')
     with pytest.raises(_lib.A3DError):
         engine.pack_masks(torch.zeros(1, 8, 8))
+    # the host-path entry points of the batch API fail with a status and a message, they do not crash or hang
+    import ctypes as C
+    lib = _lib.load()
+    buf = np.zeros(64, np.uint8)
+    assert lib.a3d_fetch_host_block(buf.ctypes.data, buf.ctypes.data, 64, None) < 0
+    assert lib.a3d_last_error_string()
+    ptrs, counts = (C.c_void_p * 1)(buf.ctypes.data), (C.c_int64 * 1)(1)
+    assert lib.a3d_upload_masks(ptrs, counts, 1, _lib.A3D_U8, 8, 8, 0.5, buf.ctypes.data, 1, buf.ctypes.data, None, 2, None) < 0
+    with pytest.raises(_lib.A3DError):
+        opt_utils.optimize_videos([(preds, None)], [1])
 
 
 def test_product_never_imports_oracle():
