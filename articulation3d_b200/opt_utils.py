@@ -1237,6 +1237,9 @@ def optimize_videos(videos, seeds, cfg=None, device=None, stats=None):
                     setattr(stats, f, getattr(stats, f) + getattr(ws_, f))
                 stats.schedule = ws_.schedule or stats.schedule
         return [o[0] for o in outs]
+    for v, (p, pl) in enumerate(videos):          # (untracked entries next to videos too big for the table schedule)
+        if pl is None:
+            videos[v] = (p, track_planes(p, cfg))
     session = _Session([(p, [pl['trans'], pl['rot']]) for p, pl in videos], cfg, device)
     stats.h2d_bytes += session.h2d_bytes
     _run_lists(session, [_video_stages(p, pl, cfg, _global_random.Random(s), o)
